@@ -1,0 +1,434 @@
+// mpi4jax_b200 -- collective entry points and the data-movement kernels.
+//
+// Data-movement collectives (allgather, alltoall, bcast, gather, scatter) share
+// ONE kernel: every rank stages the blocks its peers will need into its own
+// symmetric staging buffer, a block-paired barrier publishes them, then every
+// rank PULLS what it needs from the peers' staging straight into the final
+// layout of its (ordinary, non-symmetric) output tensor.  The "unpack" the
+// reference leaves to XLA concat/dynamic-update-slice ops after MPI_Allgather /
+// MPI_Alltoall / MPI_Gather / MPI_Scatter / MPI_Bcast
+// (mpi_ops_common.h:222-306; mpi_xla_bridge_cuda.cpp:99-148, 227-503) is fused
+// into the NVLink pull; there is no host sync and no host staging.
+//
+// Reduction collectives live in b2_reduce.cuh; this file adds the NVLS
+// (multimem) allreduce and the size-based algorithm selection.
+#include <cstdio>
+#include <cstring>
+
+#include "b2_reduce.cuh"
+#include "b2_runtime.h"
+
+b2_reduce_launch_fn b2_reduce_table[B2_DTYPE_COUNT][B2_OP_COUNT];
+b2_ll_launch_fn b2_ll_table[B2_DTYPE_COUNT][B2_OP_COUNT];
+void b2_register_reduce_group_0();
+void b2_register_reduce_group_1();
+void b2_register_reduce_group_2();
+void b2_register_reduce_group_3();
+
+extern "C" void b2_set_error(const char* fmt, ...);
+extern "C" void b2_count_launch(B2Comm* c);
+struct B2DebugScope;
+extern "C" B2DebugScope* b2_debug_begin(B2Comm* c, const char* opname, const char* details,
+                                         cudaStream_t stream);
+extern "C" void b2_debug_end(B2DebugScope* s, int code);
+
+static void b2_ensure_tables() {
+  static bool done = false;
+  if (done) return;
+  b2_register_reduce_group_0();
+  b2_register_reduce_group_1();
+  b2_register_reduce_group_2();
+  b2_register_reduce_group_3();
+  done = true;
+}
+
+// ---------------------------------------------------------------------------
+// barrier
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) b2_k_barrier(const B2DevComm c) {
+  unsigned e = b2_ld_volatile(c.epoch + blockIdx.x);
+  b2_barrier_all(c, ++e, B2_OPC_BARRIER);
+  if (threadIdx.x == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
+}
+
+// ---------------------------------------------------------------------------
+// stage -> barrier -> pull
+// ---------------------------------------------------------------------------
+struct B2MoveArgs {
+  const void* in;
+  void* out;
+  size_t blk_bytes;     // bytes of one per-rank block (chunks index into it)
+  size_t blk_stride;    // staging stride between blocks (blk_bytes rounded up to 16)
+  size_t chunk;
+  int nin;              // blocks staged by this rank (0, 1 or size)
+  int nsrc;             // blocks pulled by this rank
+  int src_rank[B2_MAX_RANKS];
+  int src_blk[B2_MAX_RANKS];
+  int dst_blk[B2_MAX_RANKS];
+  int opcode;
+};
+
+__global__ void __launch_bounds__(B2_THREADS)
+b2_k_move(const B2DevComm c, const B2MoveArgs a) {
+  const unsigned ticket = b2_ticket_read(c.ticket);
+  const size_t par = (size_t)(ticket & 1u) * c.stage_half;
+  unsigned e = b2_ld_volatile(c.epoch + blockIdx.x);
+  const char* in = (const char*)a.in;
+  char* out = (char*)a.out;
+  char* mine = c.stage[c.rank] + par;
+  const size_t nchunks = (a.blk_bytes + a.chunk - 1) / a.chunk;
+
+  for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const size_t off = ch * a.chunk;
+    const size_t len = (a.blk_bytes - off < a.chunk) ? (a.blk_bytes - off) : a.chunk;
+    for (int j = 0; j < a.nin; ++j)
+      b2_copy_bytes<false>(mine + (size_t)j * a.blk_stride + off,
+                           in + (size_t)j * a.blk_bytes + off, len);
+    b2_barrier_all(c, ++e, a.opcode);
+    for (int s = 0; s < a.nsrc; ++s) {
+      const int k = (s + c.rank) % a.nsrc;      // stagger peers across ranks
+      b2_copy_bytes<true>(out + (size_t)a.dst_blk[k] * a.blk_bytes + off,
+                          c.stage[a.src_rank[k]] + par + (size_t)a.src_blk[k] * a.blk_stride + off,
+                          len);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
+  b2_finish_bump(c.ticket, c.ticket + 1, 1u, gridDim.x);
+}
+
+// ---------------------------------------------------------------------------
+// NVLS allreduce (SUM; f32 / bf16 / f16 with fp32 accumulation in the switch)
+// ---------------------------------------------------------------------------
+template <int DT>
+__device__ __forceinline__ uint4 b2_mc_ld_reduce(const void* mc) {
+  uint4 v;
+  if (DT == B2_F32) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+  } else if (DT == B2_BF16) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+  } else {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+  }
+  return v;
+}
+__device__ __forceinline__ void b2_mc_st(void* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int DT>
+__global__ void __launch_bounds__(B2_THREADS)
+b2_k_allreduce_nvls(const B2DevComm c, const B2ReduceArgs a) {
+  const unsigned ticket = b2_ticket_read(c.ticket);
+  const size_t par = (size_t)(ticket & 1u) * c.stage_half;
+  unsigned e = b2_ld_volatile(c.epoch + blockIdx.x);
+  const char* in = (const char*)a.in;
+  char* out = (char*)a.out;
+  char* mine = c.stage[c.rank] + par;
+  char* mc = c.stage_mc + par;
+  const size_t nchunks = (a.nbytes + a.chunk - 1) / a.chunk;
+  const int t = threadIdx.x, nt = blockDim.x;
+
+  for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const size_t off = ch * a.chunk;
+    const size_t len = (a.nbytes - off < a.chunk) ? (a.nbytes - off) : a.chunk;
+    const size_t nv = (len + 15) >> 4;
+    b2_copy_bytes<false>(mine + off, in + off, len);
+    b2_barrier_all(c, ++e, a.opcode);
+    const size_t per = (nv + c.size - 1) / c.size;
+    size_t v0 = per * (size_t)c.rank;
+    if (v0 > nv) v0 = nv;
+    size_t v1 = v0 + per;
+    if (v1 > nv) v1 = nv;
+    size_t i = v0 + t;
+    // in-switch reduction of my sub-slice, broadcast back through the switch
+    for (; i + 3 * (size_t)nt < v1; i += 4 * (size_t)nt) {
+      uint4 r0 = b2_mc_ld_reduce<DT>(mc + off + (i << 4));
+      uint4 r1 = b2_mc_ld_reduce<DT>(mc + off + ((i + nt) << 4));
+      uint4 r2 = b2_mc_ld_reduce<DT>(mc + off + ((i + 2 * (size_t)nt) << 4));
+      uint4 r3 = b2_mc_ld_reduce<DT>(mc + off + ((i + 3 * (size_t)nt) << 4));
+      b2_mc_st(mc + off + (i << 4), r0);
+      b2_mc_st(mc + off + ((i + nt) << 4), r1);
+      b2_mc_st(mc + off + ((i + 2 * (size_t)nt) << 4), r2);
+      b2_mc_st(mc + off + ((i + 3 * (size_t)nt) << 4), r3);
+    }
+    for (; i < v1; i += nt) b2_mc_st(mc + off + (i << 4), b2_mc_ld_reduce<DT>(mc + off + (i << 4)));
+    b2_barrier_all(c, ++e, a.opcode);
+    b2_copy_bytes<true>(out + off, mine + off, len);
+  }
+  __syncthreads();
+  if (t == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
+  b2_finish_bump(c.ticket, c.ticket + 1, 1u, gridDim.x);
+}
+
+// ---------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------
+static size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// Same answer on every rank: depends only on (nbytes, size, sm_count, max_blocks).
+static void pick_chunks(const B2Comm* c, size_t nbytes, size_t* chunk_out, int* grid_out) {
+  const size_t unit = 16 * (size_t)c->dev.size;
+  const size_t min_chunk = round_up(16 * 1024, unit);
+  const size_t max_chunk = round_up(512 * 1024, unit);
+  const size_t target = (size_t)c->max_blocks;
+  size_t chunk = round_up((nbytes + target - 1) / target, unit);
+  if (chunk < min_chunk) chunk = min_chunk;
+  if (chunk > max_chunk) chunk = max_chunk;
+  size_t nchunks = (nbytes + chunk - 1) / chunk;
+  if (nchunks < 1) nchunks = 1;
+  int grid = (int)(nchunks < target ? nchunks : target);
+  *chunk_out = chunk;
+  *grid_out = grid;
+}
+
+extern "C" size_t b2_stage_need(int opcode, int nranks, size_t blk_bytes) {
+  const size_t stride = round_up(blk_bytes, 16);
+  switch (opcode) {
+    case B2_OPC_ALLTOALL:
+    case B2_OPC_SCATTER:
+      return stride * (size_t)nranks + 4096;
+    default:
+      return stride + 4096;
+  }
+}
+
+static int check_stage(B2Comm* c, int opcode, size_t blk_bytes, const char* name) {
+  const size_t need = b2_stage_need(opcode, c->dev.size, blk_bytes);
+  if (c->stage == nullptr || need > c->dev.stage_half) {
+    b2_set_error("%s: staging too small (need %zu bytes, have %zu); the Python layer must grow it",
+                 name, need, c->stage ? c->dev.stage_half : (size_t)0);
+    return B2_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
+static int finish_launch(B2Comm* c, cudaError_t err, const char* name) {
+  b2_count_launch(c);
+  if (err != cudaSuccess) {
+    b2_set_error("%s: kernel launch failed: %s", name, cudaGetErrorString(err));
+    return 1000 + (int)err;
+  }
+  return 0;
+}
+
+extern "C" int b2_barrier(B2Comm* c, cudaStream_t stream) {
+  B2DebugScope* dbg = b2_debug_begin(c, "Barrier", "", stream);
+  b2_k_barrier<<<1, 32, 0, stream>>>(c->dev);
+  int rc = finish_launch(c, cudaGetLastError(), "barrier");
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+static int reduce_common(B2Comm* c, const void* in, void* out, size_t count, int dtype, int op,
+                         int algo, int src_lo, int src_hi, int has_out, int opcode,
+                         const char* name, cudaStream_t stream) {
+  b2_ensure_tables();
+  if (dtype < 0 || dtype >= B2_DTYPE_COUNT || op < 0 || op >= B2_OP_COUNT ||
+      b2_reduce_table[dtype][op] == nullptr) {
+    b2_set_error("%s: unsupported dtype/op combination (dtype=%d, op=%d)", name, dtype, op);
+    return B2_ERR_BAD_ARG;
+  }
+  const size_t nbytes = count * b2_dtype_size(dtype);
+  if (nbytes == 0) return 0;
+  const int P = c->dev.size;
+  if (algo == B2_ALGO_AUTO) {
+    if (opcode != B2_OPC_ALLREDUCE) algo = B2_ALGO_ONESHOT;
+    else if (P > 1 && nbytes <= c->ll_max && nbytes * 2 <= c->dev.lay.ll_cap) algo = B2_ALGO_LL;
+    else if (P <= 2 || nbytes <= c->oneshot_max) algo = B2_ALGO_ONESHOT;
+    else if (c->dev.stage_mc != nullptr && op == B2_SUM && nbytes >= c->nvls_min &&
+             (dtype == B2_F32 || dtype == B2_BF16 || dtype == B2_F16)) algo = B2_ALGO_NVLS;
+    else algo = B2_ALGO_TWOSHOT;
+  }
+  if (algo == B2_ALGO_LL) {
+    if (opcode != B2_OPC_ALLREDUCE || nbytes * 2 > c->dev.lay.ll_cap) {
+      b2_set_error("%s: LL algorithm needs an allreduce of <= %zu bytes", name,
+                   c->dev.lay.ll_cap / 2);
+      return B2_ERR_BAD_ARG;
+    }
+    B2LLArgs a;
+    a.in = in; a.out = out; a.nbytes = nbytes; a.opcode = opcode;
+    const size_t nv = (nbytes + 15) / 16;
+    int grid = (int)((nv + B2_THREADS - 1) / B2_THREADS);
+    if (grid > c->sm_count) grid = c->sm_count;
+    if (grid < 1) grid = 1;
+    return finish_launch(c, b2_ll_table[dtype][op](c->dev, a, grid, stream), name);
+  }
+  int rc = check_stage(c, opcode, nbytes, name);
+  if (rc) return rc;
+  B2ReduceArgs a;
+  a.in = in; a.out = out; a.nbytes = nbytes;
+  a.src_lo = src_lo; a.src_hi = src_hi; a.has_out = has_out; a.opcode = opcode;
+  int grid;
+  pick_chunks(c, nbytes, &a.chunk, &grid);
+  if (algo == B2_ALGO_NVLS) {
+    if (c->dev.stage_mc == nullptr || op != B2_SUM ||
+        !(dtype == B2_F32 || dtype == B2_BF16 || dtype == B2_F16)) {
+      b2_set_error("%s: NVLS path needs a multicast-bound staging segment and SUM on f32/bf16/f16",
+                   name);
+      return B2_ERR_BAD_ARG;
+    }
+    a.algo = B2_ALGO_NVLS;
+    if (dtype == B2_F32) b2_k_allreduce_nvls<B2_F32><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
+    else if (dtype == B2_BF16) b2_k_allreduce_nvls<B2_BF16><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
+    else b2_k_allreduce_nvls<B2_F16><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
+    return finish_launch(c, cudaGetLastError(), name);
+  }
+  a.algo = (algo == B2_ALGO_TWOSHOT) ? B2_ALGO_TWOSHOT : B2_ALGO_ONESHOT;
+  return finish_launch(c, b2_reduce_table[dtype][op](c->dev, a, grid, stream), name);
+}
+
+extern "C" int b2_allreduce(B2Comm* c, const void* in, void* out, size_t count, int dtype, int op,
+                            int algo, cudaStream_t stream) {
+  char det[96];
+  snprintf(det, sizeof det, "with %zu items", count);
+  B2DebugScope* dbg = b2_debug_begin(c, "Allreduce", det, stream);
+  int rc = reduce_common(c, in, out, count, dtype, op, algo, 0, c->dev.size, 1, B2_OPC_ALLREDUCE,
+                         "allreduce", stream);
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+extern "C" int b2_reduce(B2Comm* c, const void* in, void* out, size_t count, int dtype, int op,
+                         int root, cudaStream_t stream) {
+  char det[96];
+  snprintf(det, sizeof det, "with %zu items to root %d", count, root);
+  B2DebugScope* dbg = b2_debug_begin(c, "Reduce", det, stream);
+  int rc;
+  if (root < 0 || root >= c->dev.size) {
+    b2_set_error("reduce: invalid root %d", root);
+    rc = B2_ERR_BAD_ARG;
+  } else {
+    rc = reduce_common(c, in, out, count, dtype, op, B2_ALGO_ONESHOT, 0, c->dev.size,
+                       c->dev.rank == root, B2_OPC_REDUCE, "reduce", stream);
+  }
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+extern "C" int b2_scan(B2Comm* c, const void* in, void* out, size_t count, int dtype, int op,
+                       cudaStream_t stream) {
+  char det[96];
+  snprintf(det, sizeof det, "with %zu items", count);
+  B2DebugScope* dbg = b2_debug_begin(c, "Scan", det, stream);
+  int rc = reduce_common(c, in, out, count, dtype, op, B2_ALGO_ONESHOT, 0, c->dev.rank + 1, 1,
+                         B2_OPC_SCAN, "scan", stream);
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+static int move_common(B2Comm* c, B2MoveArgs& a, const char* name, cudaStream_t stream) {
+  if (a.blk_bytes == 0) return 0;
+  int rc = check_stage(c, a.opcode, a.blk_bytes, name);
+  if (rc) return rc;
+  a.blk_stride = round_up(a.blk_bytes, 16);
+  int grid;
+  pick_chunks(c, a.blk_bytes, &a.chunk, &grid);
+  b2_k_move<<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
+  return finish_launch(c, cudaGetLastError(), name);
+}
+
+extern "C" int b2_allgather(B2Comm* c, const void* in, void* out, size_t blk_bytes,
+                            cudaStream_t stream) {
+  char det[96];
+  snprintf(det, sizeof det, "sending %zu bytes", blk_bytes);
+  B2DebugScope* dbg = b2_debug_begin(c, "Allgather", det, stream);
+  B2MoveArgs a;
+  memset(&a, 0, sizeof a);
+  a.in = in; a.out = out; a.blk_bytes = blk_bytes; a.opcode = B2_OPC_ALLGATHER;
+  a.nin = 1;
+  a.nsrc = c->dev.size;
+  for (int q = 0; q < c->dev.size; ++q) { a.src_rank[q] = q; a.src_blk[q] = 0; a.dst_blk[q] = q; }
+  int rc = move_common(c, a, "allgather", stream);
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+extern "C" int b2_alltoall(B2Comm* c, const void* in, void* out, size_t blk_bytes,
+                           cudaStream_t stream) {
+  char det[96];
+  snprintf(det, sizeof det, "sending %zu bytes per peer", blk_bytes);
+  B2DebugScope* dbg = b2_debug_begin(c, "Alltoall", det, stream);
+  B2MoveArgs a;
+  memset(&a, 0, sizeof a);
+  a.in = in; a.out = out; a.blk_bytes = blk_bytes; a.opcode = B2_OPC_ALLTOALL;
+  a.nin = c->dev.size;
+  a.nsrc = c->dev.size;
+  for (int q = 0; q < c->dev.size; ++q) {
+    a.src_rank[q] = q; a.src_blk[q] = c->dev.rank; a.dst_blk[q] = q;
+  }
+  int rc = move_common(c, a, "alltoall", stream);
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+extern "C" int b2_bcast(B2Comm* c, const void* in, void* out, size_t nbytes, int root,
+                        cudaStream_t stream) {
+  char det[96];
+  snprintf(det, sizeof det, "%zu bytes from root %d", nbytes, root);
+  B2DebugScope* dbg = b2_debug_begin(c, "Bcast", det, stream);
+  int rc;
+  if (root < 0 || root >= c->dev.size) {
+    b2_set_error("bcast: invalid root %d", root);
+    rc = B2_ERR_BAD_ARG;
+  } else {
+    B2MoveArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = in; a.out = out; a.blk_bytes = nbytes; a.opcode = B2_OPC_BCAST;
+    if (c->dev.rank == root) { a.nin = 1; a.nsrc = 0; }
+    else { a.nin = 0; a.nsrc = 1; a.src_rank[0] = root; a.src_blk[0] = 0; a.dst_blk[0] = 0; }
+    rc = move_common(c, a, "bcast", stream);
+  }
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+extern "C" int b2_gather(B2Comm* c, const void* in, void* out, size_t blk_bytes, int root,
+                         cudaStream_t stream) {
+  char det[96];
+  snprintf(det, sizeof det, "sending %zu bytes to root %d", blk_bytes, root);
+  B2DebugScope* dbg = b2_debug_begin(c, "Gather", det, stream);
+  int rc;
+  if (root < 0 || root >= c->dev.size) {
+    b2_set_error("gather: invalid root %d", root);
+    rc = B2_ERR_BAD_ARG;
+  } else {
+    B2MoveArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = in; a.out = out; a.blk_bytes = blk_bytes; a.opcode = B2_OPC_GATHER;
+    a.nin = 1;
+    if (c->dev.rank == root) {
+      a.nsrc = c->dev.size;
+      for (int q = 0; q < c->dev.size; ++q) { a.src_rank[q] = q; a.src_blk[q] = 0; a.dst_blk[q] = q; }
+    }
+    rc = move_common(c, a, "gather", stream);
+  }
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+extern "C" int b2_scatter(B2Comm* c, const void* in, void* out, size_t blk_bytes, int root,
+                          cudaStream_t stream) {
+  char det[96];
+  snprintf(det, sizeof det, "%zu bytes per rank from root %d", blk_bytes, root);
+  B2DebugScope* dbg = b2_debug_begin(c, "Scatter", det, stream);
+  int rc;
+  if (root < 0 || root >= c->dev.size) {
+    b2_set_error("scatter: invalid root %d", root);
+    rc = B2_ERR_BAD_ARG;
+  } else {
+    B2MoveArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = in; a.out = out; a.blk_bytes = blk_bytes; a.opcode = B2_OPC_SCATTER;
+    a.nin = (c->dev.rank == root) ? c->dev.size : 0;
+    a.nsrc = 1;
+    a.src_rank[0] = root; a.src_blk[0] = c->dev.rank; a.dst_blk[0] = 0;
+    rc = move_common(c, a, "scatter", stream);
+  }
+  b2_debug_end(dbg, rc);
+  return rc;
+}

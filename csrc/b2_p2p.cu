@@ -1,0 +1,310 @@
+// mpi4jax_b200 -- point-to-point send / recv / sendrecv over peer-mapped HBM.
+//
+// Replaces the reference's blocking MPI_Send / MPI_Recv / MPI_Sendrecv call
+// sites (mpi4jax/_src/xla_bridge/mpi_ops_common.h:340-389 and the CUDA callers
+// mpi_xla_bridge_cuda.cpp:650-827, each preceded by a full stream sync and,
+// by default, D2H/H2D staging through pageable host memory).
+//
+// Transport: every directed pair (s -> d) owns a ring of B2_P2P_NSLOT slots in
+// d's symmetric heap.  A message is cut into fragments of at most slot_bytes;
+// fragment number fs of the pair uses slot fs % NSLOT.  Up to 64 CTAs ("lanes")
+// cooperate on a message; lane l of the sender is paired with lane l of the
+// receiver (both derive the lane count from the byte count):
+//
+//   sender lane l          : wait credit(slot)  -> push stripe l into d's slot (NVLink stores)
+//                            -> st.release hdr[slot][l] = {fs+1, tag, nbytes}
+//   receiver lane l        : wait hdr[slot][l].seq == fs+1 -> validate -> copy stripe to the
+//                            user buffer -> last lane to finish releases ack[slot] = fs+1 to s
+//
+// The sender never waits for the receiver unless the ring is full (eager up to
+// NSLOT x slot_bytes in flight, like MPI's eager protocol); larger messages
+// stream through the ring with the two kernels running concurrently on the two
+// GPUs.  sendrecv launches both roles in ONE kernel (disjoint CTA groups), so
+// the exchange is deadlock-free for any size.  All sequence numbers live in
+// device memory and are advanced by the kernels themselves: the ops are
+// CUDA-graph capturable and never synchronise the host.  MPI semantics kept:
+// tags (validated against the pair FIFO), ANY_TAG, ANY_SOURCE (device-side
+// election over the P inbox heads), Status(source, tag, count), zero-byte
+// messages, self-sends.  Restriction (documented in docs/sharp-bits.md):
+// messages of one (source, dest) pair are matched in the order they were sent.
+#include <cstdio>
+#include <cstring>
+
+#include "b2_device.cuh"
+#include "b2_runtime.h"
+
+extern "C" void b2_set_error(const char* fmt, ...);
+extern "C" void b2_count_launch(B2Comm* c);
+struct B2DebugScope;
+extern "C" B2DebugScope* b2_debug_begin(B2Comm* c, const char* opname, const char* details,
+                                         cudaStream_t stream);
+extern "C" void b2_debug_end(B2DebugScope* s, int code);
+
+// p2p_ctl words
+#define CTL_SEND_FIN 0     // finish counter, send role
+#define CTL_RECV_FIN 1     // finish counter, recv role
+#define CTL_ELECT 2        // any-source election word: (gen << 8) | source
+#define CTL_GEN 3          // election generation
+#define CTL_SLOT_DONE 8    // [NSLOT] per-slot receiver-lane completion counters
+
+struct B2P2PArgs {
+  const void* sendbuf;
+  size_t send_bytes;
+  int dest;
+  int send_tag;
+  int send_lanes;      // 0 = no send role
+  void* recvbuf;
+  size_t recv_bytes;
+  int source;          // -1 = ANY_SOURCE
+  int recv_tag;        // -1 = ANY_TAG
+  int recv_lanes;      // 0 = no recv role
+  B2StatusRecord* status;
+  int opcode;
+};
+
+__device__ __forceinline__ void stripe_of(size_t fraglen, int lanes, int lane, size_t* lo,
+                                          size_t* hi) {
+  size_t stripe = (fraglen + lanes - 1) / lanes;
+  stripe = (stripe + 15) & ~(size_t)15;
+  size_t a = stripe * (size_t)lane;
+  if (a > fraglen) a = fraglen;
+  size_t b = a + stripe;
+  if (b > fraglen) b = fraglen;
+  *lo = a;
+  *hi = b;
+}
+
+__device__ void p2p_send_role(const B2DevComm& c, const B2P2PArgs& a, int lane) {
+  const size_t slot_bytes = c.lay.p2p_slot_bytes;
+  const unsigned seq0 = b2_ticket_read(c.p2p_send_seq + a.dest);
+  const size_t nfrag = a.send_bytes == 0 ? 1 : (a.send_bytes + slot_bytes - 1) / slot_bytes;
+  const char* src = (const char*)a.sendbuf;
+  char* dheap = c.heap[a.dest];
+  for (size_t f = 0; f < nfrag; ++f) {
+    const unsigned fs = seq0 + (unsigned)f;
+    const unsigned slot = fs % B2_P2P_NSLOT;
+    const size_t fragoff = f * slot_bytes;
+    const size_t fraglen = (a.send_bytes - fragoff < slot_bytes) ? (a.send_bytes - fragoff) : slot_bytes;
+    size_t lo, hi;
+    stripe_of(fraglen, a.send_lanes, lane, &lo, &hi);
+    // credit: the previous occupant of this slot (fragment fs - NSLOT) has been consumed
+    if (threadIdx.x == 0) {
+      const unsigned* ack =
+          (const unsigned*)(c.heap[c.rank] + c.lay.p2p_ack_off) + (size_t)a.dest * B2_P2P_NSLOT + slot;
+      b2_wait_ge(c, ack, fs + 1u - B2_P2P_NSLOT, a.opcode, a.dest);
+    }
+    __syncthreads();
+    char* dslot = dheap + c.lay.p2p_slot_off + ((size_t)c.rank * B2_P2P_NSLOT + slot) * slot_bytes;
+    b2_copy_bytes<false>(dslot + lo, src + fragoff + lo, hi - lo);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned* hdr = (unsigned*)(dheap + c.lay.p2p_hdr_off) +
+                      (((size_t)c.rank * B2_P2P_NSLOT + slot) * B2_P2P_MAX_LANES + lane) * 4;
+      b2_st_relaxed_sys(hdr + 1, (unsigned)a.send_tag);
+      b2_st_relaxed_sys(hdr + 2, (unsigned)(a.send_bytes & 0xffffffffull));
+      b2_st_relaxed_sys(hdr + 3, (unsigned)(a.send_bytes >> 32));
+      b2_st_release_sys(hdr + 0, fs + 1u);
+    }
+  }
+  b2_finish_bump(c.p2p_send_seq + a.dest, c.p2p_ctl + CTL_SEND_FIN, (unsigned)nfrag,
+                 (unsigned)a.send_lanes);
+}
+
+__device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) {
+  __shared__ int s_src;
+  __shared__ unsigned s_seq0;
+  const size_t slot_bytes = c.lay.p2p_slot_bytes;
+  const unsigned* hdr_base = (const unsigned*)(c.heap[c.rank] + c.lay.p2p_hdr_off);
+
+  // ---- resolve the source (ANY_SOURCE: lane 0 elects, the others follow) ----
+  if (threadIdx.x == 0) {
+    int src = a.source;
+    if (src < 0) {
+      const unsigned gen = b2_ld_volatile(c.p2p_ctl + CTL_GEN) & 0xffffffu;
+      if (lane == 0) {
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        int probe = 0;
+        while (src < 0) {
+          const unsigned want = b2_ld_volatile(c.p2p_recv_seq + probe);
+          const unsigned* h =
+              hdr_base + (((size_t)probe * B2_P2P_NSLOT + want % B2_P2P_NSLOT) * B2_P2P_MAX_LANES) * 4;
+          if (b2_ld_acquire_sys(h) == want + 1u &&
+              (a.recv_tag < 0 || (int)b2_ld_volatile(h + 1) == a.recv_tag)) {
+            src = probe;
+            break;
+          }
+          probe = (probe + 1) % c.size;
+          if ((++spins & 0xfffu) == 0) {
+            unsigned long long now = b2_gtime();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > c.timeout_ns) b2_fatal(c, B2_ERR_TIMEOUT, a.opcode, -1, 0, 0, 3);
+          }
+        }
+        __threadfence();
+        b2_st_volatile(c.p2p_ctl + CTL_ELECT, (gen << 8) | (unsigned)src);
+      } else {
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (true) {
+          const unsigned w = b2_ld_volatile(c.p2p_ctl + CTL_ELECT);
+          if ((w >> 8) == gen) { src = (int)(w & 0xffu); break; }
+          if ((++spins & 0xfffu) == 0) {
+            unsigned long long now = b2_gtime();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > c.timeout_ns) b2_fatal(c, B2_ERR_TIMEOUT, a.opcode, -1, gen, w, 4);
+          }
+        }
+      }
+    }
+    s_src = src;
+    s_seq0 = b2_ld_volatile(c.p2p_recv_seq + src);
+  }
+  __syncthreads();
+  const int src = s_src;
+  const unsigned seq0 = s_seq0;
+
+  const size_t nfrag = a.recv_bytes == 0 ? 1 : (a.recv_bytes + slot_bytes - 1) / slot_bytes;
+  char* dst = (char*)a.recvbuf;
+  const char* myheap = c.heap[c.rank];
+  for (size_t f = 0; f < nfrag; ++f) {
+    const unsigned fs = seq0 + (unsigned)f;
+    const unsigned slot = fs % B2_P2P_NSLOT;
+    const size_t fragoff = f * slot_bytes;
+    const size_t fraglen = (a.recv_bytes - fragoff < slot_bytes) ? (a.recv_bytes - fragoff) : slot_bytes;
+    size_t lo, hi;
+    stripe_of(fraglen, a.recv_lanes, lane, &lo, &hi);
+    const unsigned* hdr = hdr_base + (((size_t)src * B2_P2P_NSLOT + slot) * B2_P2P_MAX_LANES + lane) * 4;
+    if (threadIdx.x == 0) {
+      b2_wait_eq(c, hdr, fs + 1u, a.opcode, src);
+      if (f == 0) {
+        const int tag = (int)b2_ld_volatile(hdr + 1);
+        const unsigned long long nb =
+            (unsigned long long)b2_ld_volatile(hdr + 2) | ((unsigned long long)b2_ld_volatile(hdr + 3) << 32);
+        if (a.recv_tag >= 0 && tag != a.recv_tag)
+          b2_fatal(c, B2_ERR_TAG_MISMATCH, a.opcode, src, (unsigned)a.recv_tag, (unsigned)tag, 0);
+        if (nb != (unsigned long long)a.recv_bytes)
+          b2_fatal(c, B2_ERR_TRUNCATE, a.opcode, src, (unsigned)a.recv_bytes, (unsigned)nb, 0);
+        if (lane == 0 && a.status != nullptr) {
+          a.status->source = src;
+          a.status->tag = tag;
+          a.status->count_bytes = (long long)nb;
+          a.status->error = 0;
+          __threadfence_system();
+          a.status->ready = 1;
+        }
+      }
+    }
+    __syncthreads();
+    const char* sslot = myheap + c.lay.p2p_slot_off + ((size_t)src * B2_P2P_NSLOT + slot) * slot_bytes;
+    b2_copy_bytes<true>(dst + fragoff + lo, sslot + lo, hi - lo);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned* done = c.p2p_ctl + CTL_SLOT_DONE + slot;
+      const unsigned old = atomicAdd(done, 1u);
+      if (old == (unsigned)a.recv_lanes - 1u) {
+        b2_st_volatile(done, 0u);
+        unsigned* ack = (unsigned*)(c.heap[src] + c.lay.p2p_ack_off) + (size_t)c.rank * B2_P2P_NSLOT + slot;
+        b2_st_release_sys(ack, fs + 1u);
+      }
+    }
+  }
+  // advance recv_seq[src] (+ election generation) once every lane is done
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned old = atomicAdd(c.p2p_ctl + CTL_RECV_FIN, 1u);
+    if (old == (unsigned)a.recv_lanes - 1u) {
+      b2_st_volatile(c.p2p_ctl + CTL_RECV_FIN, 0u);
+      b2_st_volatile(c.p2p_recv_seq + src, seq0 + (unsigned)nfrag);
+      b2_st_volatile(c.p2p_ctl + CTL_GEN, b2_ld_volatile(c.p2p_ctl + CTL_GEN) + 1u);
+      __threadfence();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(B2_THREADS) b2_k_p2p(const B2DevComm c, const B2P2PArgs a) {
+  if ((int)blockIdx.x < a.send_lanes) p2p_send_role(c, a, (int)blockIdx.x);
+  else p2p_recv_role(c, a, (int)blockIdx.x - a.send_lanes);
+}
+
+// lane count: same function of the byte count on both sides of a message
+static int lanes_for(const B2Comm* c, size_t nbytes) {
+  size_t frag = nbytes < c->dev.lay.p2p_slot_bytes ? nbytes : c->dev.lay.p2p_slot_bytes;
+  size_t lanes = (frag + 65535) / 65536;
+  if (lanes < 1) lanes = 1;
+  if (lanes > B2_P2P_MAX_LANES) lanes = B2_P2P_MAX_LANES;
+  return (int)lanes;
+}
+
+static int launch_p2p(B2Comm* c, B2P2PArgs& a, const char* name, cudaStream_t stream) {
+  const int P = c->dev.size;
+  if (a.send_lanes > 0 && (a.dest < 0 || a.dest >= P)) {
+    b2_set_error("%s: invalid destination rank %d (communicator size %d)", name, a.dest, P);
+    return B2_ERR_BAD_ARG;
+  }
+  if (a.recv_lanes > 0 && (a.source < -1 || a.source >= P)) {
+    b2_set_error("%s: invalid source rank %d (communicator size %d)", name, a.source, P);
+    return B2_ERR_BAD_ARG;
+  }
+  b2_k_p2p<<<a.send_lanes + a.recv_lanes, B2_THREADS, 0, stream>>>(c->dev, a);
+  b2_count_launch(c);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    b2_set_error("%s: kernel launch failed: %s", name, cudaGetErrorString(err));
+    return 1000 + (int)err;
+  }
+  return 0;
+}
+
+extern "C" int b2_send(B2Comm* c, const void* buf, size_t nbytes, int dest, int tag,
+                       cudaStream_t stream) {
+  char det[128];
+  snprintf(det, sizeof det, "%zu bytes to %d with tag %d", nbytes, dest, tag);
+  B2DebugScope* dbg = b2_debug_begin(c, "Send", det, stream);
+  B2P2PArgs a;
+  memset(&a, 0, sizeof a);
+  a.sendbuf = buf; a.send_bytes = nbytes; a.dest = dest; a.send_tag = tag;
+  a.send_lanes = lanes_for(c, nbytes);
+  a.opcode = B2_OPC_SEND;
+  int rc = launch_p2p(c, a, "send", stream);
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+extern "C" int b2_recv(B2Comm* c, void* buf, size_t nbytes, int source, int tag,
+                       B2StatusRecord* status, cudaStream_t stream) {
+  char det[128];
+  snprintf(det, sizeof det, "%zu bytes from %d with tag %d", nbytes, source, tag);
+  B2DebugScope* dbg = b2_debug_begin(c, "Recv", det, stream);
+  B2P2PArgs a;
+  memset(&a, 0, sizeof a);
+  a.recvbuf = buf; a.recv_bytes = nbytes; a.source = source; a.recv_tag = tag;
+  a.recv_lanes = lanes_for(c, nbytes);
+  a.status = status;
+  a.opcode = B2_OPC_RECV;
+  int rc = launch_p2p(c, a, "recv", stream);
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+extern "C" int b2_sendrecv(B2Comm* c, const void* sendbuf, size_t send_bytes, int dest, int sendtag,
+                           void* recvbuf, size_t recv_bytes, int source, int recvtag,
+                           B2StatusRecord* status, cudaStream_t stream) {
+  char det[160];
+  snprintf(det, sizeof det, "<%d (%zu bytes, tag %d) / >%d (%zu bytes, tag %d)", source, recv_bytes,
+           recvtag, dest, send_bytes, sendtag);
+  B2DebugScope* dbg = b2_debug_begin(c, "Sendrecv", det, stream);
+  B2P2PArgs a;
+  memset(&a, 0, sizeof a);
+  a.sendbuf = sendbuf; a.send_bytes = send_bytes; a.dest = dest; a.send_tag = sendtag;
+  a.send_lanes = lanes_for(c, send_bytes);
+  a.recvbuf = recvbuf; a.recv_bytes = recv_bytes; a.source = source; a.recv_tag = recvtag;
+  a.recv_lanes = lanes_for(c, recv_bytes);
+  a.status = status;
+  a.opcode = B2_OPC_SENDRECV;
+  int rc = launch_p2p(c, a, "sendrecv", stream);
+  b2_debug_end(dbg, rc);
+  return rc;
+}

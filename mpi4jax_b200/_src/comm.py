@@ -1,0 +1,361 @@
+"""Communicators, reduction ops, Status -- the MPI-like object model.
+
+The reference takes ``mpi4py`` objects (``MPI.Intracomm``, ``MPI.Op``, ``MPI.Status``)
+and forwards their C handles to its C++ bridge (/root/reference/mpi4jax/_src/utils.py:
+60-153).  Neither mpi4py nor an MPI library exists on the target image, and the B200
+transport is not MPI at all, so this module supplies the small object model user code
+needs (``mpi4jax_b200.MPI``): ``COMM_WORLD``, ``Comm.Get_rank/Get_size/Clone/Split/
+Free/Barrier``, the ten predefined ``Op`` constants, ``Status`` with
+``Get_source/Get_tag/Get_count``, ``ANY_SOURCE``/``ANY_TAG``.
+
+Process model (same as the reference, README.rst:83-89): one OS process per rank, one
+GPU per process.  Ranks are launched by ``torchrun`` or ``python -m mpi4jax_b200.run``;
+the control plane (handle exchange, CPU-tensor collectives) is a ``torch.distributed``
+gloo group, the data plane for CUDA tensors is the native symmetric heap
+(``_src/backends/cuda.py``).
+"""
+
+from __future__ import annotations
+
+import atexit
+import os
+import threading
+import weakref
+from datetime import timedelta
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from .native import codes
+
+ANY_SOURCE = -1
+ANY_TAG = -1
+PROC_NULL = -2
+UNDEFINED = -32766
+
+
+class MPIError(RuntimeError):
+    """Raised (or printed before aborting) when a communication call fails."""
+
+
+class Op:
+    """A predefined reduction operator (stand-in for ``mpi4py.MPI.Op``)."""
+
+    __slots__ = ("name", "code")
+
+    def __init__(self, name: str, code: int):
+        self.name = name
+        self.code = code
+
+    def __repr__(self) -> str:
+        return f"<mpi4jax_b200.MPI.{self.name}>"
+
+    def __reduce__(self):
+        return (_op_by_name, (self.name,))
+
+
+SUM = Op("SUM", codes.SUM)
+PROD = Op("PROD", codes.PROD)
+MIN = Op("MIN", codes.MIN)
+MAX = Op("MAX", codes.MAX)
+LAND = Op("LAND", codes.LAND)
+LOR = Op("LOR", codes.LOR)
+LXOR = Op("LXOR", codes.LXOR)
+BAND = Op("BAND", codes.BAND)
+BOR = Op("BOR", codes.BOR)
+BXOR = Op("BXOR", codes.BXOR)
+_ALL_OPS = {o.name: o for o in (SUM, PROD, MIN, MAX, LAND, LOR, LXOR, BAND, BOR, BXOR)}
+
+
+def _op_by_name(name: str) -> Op:
+    return _ALL_OPS[name]
+
+
+def as_op(op) -> Op:
+    """Accept our ``Op`` or (if mpi4py happens to be installed) an ``mpi4py.MPI.Op``."""
+    if isinstance(op, Op):
+        return op
+    name = getattr(op, "name", None) or getattr(op, "Get_name", lambda: None)()
+    if isinstance(name, str):
+        key = name.replace("MPI_", "").upper()
+        if key in _ALL_OPS:
+            return _ALL_OPS[key]
+    raise TypeError(f"unsupported reduction operator: {op!r}")
+
+
+class Status:
+    """Receive status (stand-in for ``mpi4py.MPI.Status``).
+
+    On the GPU path the receive kernel writes (source, tag, byte count) into a
+    host-mapped record; the values are read lazily, after synchronising with the
+    stream the receive was enqueued on -- no host sync happens unless the user
+    actually inspects the status.
+    """
+
+    def __init__(self):
+        self._source = ANY_SOURCE
+        self._tag = ANY_TAG
+        self._count_bytes = 0
+        self._error = 0
+        self._native = None  # (record_ptr, event) while a GPU receive is pending
+        self._itemsize = 1
+
+    # -- filled by the backends ------------------------------------------------
+    def _set(self, source: int, tag: int, count_bytes: int, itemsize: int = 1) -> None:
+        self._source, self._tag, self._count_bytes = int(source), int(tag), int(count_bytes)
+        self._itemsize = itemsize
+        self._native = None
+
+    def _bind_native(self, record, event, itemsize: int) -> None:
+        self._native = (record, event)
+        self._itemsize = itemsize
+
+    def _sync(self) -> None:
+        if self._native is None:
+            return
+        record, event = self._native
+        event.synchronize()
+        rec = record.contents
+        self._source, self._tag = int(rec.source), int(rec.tag)
+        self._count_bytes, self._error = int(rec.count_bytes), int(rec.error)
+        self._native = None
+
+    # -- mpi4py-compatible accessors --------------------------------------------
+    def Get_source(self) -> int:
+        self._sync()
+        return self._source
+
+    def Get_tag(self) -> int:
+        self._sync()
+        return self._tag
+
+    def Get_error(self) -> int:
+        self._sync()
+        return self._error
+
+    def Get_count(self, datatype=None) -> int:
+        """Elements received (of the receive buffer's dtype); bytes if ``datatype`` is ``BYTE``."""
+        self._sync()
+        if datatype is BYTE:
+            return self._count_bytes
+        return self._count_bytes // max(self._itemsize, 1)
+
+    source = property(Get_source)
+    tag = property(Get_tag)
+
+
+BYTE = object()
+
+_comm_registry: "weakref.WeakSet[Comm]" = weakref.WeakSet()
+_world_lock = threading.Lock()
+_world: Optional["Comm"] = None
+_comm_counter = 0
+
+
+def _env_int(name: str, default: int) -> int:
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def local_rank() -> int:
+    return _env_int("LOCAL_RANK", _env_int("RANK", 0))
+
+
+def select_device() -> torch.device:
+    """Pin this process to its GPU (one process per GPU).  Several ranks may share a GPU
+    when there are fewer devices than local ranks (correctness testing only)."""
+    want = os.environ.get("MPI4JAX_B200_DEVICE", "").lower()
+    if want == "cpu" or not torch.cuda.is_available():
+        return torch.device("cpu")
+    idx = local_rank() % torch.cuda.device_count()
+    torch.cuda.set_device(idx)
+    return torch.device("cuda", idx)
+
+
+def _init_process_group() -> None:
+    """Create the control-plane process group if the launcher has not done so."""
+    if dist.is_initialized():
+        return
+    world = _env_int("WORLD_SIZE", 1)
+    rank = _env_int("RANK", 0)
+    timeout = timedelta(seconds=float(os.environ.get("MPI4JAX_B200_PG_TIMEOUT", "600")))
+    if world == 1 and "MASTER_ADDR" not in os.environ:
+        store = dist.HashStore()
+        dist.init_process_group("gloo", store=store, rank=0, world_size=1, timeout=timeout)
+        return
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=timeout)
+
+
+def _control_group_for_world():
+    """A gloo group spanning all ranks (the default group itself when it is gloo-capable)."""
+    backend = dist.get_backend()
+    if "gloo" in str(backend):
+        return dist.group.WORLD
+    return dist.new_group(backend="gloo")
+
+
+class Comm:
+    """An intra-communicator over a subset of the job's processes."""
+
+    def __init__(self, group, ranks: Sequence[int], name: str = "comm"):
+        global _comm_counter
+        self._group = group
+        self._ranks = list(ranks)
+        self._global_rank = dist.get_rank()
+        self._rank = self._ranks.index(self._global_rank)
+        self._name = name
+        _comm_counter += 1
+        self._id = _comm_counter
+        self._native = None        # backends.cuda.NativeComm, created on first CUDA op
+        self._cpu_state = None     # backends.cpu.CpuState, created on first CPU p2p op
+        self._freed = False
+        self.device = select_device()
+        _comm_registry.add(self)
+
+    # -- mpi4py-style API --------------------------------------------------------
+    def Get_rank(self) -> int:
+        return self._rank
+
+    def Get_size(self) -> int:
+        return len(self._ranks)
+
+    rank = property(Get_rank)
+    size = property(Get_size)
+
+    def Get_name(self) -> str:
+        return self._name
+
+    def Clone(self) -> "Comm":
+        """A communicator over the same processes with private message channels
+        (collective; reference default comm = ``COMM_WORLD.Clone()``, utils.py:20-27)."""
+        self._check_alive()
+        group = dist.new_group(ranks=self._ranks, backend="gloo")
+        return Comm(group, self._ranks, name=self._name + ".clone")
+
+    Dup = Clone
+
+    def Split(self, color: int = 0, key: int = 0) -> Optional["Comm"]:
+        """Partition the communicator (collective over all its ranks)."""
+        self._check_alive()
+        info = [None] * self.size
+        dist.all_gather_object(info, (int(color), int(key), self._global_rank), group=self._group)
+        colors = sorted({c for c, _, _ in info if c != UNDEFINED})
+        mine = None
+        for c in colors:  # every rank creates every group, in the same order
+            members = sorted((k, r) for cc, k, r in info if cc == c)
+            ranks = [r for _, r in members]
+            group = dist.new_group(ranks=ranks, backend="gloo")
+            if c == color:
+                mine = Comm(group, ranks, name=f"{self._name}.split{c}")
+        return mine
+
+    def Barrier(self) -> None:
+        """Host-side barrier on the control plane (mpi4py ``comm.Barrier()``)."""
+        self._check_alive()
+        dist.barrier(group=self._group)
+
+    barrier = Barrier
+
+    def Free(self) -> None:
+        if self._freed:
+            return
+        self._freed = True
+        if self._native is not None:
+            self._native.destroy()
+            self._native = None
+
+    def py2f(self) -> int:
+        return self._id
+
+    def __repr__(self) -> str:
+        return f"<mpi4jax_b200.MPI.Comm {self._name} rank={self._rank} size={self.size}>"
+
+    def __hash__(self) -> int:
+        return hash(("b200comm", self._id))
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, Comm) and other._id == self._id
+
+    # -- internals -----------------------------------------------------------------
+    def _check_alive(self) -> None:
+        if self._freed:
+            raise MPIError("communicator has been freed")
+
+    def _global(self, rank_in_comm: int) -> int:
+        return self._ranks[rank_in_comm]
+
+    def _native_comm(self):
+        """The native (GPU) side of the communicator; created collectively on first use."""
+        self._check_alive()
+        if self._native is None:
+            from .backends.cuda import NativeComm
+
+            self._native = NativeComm(self)
+        return self._native
+
+    def _cpu(self):
+        if self._cpu_state is None:
+            from .backends.cpu import CpuState
+
+            self._cpu_state = CpuState(self)
+        return self._cpu_state
+
+
+def get_world() -> Comm:
+    """``MPI.COMM_WORLD`` (created lazily; initialises torch.distributed if needed)."""
+    global _world
+    with _world_lock:
+        if _world is None:
+            _init_process_group()
+            group = _control_group_for_world()
+            _world = Comm(group, list(range(dist.get_world_size())), name="COMM_WORLD")
+        return _world
+
+
+def flush() -> None:
+    """Wait for every enqueued communication op to finish (reference: the atexit
+    ``jax.effects_barrier()``, mpi4jax/_src/__init__.py:13-24)."""
+    for comm in list(_comm_registry):
+        if comm._cpu_state is not None:
+            comm._cpu_state.flush()
+        if comm._native is not None:
+            comm._native.flush()
+    if torch.cuda.is_available() and torch.cuda.is_initialized():
+        torch.cuda.synchronize()
+
+
+def _shutdown() -> None:
+    try:
+        flush()
+    except Exception:  # pragma: no cover - best effort at interpreter exit
+        pass
+    for comm in list(_comm_registry):
+        try:
+            comm.Free()
+        except Exception:  # pragma: no cover
+            pass
+    try:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:  # pragma: no cover
+        pass
+
+
+atexit.register(_shutdown)
+
+
+def _op_types() -> tuple:
+    try:  # accept mpi4py operators too when mpi4py happens to be installed
+        from mpi4py import MPI as _mpi4py  # type: ignore
+
+        return (Op, _mpi4py.Op)
+    except Exception:
+        return (Op,)
+
+
+OP_TYPES = _op_types()

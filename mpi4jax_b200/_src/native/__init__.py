@@ -1,0 +1,219 @@
+"""Bridge registry: loads the native sm_100a library and exposes its C ABI.
+
+Counterpart of /root/reference/mpi4jax/_src/xla_bridge/__init__.py:1-174, which
+imports the nanobind modules, checks the MPI ABI, fans ``set_logging`` out to every
+extension and registers 12 XLA FFI targets per platform.  Here there is one shared
+library (``mpi4jax_b200/_native/libb2mpi.so``) bound through ``ctypes``; the "targets"
+are the ``b2_*`` entry points listed in ``csrc/b2_runtime.h``.  There is no MPI, so
+the ABI check degenerates to a build-info record (``NATIVE_ABI_INFO``).
+
+``HAS_CUDA_EXT`` is True when the library could be loaded (it loads on GPU-less
+hosts too: the CUDA driver is resolved lazily).  Ops on CUDA tensors fail loudly
+when it is False -- there is no silent PyTorch fallback on the GPU path.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import sys
+from ctypes import (
+    CFUNCTYPE,
+    POINTER,
+    Structure,
+    c_char_p,
+    c_double,
+    c_float,
+    c_int,
+    c_longlong,
+    c_size_t,
+    c_void_p,
+)
+from pathlib import Path
+
+from ..decorators import env_flag
+from . import codes  # noqa: F401
+
+_LIB_PATH = Path(__file__).resolve().parents[2] / "_native" / "libb2mpi.so"
+
+HAS_CUDA_EXT = False
+HAS_XPU_EXT = False  # the reference has an Intel XPU bridge; B200 does not
+CUDA_EXT_ERROR = ""
+lib = None
+
+
+class B2HaloDesc(Structure):
+    _fields_ = [
+        ("nfields", c_int),
+        ("field", c_void_p * 8),
+        ("kind", c_int * 8),
+        ("ny", c_int),
+        ("nx", c_int),
+        ("west", c_int),
+        ("east", c_int),
+        ("south", c_int),
+        ("north", c_int),
+        ("periodic_x", c_int),
+        ("at_east_wall", c_int),
+        ("at_north_wall", c_int),
+    ]
+
+
+class B2SweParams(Structure):
+    _fields_ = [
+        ("ny", c_int),
+        ("nx", c_int),
+        ("dx", c_float),
+        ("dy", c_float),
+        ("dt", c_float),
+        ("gravity", c_float),
+        ("viscosity", c_float),
+        ("ab_a", c_float),
+        ("ab_b", c_float),
+        ("first_step", c_int),
+        ("south_wall", c_int),
+        ("north_wall", c_int),
+        ("coriolis", c_void_p),
+    ]
+
+
+class B2StatusRecord(Structure):
+    _fields_ = [
+        ("source", c_int),
+        ("tag", c_int),
+        ("count_bytes", c_longlong),
+        ("error", c_int),
+        ("ready", c_int),
+    ]
+
+
+_PRINT_CB = CFUNCTYPE(None, c_char_p)
+
+
+def _py_print(msg: bytes) -> None:
+    # routed through sys.stdout so pytest's capsys / notebooks see native log lines
+    sys.stdout.write(msg.decode("utf-8", "replace") + "\n")
+    sys.stdout.flush()
+
+
+_print_cb_keepalive = _PRINT_CB(_py_print)
+
+_SIGNATURES = {
+    "b2_version": (c_char_p, []),
+    "b2_last_error": (c_char_p, []),
+    "b2_set_logging": (None, [c_int]),
+    "b2_get_logging": (c_int, []),
+    "b2_set_print_callback": (None, [_PRINT_CB]),
+    "b2_launch_count": (c_int, []),
+    "b2_init": (c_int, [c_int]),
+    "b2_multicast_supported": (c_int, [c_int]),
+    "b2_vmm_supported": (c_int, [c_int]),
+    "b2_granularity": (c_size_t, [c_int, c_int]),
+    "b2_seg_create": (c_void_p, [c_int, c_int, c_int, c_size_t, c_int]),
+    "b2_seg_export_fd": (c_int, [c_void_p]),
+    "b2_seg_import_fd": (c_int, [c_void_p, c_int, c_int]),
+    "b2_seg_ipc_handle": (c_int, [c_void_p, c_void_p]),
+    "b2_seg_import_ipc": (c_int, [c_void_p, c_int, c_void_p]),
+    "b2_seg_ptr": (c_void_p, [c_void_p, c_int]),
+    "b2_seg_bytes": (c_size_t, [c_void_p]),
+    "b2_seg_destroy": (c_int, [c_void_p]),
+    "b2_mc_create": (c_void_p, [c_int, c_int, c_size_t]),
+    "b2_mc_export_fd": (c_int, [c_void_p]),
+    "b2_mc_import": (c_void_p, [c_int, c_int, c_size_t]),
+    "b2_mc_add_device": (c_int, [c_void_p]),
+    "b2_mc_bind": (c_int, [c_void_p, c_void_p]),
+    "b2_mc_ptr": (c_void_p, [c_void_p]),
+    "b2_mc_destroy": (c_int, [c_void_p]),
+    "b2_layout_bytes": (c_size_t, [c_int, c_size_t, c_size_t, c_size_t]),
+    "b2_comm_create": (c_void_p, [c_int, c_int, c_int, c_void_p, c_size_t, c_size_t, c_size_t, c_double]),
+    "b2_comm_set_stage": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "b2_comm_stage_half": (c_size_t, [c_void_p]),
+    "b2_comm_set_tuning": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong, c_int]),
+    "b2_comm_check_error": (c_int, [c_void_p, c_char_p, c_int]),
+    "b2_comm_destroy": (c_int, [c_void_p]),
+    "b2_stage_need": (c_size_t, [c_int, c_int, c_size_t]),
+    "b2_barrier": (c_int, [c_void_p, c_void_p]),
+    "b2_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "b2_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "b2_scan": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "b2_allgather": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b2_alltoall": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b2_bcast": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "b2_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "b2_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "b2_status_alloc": (POINTER(B2StatusRecord), []),
+    "b2_status_free": (None, [POINTER(B2StatusRecord)]),
+    "b2_send": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "b2_recv": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, POINTER(B2StatusRecord), c_void_p]),
+    "b2_sendrecv": (
+        c_int,
+        [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_size_t, c_int, c_int,
+         POINTER(B2StatusRecord), c_void_p],
+    ),
+    "b2_halo_exchange": (c_int, [c_void_p, POINTER(B2HaloDesc), c_void_p]),
+    "b2_swe_fluxes": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 7 + [c_void_p]),
+    "b2_swe_tendencies": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 11 + [c_void_p]),
+    "b2_swe_friction_flux_u": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_void_p]),
+    "b2_swe_friction_u_flux_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 6 + [c_void_p]),
+    "b2_swe_friction_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_void_p]),
+}
+
+
+def _load() -> None:
+    global lib, HAS_CUDA_EXT, CUDA_EXT_ERROR
+    if not _LIB_PATH.exists():
+        CUDA_EXT_ERROR = f"{_LIB_PATH} does not exist"
+        return
+    try:
+        handle = ctypes.CDLL(str(_LIB_PATH))
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        handle.b2_set_print_callback(_print_cb_keepalive)
+    except (OSError, AttributeError) as exc:  # pragma: no cover - build problems
+        CUDA_EXT_ERROR = f"{type(exc).__name__}: {exc}"
+        return
+    lib = handle
+    HAS_CUDA_EXT = True
+
+
+_load()
+
+# python-level logging flag (the CPU backend logs from Python with the same format)
+_logging = False
+
+
+def set_logging(enable: bool) -> None:
+    """Enable/disable the per-call debug log on every backend
+    (reference: xla_bridge/__init__.py:114-125)."""
+    global _logging
+    _logging = bool(enable)
+    if HAS_CUDA_EXT:
+        lib.b2_set_logging(1 if enable else 0)
+
+
+def get_logging() -> bool:
+    return _logging
+
+
+def last_error() -> str:
+    return lib.b2_last_error().decode() if HAS_CUDA_EXT else ""
+
+
+def launch_count() -> int:
+    """Number of native kernels launched by this process (all communicators)."""
+    return int(lib.b2_launch_count()) if HAS_CUDA_EXT else 0
+
+
+NATIVE_ABI_INFO = {
+    "library": str(_LIB_PATH),
+    "loaded": HAS_CUDA_EXT,
+    "version": lib.b2_version().decode() if HAS_CUDA_EXT else None,
+    "arch": "sm_100a",
+    "sizeof_status_record": ctypes.sizeof(B2StatusRecord),
+    "sizeof_halo_desc": ctypes.sizeof(B2HaloDesc),
+}
+
+# reference: MPI4JAX_DEBUG is read at import (xla_bridge/__init__.py:128-129)
+set_logging(env_flag("MPI4JAX_B200_DEBUG", False) or env_flag("MPI4JAX_DEBUG", False))

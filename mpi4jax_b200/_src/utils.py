@@ -1,0 +1,94 @@
+"""Shared helpers of the op layer.
+
+Counterpart of /root/reference/mpi4jax/_src/utils.py:1-174: the ``NOTSET`` sentinel,
+the lazily created default communicator (a private clone of ``COMM_WORLD``), the
+token-argument rejection, dtype support table and the capability probes.  What the
+reference needs in addition -- MPI handle casts and hashable wrappers so that comm/op
+can be static primitive parameters, and the ordered JAX effect -- has no equivalent
+here: ops are ordinary Python calls that enqueue kernels on the current CUDA stream,
+and **stream order is program order**, which is exactly the guarantee the ordered
+effect token provides inside ``jax.jit`` (utils.py:45-53).  The same holds inside
+``mpi4jax_b200.jit`` (CUDA-graph capture preserves stream order).
+"""
+
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from . import comm as _comm
+from .native import codes
+
+NOTSET = object()
+
+_default_comm: Optional[_comm.Comm] = None
+
+
+def get_default_comm() -> _comm.Comm:
+    """A private clone of COMM_WORLD, so library traffic cannot interleave with the
+    user's own messages (reference: utils.py:17-27, docs/sharp-bits.rst:74-135)."""
+    global _default_comm
+    if _default_comm is None or _default_comm._freed:
+        _default_comm = _comm.get_world().Clone()
+    return _default_comm
+
+
+def raise_if_token_is_set(token: Any) -> None:
+    if token is not NOTSET:
+        raise RuntimeError(
+            "Explicit token management is not supported for mpi4jax>=0.8.0. "
+            "Tokens are now managed automatically and must not be passed "
+            "as arguments to collective operations anymore.\n"
+            "That is, please adjust your code like this:\n"
+            "     # For mpi4jax<0.8.0:\n"
+            "     result, token = mpi4jax.allgather(x, token=token)\n"
+            "     # For mpi4jax>=0.8.0:\n"
+            "     result = mpi4jax.allgather(x)"
+        )
+
+
+# dtypes with a wire representation.  The reference supports 14 numpy dtypes and NOT
+# float16/bfloat16 (utils.py:101-128); both 16-bit floats are supported here (fp32
+# accumulation inside the fused reduce kernels); float128 has no GPU representation.
+SUPPORTED_DTYPES = tuple(codes.DTYPE_CODE)
+
+
+def check_dtype(t: torch.Tensor) -> None:
+    if t.dtype not in codes.DTYPE_CODE:
+        raise RuntimeError(f"Unknown MPI type for dtype {t.dtype}")
+
+
+def as_tensor(x: Any, comm: _comm.Comm) -> torch.Tensor:
+    """Accept tensors, numpy arrays and Python scalars (scalars become 0-d tensors, as in
+    the reference's tests, e.g. tests/collective_ops/test_allreduce.py:35-54).  Non-tensor
+    inputs are placed on the communicator's device."""
+    if isinstance(x, torch.Tensor):
+        return x
+    if isinstance(x, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    elif isinstance(x, (bool, int, float, complex, np.generic)):
+        t = torch.tensor(x)
+        if t.dtype == torch.float64 and isinstance(x, float):
+            t = t.to(torch.get_default_dtype())
+    else:
+        t = torch.as_tensor(x)
+    return t.to(comm.device)
+
+
+def backend_of(t: torch.Tensor) -> str:
+    return "cuda" if t.is_cuda else "cpu"
+
+
+def has_cuda_support() -> bool:
+    """True when the native sm_100a library is loaded (reference: utils.py:159-165)."""
+    from . import native
+
+    return bool(native.HAS_CUDA_EXT)
+
+
+def has_sycl_support() -> bool:
+    """Always False: the reference's Intel XPU bridge (utils.py:168-174) is out of scope
+    for a B200-native framework."""
+    return False

@@ -1,0 +1,81 @@
+"""Runtime argument-type checks for the public ops.
+
+Same contract and error-message format as the reference's ``enforce_types``
+(/root/reference/mpi4jax/_src/validation.py:7-93; asserted by
+/root/reference/tests/test_validation.py): numpy abstract scalar types such as
+``np.integer`` accept every matching Python/numpy scalar (``int`` yes, ``bool``
+no), and a helpful hint is added when a *traced / tensor* value is passed where
+a static Python value is required (the analogue of the jax ``Tracer`` hint: here
+a ``torch.Tensor`` or a ``torch.fx.Proxy``).
+"""
+
+from __future__ import annotations
+
+import functools
+import inspect
+from typing import Any, Callable
+
+import numpy as np
+
+
+def _is_traced_value(val: Any) -> bool:
+    try:
+        import torch
+
+        if isinstance(val, torch.Tensor):
+            return True
+        from torch.fx import Proxy
+
+        return isinstance(val, Proxy)
+    except Exception:  # pragma: no cover - torch always importable here
+        return False
+
+
+def _matches(val: Any, expected: type) -> bool:
+    if isinstance(expected, type) and issubclass(expected, np.generic):
+        return bool(np.issubdtype(type(val), expected))
+    return isinstance(val, expected)
+
+
+def enforce_types(**spec: Any) -> Callable:
+    """Decorator: ``@enforce_types(root=(np.integer,), comm=(Comm, type(None)))``."""
+
+    def decorate(fn: Callable) -> Callable:
+        name = fn.__name__
+        sig = inspect.signature(fn)
+        table: dict[str, tuple] = {}
+        for arg, kinds in spec.items():
+            if arg not in sig.parameters:
+                raise ValueError(
+                    f'enforce_types decorator for {name} got unexpected argument "{arg}"'
+                )
+            table[arg] = tuple(kinds) if isinstance(kinds, (tuple, list)) else (kinds,)
+
+        @functools.wraps(fn)
+        def checked(*args, **kwargs):
+            bound = sig.bind(*args, **kwargs)
+            bound.apply_defaults()
+            for arg, kinds in table.items():
+                if arg not in bound.arguments:
+                    continue
+                val = bound.arguments[arg]
+                if any(_matches(val, k) for k in kinds):
+                    continue
+                names = [k.__qualname__ for k in kinds]
+                shown = names[0] if len(names) == 1 else names
+                hint = ""
+                if _is_traced_value(val):
+                    hint = (
+                        "\n\nAn abstract tracer was passed where a concrete value "
+                        "is expected. Pass a Python value (e.g. via functools.partial "
+                        "or a closure) instead of a tensor."
+                    )
+                raise TypeError(
+                    f'{name} got unexpected type for argument "{arg}" '
+                    f"(expected: {shown}, got: {type(val)}).{hint}"
+                )
+            return fn(*args, **kwargs)
+
+        return checked
+
+    return decorate
