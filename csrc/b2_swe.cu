@@ -187,4 +187,60 @@ int b2_swe_friction_v(B2Comm* c, const B2SweParams* p, float* v, const float* fe
   return swe_done(c, "swe_friction_v");
 }
 
+// One call = `nsteps` model steps (5 stencil launches + 4 fused halo exchanges each), all
+// enqueued on `s` without touching the host again: the whole time loop of the reference's
+// `do_multistep` (examples/shallow_water.py:406-411) becomes a launch sequence that CUDA-graph
+// capture turns into a single replayable graph.  `h0`/`h1` ping-pong; the state is returned in
+// h0 (an odd step count ends with one device copy).
+struct B2SweState {
+  float *h0, *h1, *u, *v, *dh, *du, *dv, *fe, *fn, *q, *ke, *fe2, *fn2;
+};
+
+int b2_swe_multistep(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const B2HaloDesc* topo,
+                     int nsteps, int first_step, cudaStream_t s) {
+  B2SweParams p = *p0;
+  float* h = st->h0;
+  float* hn = st->h1;
+  B2HaloDesc d = *topo;
+  d.ny = p.ny;
+  d.nx = p.nx;
+  int rc = 0;
+  for (int it = 0; it < nsteps && rc == 0; ++it) {
+    p.first_step = (first_step && it == 0) ? 1 : 0;
+    if ((rc = b2_swe_fluxes(c, &p, h, st->u, st->v, st->fe, st->fn, st->q, st->ke, s))) break;
+    d.nfields = 4;
+    d.field[0] = st->fe; d.kind[0] = 1;
+    d.field[1] = st->fn; d.kind[1] = 2;
+    d.field[2] = st->q;  d.kind[2] = 0;
+    d.field[3] = st->ke; d.kind[3] = 0;
+    if ((rc = b2_halo_exchange(c, &d, s))) break;
+    if ((rc = b2_swe_tendencies(c, &p, h, hn, st->u, st->v, st->dh, st->du, st->dv, st->fe, st->fn,
+                                st->q, st->ke, s))) break;
+    d.nfields = 3;
+    d.field[0] = hn;    d.kind[0] = 0;
+    d.field[1] = st->u; d.kind[1] = 1;
+    d.field[2] = st->v; d.kind[2] = 2;
+    if ((rc = b2_halo_exchange(c, &d, s))) break;
+    if (p.viscosity > 0.f) {
+      if ((rc = b2_swe_friction_flux_u(c, &p, st->u, st->fe, st->fn, s))) break;
+      d.nfields = 2;
+      d.field[0] = st->fe; d.kind[0] = 1;
+      d.field[1] = st->fn; d.kind[1] = 2;
+      if ((rc = b2_halo_exchange(c, &d, s))) break;
+      if ((rc = b2_swe_friction_u_flux_v(c, &p, st->u, st->v, st->fe, st->fn, st->fe2, st->fn2, s))) break;
+      d.field[0] = st->fe2;
+      d.field[1] = st->fn2;
+      if ((rc = b2_halo_exchange(c, &d, s))) break;
+      if ((rc = b2_swe_friction_v(c, &p, st->v, st->fe2, st->fn2, s))) break;
+    }
+    float* t = h; h = hn; hn = t;
+  }
+  if (rc == 0 && h != st->h0) {
+    cudaError_t e = cudaMemcpyAsync(st->h0, h, (size_t)p.ny * p.nx * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) { b2_set_error("swe_multistep: copy failed: %s", cudaGetErrorString(e)); rc = 1000 + (int)e; }
+  }
+  return rc;
+}
+
 }  // extern "C"

@@ -77,6 +77,11 @@ class B2SweParams(Structure):
     ]
 
 
+class B2SweState(Structure):
+    _fields_ = [(name, c_void_p) for name in
+                ("h0", "h1", "u", "v", "dh", "du", "dv", "fe", "fn", "q", "ke", "fe2", "fn2")]
+
+
 class B2StatusRecord(Structure):
     _fields_ = [
         ("source", c_int),
@@ -156,6 +161,10 @@ _SIGNATURES = {
     "b2_swe_friction_flux_u": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_void_p]),
     "b2_swe_friction_u_flux_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 6 + [c_void_p]),
     "b2_swe_friction_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_void_p]),
+    "b2_swe_multistep": (
+        c_int,
+        [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2HaloDesc), c_int, c_int, c_void_p],
+    ),
 }
 
 

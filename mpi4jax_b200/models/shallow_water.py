@@ -1,0 +1,360 @@
+"""Non-linear shallow-water solver on a 2-D domain decomposition -- the reference's
+flagship workload (/root/reference/examples/shallow_water.py) as a reusable model.
+
+Same discrete system as the reference: C-grid, 1-cell halos, periodic in x, walls in y,
+Adams-Bashforth time stepping, lateral friction, decomposition ``nproc_y = min(P, 2)``,
+``nproc_x = P // nproc_y`` (shallow_water.py:57-107), initial condition = geostrophically
+balanced jet (:138-169).  Two execution paths integrate it:
+
+``backend="native"`` (CUDA tensors)
+    Five fused sm_100a stencil kernels and four fused multi-field halo-exchange kernels per
+    step (csrc/b2_swe.cu, csrc/b2_halo.cu), enqueued by one native call per ``multistep`` and
+    captured into a CUDA graph by :func:`mpi4jax_b200.jit`.  This replaces the reference's
+    per-step sequence of XLA elementwise kernels + 48 blocking MPI custom calls.
+
+``backend="ops"`` (any device)
+    Plain torch arithmetic with halo exchange through the *public* ``sendrecv``/``send``/
+    ``recv`` ops in the reference's west/north/east/south order (:172-264).  It is the
+    fp32 reference implementation the native kernels are tested against, the CPU path, and
+    the demonstration that reference-style user code runs unchanged on this framework.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+from collections import namedtuple
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _src as _ops
+from .._src import native
+from .._src.comm import Comm
+from .._src.utils import get_default_comm
+
+ModelState = namedtuple("ModelState", "h, u, v, dh, du, dv")
+
+SUPPORTED_NPROC = (1, 2, 4, 6, 8, 16)
+
+
+@dataclass
+class ShallowWaterConfig:
+    nx: int = 360                 # global interior cells in x (reference default 360)
+    ny: int = 180                 # global interior cells in y (reference default 180)
+    dx: float = 5e3
+    dy: float = 5e3
+    gravity: float = 9.81
+    depth: float = 100.0
+    coriolis_f: float = 2e-4
+    coriolis_beta: float = 2e-11
+    periodic_x: bool = True
+    ab_a: float = 1.5 + 0.1
+    ab_b: float = -(0.5 + 0.1)
+
+    @property
+    def lateral_viscosity(self) -> float:
+        return 1e-3 * self.coriolis_f * self.dx**2
+
+    @property
+    def dt(self) -> float:
+        return 0.125 * min(self.dx, self.dy) / math.sqrt(self.gravity * self.depth)
+
+
+class ShallowWaterModel:
+    def __init__(self, config: Optional[ShallowWaterConfig] = None, comm: Optional[Comm] = None,
+                 device: Optional[torch.device] = None, backend: str = "auto"):
+        self.cfg = cfg = config or ShallowWaterConfig()
+        self.comm = comm = comm or get_default_comm()
+        self.device = torch.device(device) if device is not None else comm.device
+        if backend == "auto":
+            backend = "native" if self.device.type == "cuda" else "ops"
+        if backend == "native" and self.device.type != "cuda":
+            raise ValueError("backend='native' needs a CUDA device")
+        self.backend = backend
+        size, rank = comm.Get_size(), comm.Get_rank()
+        if size not in SUPPORTED_NPROC:
+            raise RuntimeError(
+                f"Got invalid number of MPI processes: {size}. "
+                f"Please choose one of these: {SUPPORTED_NPROC}."
+            )
+        if not cfg.periodic_x:
+            raise NotImplementedError("only the reference's periodic-x configuration is built in")
+        self.nproc_y = min(size, 2)
+        self.nproc_x = size // self.nproc_y
+        self.proc_idx = tuple(int(i) for i in np.unravel_index(rank, (self.nproc_y, self.nproc_x)))
+        if cfg.nx % self.nproc_x or cfg.ny % self.nproc_y:
+            raise ValueError("the process grid must divide the domain evenly")
+        self.nx_global, self.ny_global = cfg.nx + 2, cfg.ny + 2
+        self.nx_local = cfg.nx // self.nproc_x + 2
+        self.ny_local = cfg.ny // self.nproc_y + 2
+        py, px = self.proc_idx
+        self.local_slice = (
+            slice((self.ny_local - 2) * py, (self.ny_local - 2) * py + self.ny_local),
+            slice((self.nx_local - 2) * px, (self.nx_local - 2) * px + self.nx_local),
+        )
+
+        def flat(iy, ix):
+            return int(np.ravel_multi_index((iy, ix), (self.nproc_y, self.nproc_x)))
+
+        self.neighbors = {
+            "south": flat(py - 1, px) if py > 0 else None,
+            "north": flat(py + 1, px) if py < self.nproc_y - 1 else None,
+            "west": flat(py, (px - 1) % self.nproc_x) if (px > 0 or cfg.periodic_x) else None,
+            "east": flat(py, (px + 1) % self.nproc_x) if (px < self.nproc_x - 1 or cfg.periodic_x) else None,
+        }
+        self.at_north_wall = py == self.nproc_y - 1
+        self.at_south_wall = py == 0
+        self.at_east_wall = px == self.nproc_x - 1
+        self.steps_done = 0
+        self._alloc()
+        self.reset()
+
+    # ------------------------------------------------------------------ setup
+    def _alloc(self) -> None:
+        shape = (self.ny_local, self.nx_local)
+        z = lambda: torch.zeros(shape, dtype=torch.float32, device=self.device)  # noqa: E731
+        self.h, self.u, self.v = z(), z(), z()
+        self.dh, self.du, self.dv = z(), z(), z()
+        self._h1 = z()
+        self.fe, self.fn, self.q, self.ke, self.fe2, self.fn2 = z(), z(), z(), z(), z(), z()
+        y_global = (np.arange(-1, self.ny_global - 1) * self.cfg.dy)
+        cor = self.cfg.coriolis_f + y_global[self.local_slice[0]] * self.cfg.coriolis_beta
+        self.coriolis = torch.tensor(cor, dtype=torch.float32, device=self.device)
+        if self.backend == "native":
+            self._params = native.B2SweParams()
+            p = self._params
+            p.ny, p.nx = self.ny_local, self.nx_local
+            p.dx, p.dy, p.dt = self.cfg.dx, self.cfg.dy, self.cfg.dt
+            p.gravity, p.viscosity = self.cfg.gravity, self.cfg.lateral_viscosity
+            p.ab_a, p.ab_b = self.cfg.ab_a, self.cfg.ab_b
+            p.first_step = 0
+            p.south_wall, p.north_wall = int(self.at_south_wall), int(self.at_north_wall)
+            p.coriolis = self.coriolis.data_ptr()
+            st = self._state = native.B2SweState()
+            st.h0, st.h1 = self.h.data_ptr(), self._h1.data_ptr()
+            for name in ("u", "v", "dh", "du", "dv", "fe", "fn", "q", "ke", "fe2", "fn2"):
+                setattr(st, name, getattr(self, name).data_ptr())
+            t = self._topo = native.B2HaloDesc()
+            nb = self.neighbors
+            t.west = -1 if nb["west"] is None else nb["west"]
+            t.east = -1 if nb["east"] is None else nb["east"]
+            t.south = -1 if nb["south"] is None else nb["south"]
+            t.north = -1 if nb["north"] is None else nb["north"]
+            t.periodic_x = int(self.cfg.periodic_x)
+            t.at_east_wall, t.at_north_wall = int(self.at_east_wall), int(self.at_north_wall)
+            t.ny, t.nx = self.ny_local, self.nx_local
+
+    def initial_conditions_global(self):
+        """Global (ny_global, nx_global) float32 fields of the balanced jet + perturbation
+        (shallow_water.py:138-164)."""
+        cfg = self.cfg
+        x = np.arange(-1, self.nx_global - 1) * cfg.dx
+        y = np.arange(-1, self.ny_global - 1) * cfg.dy
+        yy, xx = np.meshgrid(y, x, indexing="ij")
+        length_x = x[-2] - x[1]
+        length_y = y[-2] - y[1]
+        u0 = (10 * np.exp(-((yy - 0.5 * length_y) ** 2) / (0.02 * length_x) ** 2)).astype(np.float32)
+        v0 = np.zeros_like(u0)
+        cor = (cfg.coriolis_f + yy * cfg.coriolis_beta).astype(np.float32)
+        h_geo = np.cumsum(-cfg.dy * u0 * cor / np.float32(cfg.gravity), axis=0, dtype=np.float32)
+        h0 = (
+            cfg.depth + h_geo - h_geo.mean()
+            + 0.2 * np.sin(xx / length_x * 10 * np.pi) * np.cos(yy / length_y * 8 * np.pi)
+        ).astype(np.float32)
+        return h0, u0, v0
+
+    def reset(self) -> None:
+        h0, u0, v0 = self.initial_conditions_global()
+        sl = self.local_slice
+        self.h.copy_(torch.from_numpy(np.ascontiguousarray(h0[sl])))
+        self.u.copy_(torch.from_numpy(np.ascontiguousarray(u0[sl])))
+        self.v.copy_(torch.from_numpy(np.ascontiguousarray(v0[sl])))
+        for t in (self.dh, self.du, self.dv, self.fe, self.fn, self.q, self.ke, self.fe2, self.fn2):
+            t.zero_()
+        self.enforce_boundaries([self.h, self.u, self.v], ["h", "u", "v"])
+        self.steps_done = 0
+
+    def load_state(self, state: ModelState) -> None:
+        """Overwrite the prognostic fields (e.g. from pinned host memory, non-blocking)."""
+        for dst, src in zip((self.h, self.u, self.v, self.dh, self.du, self.dv), state):
+            dst.copy_(src, non_blocking=True)
+
+    @property
+    def state(self) -> ModelState:
+        return ModelState(self.h, self.u, self.v, self.dh, self.du, self.dv)
+
+    # ------------------------------------------------------------------ halo exchange
+    def enforce_boundaries(self, fields, kinds) -> None:
+        """In-place halo exchange + wall conditions for several fields at once."""
+        if self.backend == "native":
+            nb = self.neighbors
+            g = lambda k: -1 if nb[k] is None else nb[k]  # noqa: E731
+            self.comm._native_comm().halo_exchange(
+                fields, kinds, g("west"), g("east"), g("south"), g("north"),
+                periodic_x=self.cfg.periodic_x, at_east_wall=self.at_east_wall,
+                at_north_wall=self.at_north_wall)
+            return
+        for f, kind in zip(fields, kinds):
+            self._enforce_boundaries_ops(f, kind)
+
+    def _enforce_boundaries_ops(self, arr: torch.Tensor, grid: str) -> None:
+        """Halo exchange with the public p2p ops, in the reference's message order."""
+        send_order = ("west", "north", "east", "south")
+        recv_order = ("east", "south", "west", "north")
+        send_idx = {"south": (1, slice(None)), "west": (slice(None), 1),
+                    "north": (-2, slice(None)), "east": (slice(None), -2)}
+        recv_idx = {"south": (0, slice(None)), "west": (slice(None), 0),
+                    "north": (-1, slice(None)), "east": (slice(None), -1)}
+        for sdir, rdir in zip(send_order, recv_order):
+            sp, rp = self.neighbors[sdir], self.neighbors[rdir]
+            if sp is None and rp is None:
+                continue
+            send_arr = arr[send_idx[sdir]].contiguous()
+            template = torch.empty_like(arr[recv_idx[rdir]].contiguous())
+            if sp is None:
+                arr[recv_idx[rdir]] = _ops.recv(template, source=rp, comm=self.comm)
+            elif rp is None:
+                _ops.send(send_arr, dest=sp, comm=self.comm)
+            else:
+                arr[recv_idx[rdir]] = _ops.sendrecv(send_arr, template, source=rp, dest=sp,
+                                                    comm=self.comm)
+        if not self.cfg.periodic_x and grid == "u" and self.at_east_wall:
+            arr[:, -2] = 0.0
+        if grid == "v" and self.at_north_wall:
+            arr[-2, :] = 0.0
+
+    # ------------------------------------------------------------------ time stepping
+    def step(self, first_step: Optional[bool] = None) -> None:
+        self.multistep(1, first_step=first_step)
+
+    def multistep(self, nsteps: int, first_step: Optional[bool] = None) -> None:
+        """Advance ``nsteps`` model steps (the reference's ``do_multistep``, :406-411)."""
+        if first_step is None:
+            first_step = self.steps_done == 0
+        if self.backend == "native":
+            nc = self.comm._native_comm()
+            rc = native.lib.b2_swe_multistep(
+                nc.handle, ctypes.byref(self._params), ctypes.byref(self._state),
+                ctypes.byref(self._topo), int(nsteps), int(bool(first_step)),
+                torch.cuda.current_stream().cuda_stream)
+            nc._check(rc, "Halo")
+        else:
+            for it in range(nsteps):
+                self._step_ops(first_step and it == 0)
+        self.steps_done += nsteps
+
+    def _step_ops(self, first: bool) -> None:
+        cfg = self.cfg
+        dx, dy, dt, g = cfg.dx, cfg.dy, cfg.dt, cfg.gravity
+        h, u, v = self.h, self.u, self.v
+        C = (slice(1, -1), slice(1, -1))          # centre
+        E = (slice(1, -1), slice(2, None))        # east neighbour
+        W = (slice(1, -1), slice(None, -2))
+        N = (slice(2, None), slice(1, -1))
+        S = (slice(None, -2), slice(1, -1))
+        NE = (slice(2, None), slice(2, None))
+        SE = (slice(None, -2), slice(2, None))
+        NW = (slice(2, None), slice(None, -2))
+
+        hc = torch.nn.functional.pad(h[C][None, None], (1, 1, 1, 1), mode="replicate")[0, 0]
+        self._enforce_boundaries_ops(hc, "h")
+        fe, fn, q, ke = self.fe, self.fn, self.q, self.ke
+        fe[C] = 0.5 * (hc[C] + hc[E]) * u[C]
+        fn[C] = 0.5 * (hc[C] + hc[N]) * v[C]
+        self._enforce_boundaries_ops(fe, "u")
+        self._enforce_boundaries_ops(fn, "v")
+        dh_new = -(fe[C] - fe[W]) / dx - (fn[C] - fn[S]) / dy
+        q[C] = (self.coriolis[1:-1, None] + ((v[E] - v[C]) / dx - (u[N] - u[C]) / dy)) * (
+            1.0 / (0.25 * (hc[C] + hc[E] + hc[N] + hc[NE])))
+        self._enforce_boundaries_ops(q, "h")
+        du_new = -g * (h[E] - h[C]) / dx + 0.5 * (
+            q[C] * 0.5 * (fn[C] + fn[E]) + q[S] * 0.5 * (fn[S] + fn[SE]))
+        dv_new = -g * (h[N] - h[C]) / dy - 0.5 * (
+            q[C] * 0.5 * (fe[C] + fe[N]) + q[W] * 0.5 * (fe[W] + fe[NW]))
+        ke[C] = 0.5 * (0.5 * (u[C] ** 2 + u[W] ** 2) + 0.5 * (v[C] ** 2 + v[S] ** 2))
+        self._enforce_boundaries_ops(ke, "h")
+        du_new = du_new - (ke[E] - ke[C]) / dx
+        dv_new = dv_new - (ke[N] - ke[C]) / dy
+        if first:
+            u[C] += dt * du_new
+            v[C] += dt * dv_new
+            h[C] += dt * dh_new
+        else:
+            u[C] += dt * (cfg.ab_a * du_new + cfg.ab_b * self.du[C])
+            v[C] += dt * (cfg.ab_a * dv_new + cfg.ab_b * self.dv[C])
+            h[C] += dt * (cfg.ab_a * dh_new + cfg.ab_b * self.dh[C])
+        self.dh[C], self.du[C], self.dv[C] = dh_new, du_new, dv_new
+        self._enforce_boundaries_ops(h, "h")
+        self._enforce_boundaries_ops(u, "u")
+        self._enforce_boundaries_ops(v, "v")
+        visc = cfg.lateral_viscosity
+        if visc > 0:
+            fe[C] = visc * (u[E] - u[C]) / dx
+            fn[C] = visc * (u[N] - u[C]) / dy
+            self._enforce_boundaries_ops(fe, "u")
+            self._enforce_boundaries_ops(fn, "v")
+            u[C] += dt * ((fe[C] - fe[W]) / dx + (fn[C] - fn[S]) / dy)
+            fe[C] = visc * (v[E] - u[C]) / dx      # sic: the reference subtracts u here
+            fn[C] = visc * (v[N] - u[C]) / dy
+            self._enforce_boundaries_ops(fe, "u")
+            self._enforce_boundaries_ops(fn, "v")
+            v[C] += dt * ((fe[C] - fe[W]) / dx + (fn[C] - fn[S]) / dy)
+
+    # ------------------------------------------------------------------ diagnostics / IO
+    def total_mass(self) -> torch.Tensor:
+        """Global sum of h over interior cells (conserved up to round-off)."""
+        local = self.h[1:-1, 1:-1].double().sum()
+        return _ops.allreduce(local, _ops.comm.SUM, comm=self.comm)
+
+    def gather_global(self, field: torch.Tensor, root: int = 0) -> Optional[torch.Tensor]:
+        """Reassemble a decomposed field on ``root`` (shallow_water.py:466-491, 579-584)."""
+        parts = _ops.gather(field.contiguous(), root, comm=self.comm)
+        if self.comm.Get_rank() != root:
+            return None
+        out = torch.empty((self.ny_global, self.nx_global), dtype=field.dtype, device=field.device)
+        for r in range(self.comm.Get_size()):
+            iy, ix = np.unravel_index(r, (self.nproc_y, self.nproc_x))
+            sl = (slice((self.ny_local - 2) * iy, (self.ny_local - 2) * iy + self.ny_local),
+                  slice((self.nx_local - 2) * ix, (self.nx_local - 2) * ix + self.nx_local))
+            out[sl] = parts[r]
+        return out
+
+
+def solve_shallow_water(t1: float, num_multisteps: int = 10, config: Optional[ShallowWaterConfig] = None,
+                        comm: Optional[Comm] = None, device=None, backend: str = "auto",
+                        use_graph: bool = True, verbose: bool = True):
+    """Integrate to model time ``t1`` seconds, returning snapshots every ``num_multisteps``
+    steps (the reference's ``solve_shallow_water``, shallow_water.py:414-463)."""
+    import time
+
+    from .. import jit
+
+    model = ShallowWaterModel(config, comm, device, backend)
+    dt = model.cfg.dt
+    sol = [ModelState(*[t.clone() for t in model.state])]
+    model.step(first_step=True)
+    sol.append(ModelState(*[t.clone() for t in model.state]))
+    t = dt
+
+    def advance():
+        model.multistep(num_multisteps, first_step=False)
+
+    run = jit(advance) if (use_graph and model.backend == "native") else advance
+    run()   # warm-up (the reference pre-compiles the same way, :440-441)
+    t += dt * num_multisteps
+    if model.device.type == "cuda":
+        torch.cuda.synchronize()
+    start = time.perf_counter()
+    while t < t1:
+        run()
+        sol.append(ModelState(*[x.clone() for x in model.state]))
+        t += dt * num_multisteps
+    if model.device.type == "cuda":
+        torch.cuda.synchronize()
+    end = time.perf_counter()
+    if verbose and model.comm.Get_rank() == 0:
+        print(f"\nSolution took {end - start:.2f}s")
+    return sol
