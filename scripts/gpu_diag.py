@@ -55,7 +55,13 @@ say("device", dev, torch.cuda.get_device_name(dev), "world", size)
 
 @step("native-init")
 def _():
-    nc = comm._native_comm()
+    try:
+        nc = comm._native_comm()
+    except Exception as exc:
+        say("native init with VMM failed, retrying with cudaIpc:", exc)
+        os.environ["MPI4JAX_B200_HEAP"] = "ipc"
+        comm._native = None
+        nc = comm._native_comm()
     return f"mode={nc.mode} nvls={nc.has_nvls} shared_gpu={nc.shared_gpu}"
 
 
