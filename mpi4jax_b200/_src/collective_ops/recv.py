@@ -16,7 +16,8 @@ import numpy as np
 import torch
 
 from ..comm import ANY_SOURCE, ANY_TAG, Comm, Status
-from ..utils import NOTSET, as_tensor, check_dtype, get_default_comm, raise_if_token_is_set
+from ..utils import (NOTSET, as_tensor, check_dtype, check_rank, get_default_comm,
+                     raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
 
@@ -58,4 +59,5 @@ def recv(x, source=ANY_SOURCE, *, tag=ANY_TAG, comm=None, status=None, token=NOT
         comm = get_default_comm()
     x = as_tensor(x, comm)
     check_dtype(x)
+    check_rank(int(source), comm, "Recv", "source", allow_any=True)
     return _Recv.apply(x, int(source), int(tag), comm, status)

@@ -16,7 +16,8 @@ import numpy as np
 import torch
 
 from ..comm import Comm
-from ..utils import NOTSET, as_tensor, check_dtype, get_default_comm, raise_if_token_is_set
+from ..utils import (NOTSET, as_tensor, check_dtype, check_rank, get_default_comm,
+                     raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
 
@@ -51,6 +52,7 @@ def send(x, dest, *, tag=0, comm=None, token=NOTSET):
         comm = get_default_comm()
     x = as_tensor(x, comm)
     check_dtype(x)
+    check_rank(int(dest), comm, "Send", "destination")
     _dispatch.send(comm, x.detach(), int(dest), int(tag))
 
 
@@ -62,4 +64,5 @@ def send_with_grad(x, dest, *, tag=0, comm=None):
         comm = get_default_comm()
     x = as_tensor(x, comm)
     check_dtype(x)
+    check_rank(int(dest), comm, "Send", "destination")
     return _SendWithGrad.apply(x, int(dest), int(tag), comm)

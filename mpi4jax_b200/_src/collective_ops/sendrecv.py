@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 from ..comm import ANY_TAG, Comm, Status
-from ..utils import NOTSET, as_tensor, check_dtype, get_default_comm, raise_if_token_is_set
+from ..utils import (NOTSET, as_tensor, check_dtype, check_rank, get_default_comm,
+                     raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
 
@@ -88,5 +89,7 @@ def sendrecv(sendbuf, recvbuf, source, dest, *, sendtag=0, recvtag=ANY_TAG, comm
     recvbuf = as_tensor(recvbuf, comm)
     check_dtype(sendbuf)
     check_dtype(recvbuf)
+    check_rank(int(dest), comm, "Sendrecv", "destination")
+    check_rank(int(source), comm, "Sendrecv", "source", allow_any=True)
     return _Sendrecv.apply(sendbuf, recvbuf, int(source), int(dest), int(sendtag), int(recvtag),
                            comm, status)

@@ -74,10 +74,17 @@ class _Captured:
     __slots__ = ("graph", "static_in", "out_spec", "static_out")
 
 
-def jit(fn: Callable = None, *, donate_outputs: bool = False, warmup: int = 1) -> Callable:
-    """Decorator / wrapper: ``fast = mpi4jax_b200.jit(fn)``."""
+def jit(fn: Callable = None, *, donate_outputs: bool = False, static_inputs: bool = False,
+        warmup: int = 1) -> Callable:
+    """Decorator / wrapper: ``fast = mpi4jax_b200.jit(fn)``.
+
+    ``donate_outputs``: return the graph's own output buffers (overwritten by the next call)
+    instead of clones.  ``static_inputs``: capture the caller's tensors themselves as the graph
+    inputs (no copy-in; later calls must pass the same storage, or pay one copy).
+    """
     if fn is None:
-        return functools.partial(jit, donate_outputs=donate_outputs, warmup=warmup)
+        return functools.partial(jit, donate_outputs=donate_outputs, static_inputs=static_inputs,
+                                 warmup=warmup)
 
     cache: dict = {}
     calls: dict = {}
@@ -99,7 +106,7 @@ def jit(fn: Callable = None, *, donate_outputs: bool = False, warmup: int = 1) -
             return fn(*args, **kwargs)
         cap = cache.get(key)
         if cap is None:
-            cap = _capture(fn, spec, leaves)
+            cap = _capture(fn, spec, leaves, static_inputs)
             cache[key] = cap
         else:
             for dst, src in zip(cap.static_in, leaves):
@@ -120,9 +127,9 @@ def _default_device_is_cuda() -> bool:
     return get_default_comm().device.type == "cuda"
 
 
-def _capture(fn, spec, leaves) -> _Captured:
+def _capture(fn, spec, leaves, static_inputs: bool = False) -> _Captured:
     cap = _Captured()
-    cap.static_in = [t.clone() if t.is_cuda else t for t in leaves]
+    cap.static_in = [t.clone() if (t.is_cuda and not static_inputs) else t for t in leaves]
     a, k = _unflatten(spec, cap.static_in)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()

@@ -92,3 +92,20 @@ def has_sycl_support() -> bool:
     """Always False: the reference's Intel XPU bridge (utils.py:168-174) is out of scope
     for a B200-native framework."""
     return False
+
+
+def check_rank(value: int, comm: _comm.Comm, opname: str, what: str, allow_any: bool = False) -> None:
+    """Fail fast on an out-of-range peer rank, like the reference's abort_on_error path does
+    when MPI reports MPI_ERR_RANK (mpi_ops_common.h:60-78; exercised by
+    tests/collective_ops/test_common.py:60-88): prints
+    ``r<rank> | MPI_<Op> returned error code 6: ... - aborting`` and aborts (or raises
+    MPIError when MPI4JAX_B200_ABORT_ON_ERROR=0)."""
+    if allow_any and value == _comm.ANY_SOURCE:
+        return
+    if 0 <= value < comm.Get_size():
+        return
+    from .backends.cuda import abort_or_raise
+
+    abort_or_raise(
+        f"r{comm.Get_rank()} | MPI_{opname} returned error code 6: invalid {what} rank {value} "
+        f"(communicator size {comm.Get_size()}) - aborting", 6)
