@@ -98,7 +98,7 @@ def main() -> int:
     K, W = ns.steps, max(ns.warmup, 3)
     dev = comm.device
 
-    model = ShallowWaterModel(ShallowWaterConfig(nx=ns.grid, ny=ns.grid), comm=comm, device=dev,
+    model = ShallowWaterModel(ShallowWaterConfig.for_resolution(ns.grid, ns.grid), comm=comm, device=dev,
                               backend="native")
     model.step(first_step=True)
 
@@ -208,7 +208,7 @@ def main() -> int:
             "impl": "ours",
             "config": {
                 "model": "examples/shallow_water.py (non-linear shallow water, C-grid, AB2)",
-                "global_batch": f"{ns.grid}x{ns.grid} grid",
+                "global_batch": f"{ns.grid}x{ns.grid} grid (the demo's 1800 km x 900 km domain)",
                 "seq_len": None,
                 "parallelism": f"2-D domain decomposition {model.nproc_y}x{model.nproc_x}",
                 "l2": ("L2 flushed before the timed region; per-rank state "

@@ -101,10 +101,10 @@ static inline size_t b2_dtype_size(int dt) {
 //   [flags]      B2_MAX_BLOCKS x B2_MAX_RANKS u32   block-paired barrier flags
 //   [p2p hdr]    P x NSLOT x LANES x 16 B           inbox headers (written by the sender)
 //   [p2p ack]    P x NSLOT x LANES x 4 B            slot credits  (written by the receiver)
-//   [halo flags] 2 phases x 4 dirs x 2 parities     fused halo exchange
+//   [halo flags] 8 sides x 64 B                     fused halo exchange (arrival counters)
 //   [ll]         2 parities x P x ll_cap            flag-in-data allreduce buffers
 //   [p2p slots]  P x NSLOT x slot_bytes             eager/streaming payload ring
-//   [halo bufs]  2 parities x 4 dirs x halo_cap
+//   [halo bufs]  2 parities x 8 sides x halo_cap
 //   -- separate, growable segment --
 //   [staging]    2 parities x stage_half            collective staging
 // ---------------------------------------------------------------------------
@@ -135,7 +135,8 @@ struct B2DevComm {
   B2Layout lay;
   // local (non-symmetric) device memory
   unsigned* epoch;                      // [B2_MAX_BLOCKS] per-CTA barrier epochs
-  unsigned* ticket;                     // [0]=collective ticket [1]=arrive ctr [2]=halo ticket [3]=halo arrive
+  unsigned* ticket;                     // [0] collective ticket [1] finish ctr [3] halo finish ctr
+                                        // [8..15] halo msgs received per side [16..23] sent per side
   unsigned* p2p_send_seq;               // [P] fragments sent to each destination
   unsigned* p2p_recv_seq;               // [P] fragments consumed from each source
   unsigned* p2p_ctl;                    // [8] arrive counters / any-source election word

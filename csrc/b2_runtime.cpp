@@ -357,13 +357,13 @@ static B2Layout make_layout(int nranks, size_t slot_bytes, size_t ll_cap, size_t
   L.flags_off = take((size_t)B2_MAX_BLOCKS * B2_MAX_RANKS * 4);
   L.p2p_hdr_off = take((size_t)nranks * B2_P2P_NSLOT * B2_P2P_MAX_LANES * 16);
   L.p2p_ack_off = take((size_t)nranks * B2_P2P_NSLOT * 4);
-  L.halo_flag_off = take(2 * 4 * 2 * 64);
+  L.halo_flag_off = take(8 * 64);
   L.ll_cap = round_up(ll_cap, 4096);
   L.ll_off = take(2 * (size_t)nranks * L.ll_cap);
   L.p2p_slot_bytes = round_up(slot_bytes, 4096);
   L.p2p_slot_off = take((size_t)nranks * B2_P2P_NSLOT * L.p2p_slot_bytes);
   L.halo_cap = round_up(halo_cap, 4096);
-  L.halo_buf_off = take(2 * 4 * L.halo_cap);
+  L.halo_buf_off = take(2 * 8 * L.halo_cap);
   L.total = off;
   return L;
 }
@@ -394,7 +394,7 @@ extern "C" B2Comm* b2_comm_create(int device, int rank, int nranks, B2Seg* ctl, 
   d.lay = L;
   for (int p = 0; p < nranks; ++p) d.heap[p] = (char*)ctl->ptr[p];
   // local counters: epoch[B2_MAX_BLOCKS] | ticket[8] | send_seq[16] | recv_seq[16] | p2p_ctl[32]
-  const size_t nwords = B2_MAX_BLOCKS + 8 + B2_MAX_RANKS + B2_MAX_RANKS + 32;
+  const size_t nwords = B2_MAX_BLOCKS + 32 + B2_MAX_RANKS + B2_MAX_RANKS + 32;
   unsigned* local = nullptr;
   if (cudaMalloc(&local, nwords * 4) != cudaSuccess || cudaMemset(local, 0, nwords * 4) != cudaSuccess) {
     b2_set_error("allocating local counters failed");
@@ -403,7 +403,7 @@ extern "C" B2Comm* b2_comm_create(int device, int rank, int nranks, B2Seg* ctl, 
   }
   d.epoch = local;
   d.ticket = local + B2_MAX_BLOCKS;
-  d.p2p_send_seq = d.ticket + 8;
+  d.p2p_send_seq = d.ticket + 32;
   d.p2p_recv_seq = d.p2p_send_seq + B2_MAX_RANKS;
   d.p2p_ctl = d.p2p_recv_seq + B2_MAX_RANKS;
   // any-source election generation starts at 1 (0 would match the zero-filled word)

@@ -140,7 +140,9 @@ struct B2HaloDesc {
   float* field[B2_HALO_MAX_FIELDS];   // (ny, nx) row-major fp32 arrays with a 1-cell halo
   int kind[B2_HALO_MAX_FIELDS];       // 0 = "h", 1 = "u", 2 = "v"  (wall conditions)
   int ny, nx;
+  int pitch;                          // row pitch in floats (>= nx)
   int west, east, south, north;       // neighbour ranks, -1 = wall
+  int sw, se, nw, ne;                 // diagonal neighbours (-1 where south/north is a wall)
   int periodic_x;
   int at_east_wall;                   // last column of processes (u wall, non-periodic only)
   int at_north_wall;                  // last row of processes (v wall)

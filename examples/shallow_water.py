@@ -87,7 +87,8 @@ def main(argv=None):
 
     comm = MPI.COMM_WORLD
     days = ns.days if ns.days is not None else (0.1 if ns.benchmark else 10.0)
-    cfg = ShallowWaterConfig(nx=ns.nx, ny=ns.ny)
+    cfg = (ShallowWaterConfig(nx=ns.nx, ny=ns.ny) if (ns.nx, ns.ny) == (360, 180)
+           else ShallowWaterConfig.for_resolution(ns.nx, ns.ny))
     sol = solve_shallow_water(t1=days * DAY_IN_SECONDS, num_multisteps=PLOT_EVERY, config=cfg,
                               comm=comm, backend=ns.backend)
     if ns.benchmark:

@@ -240,6 +240,7 @@ class NativeComm:
         if not self.handle:
             raise MPIError(f"native communicator creation failed: {native.last_error()}")
         self.stage: Optional[_Segment] = None
+        self._stage_half = 0
         self._retired: list = []
         self._status_pool: list = []
         self._grow_stage(_MIN_STAGE)
@@ -261,14 +262,17 @@ class NativeComm:
         torch.cuda.synchronize()
         new = _Segment(self.comm, self.device, size, self.mode, want_mc=self.want_mc)
         lib.b2_comm_set_stage(self.handle, new.seg, new.mc)
+        self._stage_half = int(lib.b2_comm_stage_half(self.handle))
         old, self.stage = self.stage, new
         if old is not None:
             old.destroy()
 
     def ensure_stage(self, opcode: int, blk_bytes: int) -> None:
-        lib = _lib()
-        need = int(lib.b2_stage_need(opcode, self.comm.size, blk_bytes))
-        if need > int(lib.b2_comm_stage_half(self.handle)):
+        # same formula as b2_stage_need() (csrc/b2_collectives.cu), evaluated without leaving Python
+        stride = (blk_bytes + 15) & ~15
+        mult = self.comm.size if opcode in (codes.OPC_ALLTOALL, codes.OPC_SCATTER) else 1
+        need = stride * mult + 4096
+        if need > self._stage_half:
             self._grow_stage(2 * need + 8192)
 
     @property
@@ -458,17 +462,22 @@ class NativeComm:
 
     # -- fused halo exchange ---------------------------------------------------------
     def halo_exchange(self, fields, kinds, west, east, south, north, periodic_x=True,
-                      at_east_wall=False, at_north_wall=False) -> None:
+                      at_east_wall=False, at_north_wall=False, sw=-1, se=-1, nw=-1, ne=-1) -> None:
+        """Fused single-phase 8-neighbour halo exchange (csrc/b2_halo.cu).  ``fields`` are
+        float32 ``(ny, nx)`` tensors with unit inner stride and a common row pitch."""
         d = native.B2HaloDesc()
         d.nfields = len(fields)
         ny, nx = fields[0].shape
+        pitch = fields[0].stride(0)
         for k, (f, kind) in enumerate(zip(fields, kinds)):
-            if f.dtype != torch.float32 or not f.is_contiguous() or tuple(f.shape) != (ny, nx):
-                raise ValueError("halo_exchange needs contiguous float32 fields of one shape")
+            if (f.dtype != torch.float32 or tuple(f.shape) != (ny, nx) or f.stride(1) != 1
+                    or f.stride(0) != pitch):
+                raise ValueError("halo_exchange needs float32 fields of one shape and row pitch")
             d.field[k] = f.data_ptr()
             d.kind[k] = {"h": 0, "u": 1, "v": 2}[kind]
-        d.ny, d.nx = ny, nx
+        d.ny, d.nx, d.pitch = ny, nx, pitch
         d.west, d.east, d.south, d.north = west, east, south, north
+        d.sw, d.se, d.nw, d.ne = sw, se, nw, ne
         d.periodic_x = int(periodic_x)
         d.at_east_wall = int(at_east_wall)
         d.at_north_wall = int(at_north_wall)

@@ -11,7 +11,8 @@ from __future__ import annotations
 import torch
 
 from ..comm import SUM, Comm
-from ..utils import NOTSET, as_tensor, check_dtype, get_default_comm, raise_if_token_is_set
+from ..utils import (NOTSET, as_tensor, check_dtype, get_default_comm, needs_autograd,
+                     raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
 
@@ -45,4 +46,6 @@ def allgather(x, *, comm=None, token=NOTSET):
         comm = get_default_comm()
     x = as_tensor(x, comm)
     check_dtype(x)
+    if not needs_autograd(x):
+        return _dispatch.allgather(comm, x)
     return _Allgather.apply(x, comm)

@@ -13,7 +13,8 @@ import torch
 
 from ..comm import OP_TYPES, SUM, Comm, Op, as_op
 from ..native import codes
-from ..utils import NOTSET, as_tensor, check_dtype, get_default_comm, raise_if_token_is_set
+from ..utils import (NOTSET, as_tensor, check_dtype, get_default_comm, needs_autograd,
+                     raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
 
@@ -74,4 +75,7 @@ def allreduce(x, op, *, comm=None, token=NOTSET, algorithm="auto"):
     op = as_op(op)
     x = as_tensor(x, comm)
     check_dtype(x)
-    return _Allreduce.apply(x, op, comm, False, codes.ALGO_BY_NAME[algorithm])
+    algo = codes.ALGO_BY_NAME[algorithm]
+    if not needs_autograd(x):
+        return _dispatch.allreduce(comm, x, op.code, algo)
+    return _Allreduce.apply(x, op, comm, False, algo)

@@ -10,7 +10,8 @@ from __future__ import annotations
 import torch
 
 from ..comm import Comm
-from ..utils import NOTSET, as_tensor, check_dtype, get_default_comm, raise_if_token_is_set
+from ..utils import (NOTSET, as_tensor, check_dtype, get_default_comm, needs_autograd,
+                     raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
 
@@ -46,4 +47,6 @@ def alltoall(x, *, comm=None, token=NOTSET):
     check_dtype(x)
     if x.dim() == 0 or x.shape[0] != comm.Get_size():
         raise ValueError("Alltoall input must have shape (nproc, ...)")
+    if not needs_autograd(x):
+        return _dispatch.alltoall(comm, x)
     return _Alltoall.apply(x, comm)

@@ -13,7 +13,8 @@ import numpy as np
 import torch
 
 from ..comm import SUM, Comm
-from ..utils import NOTSET, as_tensor, check_dtype, get_default_comm, raise_if_token_is_set
+from ..utils import (NOTSET, as_tensor, check_dtype, get_default_comm, needs_autograd,
+                     raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
 
@@ -53,6 +54,9 @@ def bcast(x, root, *, comm=None, token=NOTSET):
     x = as_tensor(x, comm)
     check_dtype(x)
     _check_root(root, comm, "Bcast")
+    if not needs_autograd(x):
+        out = _dispatch.bcast(comm, x, int(root))
+        return x if comm.Get_rank() == root else out
     return _Bcast.apply(x, int(root), comm)
 
 

@@ -17,7 +17,7 @@ import torch
 
 from ..comm import ANY_SOURCE, ANY_TAG, Comm, Status
 from ..utils import (NOTSET, as_tensor, check_dtype, check_rank, get_default_comm,
-                     raise_if_token_is_set)
+                     needs_autograd, raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
 
@@ -60,4 +60,6 @@ def recv(x, source=ANY_SOURCE, *, tag=ANY_TAG, comm=None, status=None, token=NOT
     x = as_tensor(x, comm)
     check_dtype(x)
     check_rank(int(source), comm, "Recv", "source", allow_any=True)
+    if not needs_autograd(x):
+        return _dispatch.recv(comm, x, int(source), int(tag), status)
     return _Recv.apply(x, int(source), int(tag), comm, status)

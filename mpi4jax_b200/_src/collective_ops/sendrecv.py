@@ -15,7 +15,7 @@ import torch
 
 from ..comm import ANY_TAG, Comm, Status
 from ..utils import (NOTSET, as_tensor, check_dtype, check_rank, get_default_comm,
-                     raise_if_token_is_set)
+                     needs_autograd, raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
 
@@ -91,5 +91,8 @@ def sendrecv(sendbuf, recvbuf, source, dest, *, sendtag=0, recvtag=ANY_TAG, comm
     check_dtype(recvbuf)
     check_rank(int(dest), comm, "Sendrecv", "destination")
     check_rank(int(source), comm, "Sendrecv", "source", allow_any=True)
+    if not needs_autograd(sendbuf, recvbuf):
+        return _dispatch.sendrecv(comm, sendbuf, recvbuf, int(source), int(dest), int(sendtag),
+                                  int(recvtag), status)
     return _Sendrecv.apply(sendbuf, recvbuf, int(source), int(dest), int(sendtag), int(recvtag),
                            comm, status)

@@ -49,10 +49,15 @@ class B2HaloDesc(Structure):
         ("kind", c_int * 8),
         ("ny", c_int),
         ("nx", c_int),
+        ("pitch", c_int),
         ("west", c_int),
         ("east", c_int),
         ("south", c_int),
         ("north", c_int),
+        ("sw", c_int),
+        ("se", c_int),
+        ("nw", c_int),
+        ("ne", c_int),
         ("periodic_x", c_int),
         ("at_east_wall", c_int),
         ("at_north_wall", c_int),
@@ -63,6 +68,7 @@ class B2SweParams(Structure):
     _fields_ = [
         ("ny", c_int),
         ("nx", c_int),
+        ("pitch", c_int),
         ("dx", c_float),
         ("dy", c_float),
         ("dt", c_float),

@@ -77,6 +77,23 @@ def as_tensor(x: Any, comm: _comm.Comm) -> torch.Tensor:
     return t.to(comm.device)
 
 
+_functorch = torch._C._functorch
+
+
+def needs_autograd(*tensors) -> bool:
+    """True when an op must go through its ``torch.autograd.Function`` (reverse-mode graph
+    recording, or any active torch.func transform: vmap / grad / jvp / vjp).  Otherwise ops
+    call their backend directly -- ``Function.apply`` alone costs ~25 us, an order of
+    magnitude more than a small-message collective."""
+    if _functorch.peek_interpreter_stack() is not None:
+        return True
+    if torch.is_grad_enabled():
+        for t in tensors:
+            if t.requires_grad:
+                return True
+    return torch.autograd.forward_ad._current_level >= 0
+
+
 def backend_of(t: torch.Tensor) -> str:
     return "cuda" if t.is_cuda else "cpu"
 

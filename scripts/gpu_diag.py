@@ -250,7 +250,7 @@ def _():
         us = timeit(lambda: m.sendrecv(x, x, source=(rank - 1) % size, dest=(rank + 1) % size, comm=comm), iters=20)
         out.append(f"sendrecv {nbytes}B {us:.1f}us {nbytes / us / 1e3:.1f}GB/s")
     from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
-    mod = ShallowWaterModel(ShallowWaterConfig(nx=4096, ny=4096), comm=comm, device=dev)
+    mod = ShallowWaterModel(ShallowWaterConfig.for_resolution(4096, 4096), comm=comm, device=dev)
     us = timeit(lambda: mod.enforce_boundaries([mod.fe, mod.fn, mod.q, mod.ke], ["u", "v", "h", "h"]), iters=50)
     out.append(f"halo4 {us:.1f}us")
     run = m.jit(lambda: mod.multistep(20, first_step=False))
