@@ -56,7 +56,7 @@ def test_native_kernels_match_ops_path():
         scale = y.abs().max().item() + 1e-30
         # tendencies are differences of O(1e3) fluxes: fp32 rounding (FMA contraction in the
         # CUDA kernels vs separate mul/add in torch) shows up at the 1e-4 level there
-        tol = 5e-5 if name in ("h", "u", "v") else 2e-3
+        tol = 2e-4 if name in ("h", "u", "v") else 2e-3
         assert (x - y).abs().max().item() / scale < tol, name
 
 

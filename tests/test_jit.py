@@ -24,10 +24,11 @@ def test_jit_pytree_and_static_args(device):
         res = f({"a": a + i, "b": b}, 2.0)
         assert torch.equal(res["sum"], (a + i + b) * size * 2.0)
         assert torch.equal(res["pair"][0], a + i)
-    res = f({"a": a, "b": b}, 2.0, flag=False)        # new static arg -> new graph
-    assert torch.equal(res["pair"][1], b)
+    for _ in range(2):                                # new static arg -> warm-up, then a new graph
+        res = f({"a": a, "b": b}, 2.0, flag=False)
+        assert torch.equal(res["pair"][1], b)
     if device.type == "cuda":
-        assert len(calls) < 7          # replays do not re-run Python
+        assert len(calls) < 8          # replays do not re-run Python
         assert len(f._cache) == 2
 
 
