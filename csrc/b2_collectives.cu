@@ -66,6 +66,7 @@ struct B2MoveArgs {
   int src_blk[B2_MAX_RANKS];
   int dst_blk[B2_MAX_RANKS];
   int opcode;
+  int vec_ok;           // out and every block offset are 16-byte aligned -> batched vector pulls
 };
 
 __global__ void __launch_bounds__(B2_THREADS)
@@ -85,11 +86,41 @@ b2_k_move(const B2DevComm c, const B2MoveArgs a) {
       b2_copy_bytes<false>(mine + (size_t)j * a.blk_stride + off,
                            in + (size_t)j * a.blk_bytes + off, len);
     b2_barrier_all(c, ++e, a.opcode);
-    for (int s = 0; s < a.nsrc; ++s) {
-      const int k = (s + c.rank) % a.nsrc;      // stagger peers across ranks
-      b2_copy_bytes<true>(out + (size_t)a.dst_blk[k] * a.blk_bytes + off,
-                          c.stage[a.src_rank[k]] + par + (size_t)a.src_blk[k] * a.blk_stride + off,
-                          len);
+    if (a.vec_ok) {
+      // all sources of a vector are loaded before any is stored: the NVLink round trips of the
+      // P pulls overlap instead of adding up (one latency instead of P)
+      const size_t nv = len >> 4, tail = len & 15;
+      for (size_t i = threadIdx.x; i < nv; i += blockDim.x) {
+        uint4 v[B2_MAX_RANKS];
+#pragma unroll
+        for (int s = 0; s < B2_MAX_RANKS; ++s)
+          if (s < a.nsrc) {
+            const int k = (s + c.rank) % a.nsrc;      // stagger peers across ranks
+            v[s] = b2_ld_peer16(c.stage[a.src_rank[k]] + par + (size_t)a.src_blk[k] * a.blk_stride +
+                                off + (i << 4));
+          }
+#pragma unroll
+        for (int s = 0; s < B2_MAX_RANKS; ++s)
+          if (s < a.nsrc) {
+            const int k = (s + c.rank) % a.nsrc;
+            b2_st16(out + (size_t)a.dst_blk[k] * a.blk_bytes + off + (i << 4), v[s]);
+          }
+      }
+      if (tail) {
+        for (int s = 0; s < a.nsrc; ++s)
+          if (threadIdx.x < tail) {
+            const size_t b = (nv << 4) + threadIdx.x;
+            out[(size_t)a.dst_blk[s] * a.blk_bytes + off + b] =
+                ((const volatile char*)(c.stage[a.src_rank[s]] + par + (size_t)a.src_blk[s] * a.blk_stride + off))[b];
+          }
+      }
+    } else {
+      for (int s = 0; s < a.nsrc; ++s) {
+        const int k = (s + c.rank) % a.nsrc;
+        b2_copy_bytes<true>(out + (size_t)a.dst_blk[k] * a.blk_bytes + off,
+                            c.stage[a.src_rank[k]] + par + (size_t)a.src_blk[k] * a.blk_stride + off,
+                            len);
+      }
     }
   }
   __syncthreads();
@@ -176,7 +207,9 @@ static void pick_chunks(const B2Comm* c, size_t nbytes, size_t* chunk_out, int* 
   const size_t min_chunk = round_up(16 * 1024, unit);
   const size_t max_chunk = round_up(512 * 1024, unit);
   const size_t target = (size_t)c->max_blocks;
-  size_t chunk = round_up((nbytes + target - 1) / target, unit);
+  // aim for ~4 chunks per CTA: CTAs then sit at different phases (copy-in / reduce-scatter /
+  // all-gather / copy-out), which overlaps local HBM traffic with both NVLink directions
+  size_t chunk = round_up((nbytes + 4 * target - 1) / (4 * target), unit);
   if (chunk < min_chunk) chunk = min_chunk;
   if (chunk > max_chunk) chunk = max_chunk;
   size_t nchunks = (nbytes + chunk - 1) / chunk;
@@ -239,9 +272,10 @@ static int reduce_common(B2Comm* c, const void* in, void* out, size_t count, int
   if (algo == B2_ALGO_AUTO) {
     if (opcode != B2_OPC_ALLREDUCE) algo = B2_ALGO_ONESHOT;
     else if (P > 1 && nbytes <= c->ll_max && nbytes * 2 <= c->dev.lay.ll_cap) algo = B2_ALGO_LL;
-    else if (P <= 2 || nbytes <= c->oneshot_max) algo = B2_ALGO_ONESHOT;
+    else if (P <= 2) algo = B2_ALGO_ONESHOT;
     else if (c->dev.stage_mc != nullptr && op == B2_SUM && nbytes >= c->nvls_min &&
              (dtype == B2_F32 || dtype == B2_BF16 || dtype == B2_F16)) algo = B2_ALGO_NVLS;
+    else if (nbytes <= c->oneshot_max) algo = B2_ALGO_ONESHOT;
     else algo = B2_ALGO_TWOSHOT;
   }
   if (algo == B2_ALGO_LL) {
@@ -326,6 +360,7 @@ static int move_common(B2Comm* c, B2MoveArgs& a, const char* name, cudaStream_t 
   int rc = check_stage(c, a.opcode, a.blk_bytes, name);
   if (rc) return rc;
   a.blk_stride = round_up(a.blk_bytes, 16);
+  a.vec_ok = ((((uintptr_t)a.out) & 15) == 0 && (a.blk_bytes % 16 == 0 || a.nsrc <= 1)) ? 1 : 0;
   int grid;
   pick_chunks(c, a.blk_bytes, &a.chunk, &grid);
   b2_k_move<<<grid, B2_THREADS, 0, stream>>>(c->dev, a);

@@ -105,6 +105,7 @@ static inline size_t b2_dtype_size(int dt) {
 //   [ll]         2 parities x P x ll_cap            flag-in-data allreduce buffers
 //   [p2p slots]  P x NSLOT x slot_bytes             eager/streaming payload ring
 //   [halo bufs]  2 parities x 8 sides x halo_cap
+//   [halo LL]    2 parities x 8 sides x 2*halo_cap  (fused stencil+halo kernels)
 //   -- separate, growable segment --
 //   [staging]    2 parities x stage_half            collective staging
 // ---------------------------------------------------------------------------
@@ -119,6 +120,8 @@ struct B2Layout {
   size_t p2p_slot_bytes;
   size_t halo_buf_off;
   size_t halo_cap;        // bytes per (parity, direction)
+  size_t halo_ll_off;     // flag-in-data halo buffers of the fused stencil kernels
+  size_t halo_ll_cap;     // bytes per (parity, side): 8 B per element
   size_t total;
 };
 
@@ -137,6 +140,7 @@ struct B2DevComm {
   unsigned* epoch;                      // [B2_MAX_BLOCKS] per-CTA barrier epochs
   unsigned* ticket;                     // [0] collective ticket [1] finish ctr [3] halo finish ctr
                                         // [8..15] halo msgs received per side [16..23] sent per side
+                                        // [5] fused-halo ready ctr [6] finish ctr [32..47] fused rx/tx
   unsigned* p2p_send_seq;               // [P] fragments sent to each destination
   unsigned* p2p_recv_seq;               // [P] fragments consumed from each source
   unsigned* p2p_ctl;                    // [8] arrive counters / any-source election word

@@ -364,6 +364,8 @@ static B2Layout make_layout(int nranks, size_t slot_bytes, size_t ll_cap, size_t
   L.p2p_slot_off = take((size_t)nranks * B2_P2P_NSLOT * L.p2p_slot_bytes);
   L.halo_cap = round_up(halo_cap, 4096);
   L.halo_buf_off = take(2 * 8 * L.halo_cap);
+  L.halo_ll_cap = 2 * L.halo_cap;
+  L.halo_ll_off = take(2 * 8 * L.halo_ll_cap);
   L.total = off;
   return L;
 }
@@ -394,7 +396,7 @@ extern "C" B2Comm* b2_comm_create(int device, int rank, int nranks, B2Seg* ctl, 
   d.lay = L;
   for (int p = 0; p < nranks; ++p) d.heap[p] = (char*)ctl->ptr[p];
   // local counters: epoch[B2_MAX_BLOCKS] | ticket[8] | send_seq[16] | recv_seq[16] | p2p_ctl[32]
-  const size_t nwords = B2_MAX_BLOCKS + 32 + B2_MAX_RANKS + B2_MAX_RANKS + 32;
+  const size_t nwords = B2_MAX_BLOCKS + 64 + B2_MAX_RANKS + B2_MAX_RANKS + 32;
   unsigned* local = nullptr;
   if (cudaMalloc(&local, nwords * 4) != cudaSuccess || cudaMemset(local, 0, nwords * 4) != cudaSuccess) {
     b2_set_error("allocating local counters failed");
@@ -403,7 +405,7 @@ extern "C" B2Comm* b2_comm_create(int device, int rank, int nranks, B2Seg* ctl, 
   }
   d.epoch = local;
   d.ticket = local + B2_MAX_BLOCKS;
-  d.p2p_send_seq = d.ticket + 32;
+  d.p2p_send_seq = d.ticket + 64;
   d.p2p_recv_seq = d.p2p_send_seq + B2_MAX_RANKS;
   d.p2p_ctl = d.p2p_recv_seq + B2_MAX_RANKS;
   // any-source election generation starts at 1 (0 would match the zero-filled word)
@@ -421,9 +423,12 @@ extern "C" B2Comm* b2_comm_create(int device, int rank, int nranks, B2Seg* ctl, 
   void* edev = nullptr;
   cudaHostGetDevicePointer(&edev, (void*)eh, 0);
   d.err = (B2ErrorRecord*)edev;
-  c->ll_max = 32 * 1024;
-  c->oneshot_max = 256 * 1024;
-  c->nvls_min = 256 * 1024;
+  // measured on 8 x B200 (profiles/r1_collectives_sweep_8gpu_v1.json): LL wins up to its 64 KiB
+  // buffer limit (7-12 us vs 13+), in-switch reduction wins from there on, one-shot beats
+  // two-shot up to ~512 KiB when multicast is unavailable
+  c->ll_max = 64 * 1024;
+  c->oneshot_max = 512 * 1024;
+  c->nvls_min = 64 * 1024 + 1;
   c->max_blocks = c->sm_count * 2;
   if (c->max_blocks > B2_MAX_BLOCKS) c->max_blocks = B2_MAX_BLOCKS;
   cudaDeviceSynchronize();

@@ -32,61 +32,7 @@
 extern "C" void b2_set_error(const char* fmt, ...);
 extern "C" void b2_count_launch(B2Comm* c);
 
-struct B2SweParams {
-  int ny, nx, pitch;
-  float dx, dy, dt, gravity, viscosity;
-  float ab_a, ab_b;           // Adams-Bashforth weights
-  int first_step;
-  int south_wall, north_wall; // this rank touches the y walls (hc edge padding)
-  const float* coriolis;      // [ny]
-};
-
-#define SWE_THREADS 256
-
-// An aligned group of four cells plus its west / east neighbours.
-struct Row6 {
-  float w, c0, c1, c2, c3, e;
-};
-
-__device__ __forceinline__ float4 ld4(const float* __restrict__ a, size_t off) {
-  return *reinterpret_cast<const float4*>(a + off);
-}
-__device__ __forceinline__ void st4(float* __restrict__ a, size_t off, float4 v) {
-  *reinterpret_cast<float4*>(a + off) = v;
-}
-// row `j`, group starting at column i0 (multiple of 4); neighbours are fetched only when asked
-template <bool W, bool E>
-__device__ __forceinline__ Row6 ld_row(const float* __restrict__ a, int j, int i0, int pitch) {
-  const size_t off = (size_t)j * pitch + i0;
-  const float4 v = ld4(a, off);
-  Row6 r;
-  r.c0 = v.x; r.c1 = v.y; r.c2 = v.z; r.c3 = v.w;
-  r.w = (W && i0 > 0) ? a[off - 1] : 0.f;
-  r.e = (E && i0 + 4 < pitch) ? a[off + 4] : 0.f;
-  return r;
-}
-__device__ __forceinline__ float4 sel4(const bool m[4], float4 a, float4 b) {
-  return make_float4(m[0] ? a.x : b.x, m[1] ? a.y : b.y, m[2] ? a.z : b.z, m[3] ? a.w : b.w);
-}
-
-// thread -> (row j in [1, ny-2], group g); returns false when out of range
-__device__ __forceinline__ bool swe_map(const B2SweParams& p, int& j, int& i0, bool m[4]) {
-  const int ngroups = p.pitch >> 2;
-  const long long idx = (long long)blockIdx.x * SWE_THREADS + threadIdx.x;
-  if (idx >= (long long)(p.ny - 2) * ngroups) return false;
-  j = (int)(idx / ngroups) + 1;
-  i0 = (int)(idx % ngroups) << 2;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) m[k] = (i0 + k >= 1) && (i0 + k <= p.nx - 2);
-  return m[0] || m[1] || m[2] || m[3];
-}
-
-__device__ __forceinline__ int hc_row(const B2SweParams& p, int j) {
-  // hc = h with the physical wall rows replaced by their neighbouring interior row
-  if (p.south_wall && j == 0) return 1;
-  if (p.north_wall && j == p.ny - 1) return p.ny - 2;
-  return j;
-}
+#include "b2_swe_body.cuh"
 
 __global__ void __launch_bounds__(SWE_THREADS)
 swe_k1_fluxes(B2SweParams p, const float* __restrict__ h, const float* __restrict__ u,
@@ -95,33 +41,8 @@ swe_k1_fluxes(B2SweParams p, const float* __restrict__ h, const float* __restric
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
-  const int P = p.pitch;
-  const Row6 hc = ld_row<false, true>(h, hc_row(p, j), i0, P);
-  const Row6 hn = ld_row<false, true>(h, hc_row(p, j + 1), i0, P);
-  const Row6 uc = ld_row<true, false>(u, j, i0, P);
-  const Row6 un = ld_row<false, false>(u, j + 1, i0, P);
-  const Row6 vc = ld_row<false, true>(v, j, i0, P);
-  const Row6 vs = ld_row<false, false>(v, j - 1, i0, P);
-  const float cor = p.coriolis[j];
-  const float H[5] = {hc.c0, hc.c1, hc.c2, hc.c3, hc.e}, HN[5] = {hn.c0, hn.c1, hn.c2, hn.c3, hn.e};
-  const float U[5] = {uc.w, uc.c0, uc.c1, uc.c2, uc.c3}, UN[4] = {un.c0, un.c1, un.c2, un.c3};
-  const float V[5] = {vc.c0, vc.c1, vc.c2, vc.c3, vc.e}, VS[4] = {vs.c0, vs.c1, vs.c2, vs.c3};
-  float FE[4], FN[4], Q[4], KE[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float uk = U[k + 1], vk = V[k];
-    FE[k] = 0.5f * (H[k] + H[k + 1]) * uk;
-    FN[k] = 0.5f * (H[k] + HN[k]) * vk;
-    const float rel = (V[k + 1] - vk) / p.dx - (UN[k] - uk) / p.dy;
-    Q[k] = (cor + rel) * (1.0f / (0.25f * (H[k] + H[k + 1] + HN[k] + HN[k + 1])));
-    KE[k] = 0.5f * (0.5f * (uk * uk + U[k] * U[k]) + 0.5f * (vk * vk + VS[k] * VS[k]));
-    if (!m[k]) FE[k] = FN[k] = Q[k] = KE[k] = 0.f;   // halo / pad lanes: refreshed by the exchange
-  }
-  const size_t off = (size_t)j * P + i0;
-  st4(fe, off, make_float4(FE[0], FE[1], FE[2], FE[3]));
-  st4(fn, off, make_float4(FN[0], FN[1], FN[2], FN[3]));
-  st4(q, off, make_float4(Q[0], Q[1], Q[2], Q[3]));
-  st4(ke, off, make_float4(KE[0], KE[1], KE[2], KE[3]));
+  SweOut4 o;
+  swe_k1_body(p, h, u, v, fe, fn, q, ke, j, i0, m, o);
 }
 
 __global__ void __launch_bounds__(SWE_THREADS)
@@ -133,53 +54,8 @@ swe_k2_tendencies(B2SweParams p, const float* __restrict__ h, float* __restrict_
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
-  const int P = p.pitch;
-  const size_t off = (size_t)j * P + i0;
-  const Row6 fec = ld_row<true, false>(fe, j, i0, P), fen = ld_row<true, false>(fe, j + 1, i0, P);
-  const Row6 fnc = ld_row<false, true>(fn, j, i0, P), fns = ld_row<false, true>(fn, j - 1, i0, P);
-  const Row6 qc = ld_row<true, false>(q, j, i0, P), qs = ld_row<false, false>(q, j - 1, i0, P);
-  const Row6 kec = ld_row<false, true>(ke, j, i0, P), ken = ld_row<false, false>(ke, j + 1, i0, P);
-  const Row6 hc = ld_row<false, true>(h, j, i0, P), hn = ld_row<false, false>(h, j + 1, i0, P);
-  const float4 u4 = ld4(u, off), v4 = ld4(v, off);
-  float4 dh4 = make_float4(0, 0, 0, 0), du4 = dh4, dv4 = dh4;
-  if (!p.first_step) { dh4 = ld4(dh, off); du4 = ld4(du, off); dv4 = ld4(dv, off); }
-  const float FE[5] = {fec.w, fec.c0, fec.c1, fec.c2, fec.c3}, FEN[5] = {fen.w, fen.c0, fen.c1, fen.c2, fen.c3};
-  const float FN[5] = {fnc.c0, fnc.c1, fnc.c2, fnc.c3, fnc.e}, FNS[5] = {fns.c0, fns.c1, fns.c2, fns.c3, fns.e};
-  const float Q[5] = {qc.w, qc.c0, qc.c1, qc.c2, qc.c3}, QS[4] = {qs.c0, qs.c1, qs.c2, qs.c3};
-  const float KE[5] = {kec.c0, kec.c1, kec.c2, kec.c3, kec.e}, KEN[4] = {ken.c0, ken.c1, ken.c2, ken.c3};
-  const float H[5] = {hc.c0, hc.c1, hc.c2, hc.c3, hc.e}, HN[4] = {hn.c0, hn.c1, hn.c2, hn.c3};
-  const float Uo[4] = {u4.x, u4.y, u4.z, u4.w}, Vo[4] = {v4.x, v4.y, v4.z, v4.w};
-  const float DHo[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, DUo[4] = {du4.x, du4.y, du4.z, du4.w},
-              DVo[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
-  float Un[4], Vn[4], Hn[4], DH[4], DU[4], DV[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float fe_c = FE[k + 1], fe_w = FE[k], fn_c = FN[k], q_c = Q[k + 1];
-    const float dh_new = -(fe_c - fe_w) / p.dx - (fn_c - FNS[k]) / p.dy;
-    float du_new = -p.gravity * (H[k + 1] - H[k]) / p.dx +
-                   0.5f * (q_c * 0.5f * (fn_c + FN[k + 1]) + QS[k] * 0.5f * (FNS[k] + FNS[k + 1]));
-    float dv_new = -p.gravity * (HN[k] - H[k]) / p.dy -
-                   0.5f * (q_c * 0.5f * (fe_c + FEN[k + 1]) + Q[k] * 0.5f * (fe_w + FEN[k]));
-    du_new += -(KE[k + 1] - KE[k]) / p.dx;
-    dv_new += -(KEN[k] - KE[k]) / p.dy;
-    if (p.first_step) {
-      Un[k] = Uo[k] + p.dt * du_new;
-      Vn[k] = Vo[k] + p.dt * dv_new;
-      Hn[k] = H[k] + p.dt * dh_new;
-    } else {
-      Un[k] = Uo[k] + p.dt * (p.ab_a * du_new + p.ab_b * DUo[k]);
-      Vn[k] = Vo[k] + p.dt * (p.ab_a * dv_new + p.ab_b * DVo[k]);
-      Hn[k] = H[k] + p.dt * (p.ab_a * dh_new + p.ab_b * DHo[k]);
-    }
-    DH[k] = dh_new; DU[k] = du_new; DV[k] = dv_new;
-    if (!m[k]) { Un[k] = Uo[k]; Vn[k] = Vo[k]; Hn[k] = H[k]; DH[k] = DU[k] = DV[k] = 0.f; }
-  }
-  st4(u, off, make_float4(Un[0], Un[1], Un[2], Un[3]));
-  st4(v, off, make_float4(Vn[0], Vn[1], Vn[2], Vn[3]));
-  st4(h_new, off, make_float4(Hn[0], Hn[1], Hn[2], Hn[3]));
-  st4(dh, off, make_float4(DH[0], DH[1], DH[2], DH[3]));
-  st4(du, off, make_float4(DU[0], DU[1], DU[2], DU[3]));
-  st4(dv, off, make_float4(DV[0], DV[1], DV[2], DV[3]));
+  SweOut4 o;
+  swe_k2_body(p, h, h_new, u, v, dh, du, dv, fe, fn, q, ke, j, i0, m, o);
 }
 
 __global__ void __launch_bounds__(SWE_THREADS)
@@ -188,18 +64,7 @@ swe_k3_friction_flux_u(B2SweParams p, const float* __restrict__ u, float* __rest
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
-  const int P = p.pitch;
-  const Row6 uc = ld_row<false, true>(u, j, i0, P), un = ld_row<false, false>(u, j + 1, i0, P);
-  const float U[5] = {uc.c0, uc.c1, uc.c2, uc.c3, uc.e}, UN[4] = {un.c0, un.c1, un.c2, un.c3};
-  float FE[4], FN[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    FE[k] = m[k] ? p.viscosity * (U[k + 1] - U[k]) / p.dx : 0.f;
-    FN[k] = m[k] ? p.viscosity * (UN[k] - U[k]) / p.dy : 0.f;
-  }
-  const size_t off = (size_t)j * P + i0;
-  st4(fe, off, make_float4(FE[0], FE[1], FE[2], FE[3]));
-  st4(fn, off, make_float4(FN[0], FN[1], FN[2], FN[3]));
+  swe_k3_body(p, u, fe, fn, j, i0, m, false, false);
 }
 
 __global__ void __launch_bounds__(SWE_THREADS)
@@ -209,28 +74,8 @@ swe_k4_friction_u_flux_v(B2SweParams p, float* __restrict__ u, const float* __re
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
-  const int P = p.pitch;
-  const size_t off = (size_t)j * P + i0;
-  const Row6 fec = ld_row<true, false>(fe, j, i0, P);
-  const float4 fnc = ld4(fn, off), fns = ld4(fn, off - P), u4 = ld4(u, off);
-  const Row6 vc = ld_row<false, true>(v, j, i0, P);
-  const float4 vn = ld4(v, off + P);
-  const float FE[5] = {fec.w, fec.c0, fec.c1, fec.c2, fec.c3};
-  const float FN[4] = {fnc.x, fnc.y, fnc.z, fnc.w}, FNS[4] = {fns.x, fns.y, fns.z, fns.w};
-  const float Uo[4] = {u4.x, u4.y, u4.z, u4.w};
-  const float V[5] = {vc.c0, vc.c1, vc.c2, vc.c3, vc.e}, VN[4] = {vn.x, vn.y, vn.z, vn.w};
-  float Un[4], FE2[4], FN2[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float un = Uo[k] + p.dt * ((FE[k + 1] - FE[k]) / p.dx + (FN[k] - FNS[k]) / p.dy);
-    Un[k] = m[k] ? un : Uo[k];
-    // NOTE: `v - u` mirrors the reference (examples/shallow_water.py:387-392)
-    FE2[k] = m[k] ? p.viscosity * (V[k + 1] - un) / p.dx : 0.f;
-    FN2[k] = m[k] ? p.viscosity * (VN[k] - un) / p.dy : 0.f;
-  }
-  st4(u, off, make_float4(Un[0], Un[1], Un[2], Un[3]));
-  st4(fe2, off, make_float4(FE2[0], FE2[1], FE2[2], FE2[3]));
-  st4(fn2, off, make_float4(FN2[0], FN2[1], FN2[2], FN2[3]));
+  SweOut4 o;
+  swe_k4_body(p, u, v, fe, fn, fe2, fn2, j, i0, m, o);
 }
 
 __global__ void __launch_bounds__(SWE_THREADS)
@@ -239,20 +84,7 @@ swe_k5_friction_v(B2SweParams p, float* __restrict__ v, const float* __restrict_
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
-  const int P = p.pitch;
-  const size_t off = (size_t)j * P + i0;
-  const Row6 fec = ld_row<true, false>(fe2, j, i0, P);
-  const float4 fnc = ld4(fn2, off), fns = ld4(fn2, off - P), v4 = ld4(v, off);
-  const float FE[5] = {fec.w, fec.c0, fec.c1, fec.c2, fec.c3};
-  const float FN[4] = {fnc.x, fnc.y, fnc.z, fnc.w}, FNS[4] = {fns.x, fns.y, fns.z, fns.w};
-  const float Vo[4] = {v4.x, v4.y, v4.z, v4.w};
-  float Vn[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float vn = Vo[k] + p.dt * ((FE[k + 1] - FE[k]) / p.dx + (FN[k] - FNS[k]) / p.dy);
-    Vn[k] = m[k] ? vn : Vo[k];
-  }
-  st4(v, off, make_float4(Vn[0], Vn[1], Vn[2], Vn[3]));
+  swe_k5_body(p, v, fe2, fn2, j, i0, m);
 }
 
 static unsigned swe_blocks(const B2SweParams* p) {

@@ -33,6 +33,7 @@ import torch
 from .. import _src as _ops
 from .._src import native
 from .._src.comm import Comm
+from .._src.decorators import env_flag
 from .._src.utils import get_default_comm
 
 ModelState = namedtuple("ModelState", "h, u, v, dh, du, dv")
@@ -73,7 +74,8 @@ class ShallowWaterConfig:
 
 class ShallowWaterModel:
     def __init__(self, config: Optional[ShallowWaterConfig] = None, comm: Optional[Comm] = None,
-                 device: Optional[torch.device] = None, backend: str = "auto"):
+                 device: Optional[torch.device] = None, backend: str = "auto",
+                 fused: Optional[bool] = None):
         self.cfg = cfg = config or ShallowWaterConfig()
         self.comm = comm = comm or get_default_comm()
         self.device = torch.device(device) if device is not None else comm.device
@@ -82,6 +84,8 @@ class ShallowWaterModel:
         if backend == "native" and self.device.type != "cuda":
             raise ValueError("backend='native' needs a CUDA device")
         self.backend = backend
+        # halo exchange fused into the stencil kernels (csrc/b2_swe_fused.cu) unless disabled
+        self.fused = env_flag("MPI4JAX_B200_SWE_FUSED", True) if fused is None else bool(fused)
         size, rank = comm.Get_size(), comm.Get_rank()
         if size not in SUPPORTED_NPROC:
             raise RuntimeError(
@@ -266,7 +270,8 @@ class ShallowWaterModel:
             first_step = self.steps_done == 0
         if self.backend == "native":
             nc = self.comm._native_comm()
-            rc = native.lib.b2_swe_multistep(
+            fn = native.lib.b2_swe_multistep_fused if self.fused else native.lib.b2_swe_multistep
+            rc = fn(
                 nc.handle, ctypes.byref(self._params), ctypes.byref(self._state),
                 ctypes.byref(self._topo), int(nsteps), int(bool(first_step)),
                 torch.cuda.current_stream().cuda_stream)

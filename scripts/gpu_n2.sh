@@ -1,6 +1,7 @@
 #!/bin/bash
 # 2-GPU validation of the vectorised stencils + single-phase halo, perf snapshot
 mkdir -p gpurun_out
+export MPI4JAX_B200_TIMEOUT=20
 timeout 600 python -m pytest tests/test_examples.py tests/test_models.py tests/test_jit.py tests/test_common.py -x -q -m gpu -p no:cacheprovider > gpurun_out/pytest_a_n1.log 2>&1
 echo "pytest n=1 exit $?" >> gpurun_out/pytest_a_n1.log
 timeout 900 python -m pytest tests/test_multirank.py -x -q -m gpu -p no:cacheprovider > gpurun_out/pytest_multirank.log 2>&1
