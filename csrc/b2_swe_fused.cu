@@ -39,12 +39,13 @@ extern "C" void b2_count_launch(B2Comm* c);
 
 #include "b2_swe_body.cuh"
 
-#define SWE_UNPACKERS 8
+#define SWE_UNPACKERS 16
 enum { FS_W = 0, FS_E, FS_S, FS_N, FS_SW, FS_SE, FS_NW, FS_NE, FS_NSIDES };
 
 // ticket words used by the fused path (local device memory)
 #define TK_READY 5     // += 1 per unpacker CTA, reset to 0 by the last CTA of the kernel
 #define TK_FIN 6       // finish counter
+#define TK_TILE 7      // dynamic tile scheduler (reset by the last CTA)
 #define TK_RX 32       // [8] messages received per side
 #define TK_TX 40       // [8] messages sent per side
 
@@ -64,12 +65,14 @@ __device__ __forceinline__ uint2* fz_buf(const B2DevComm& c, int rank, unsigned 
                   ((size_t)parity * FS_NSIDES + side) * c.lay.halo_ll_cap);
 }
 __device__ __forceinline__ void fz_put(uint2* p, float v, unsigned flag) {
+  // no "memory" clobber: the value comes from registers and nothing in this kernel reads the
+  // (remote) target, so the compiler stays free to overlap the next group's loads with the push
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)),
-               "r"(flag) : "memory");
+               "r"(flag));
 }
 __device__ __forceinline__ void fz_put2(uint2* p, float v0, float v1, unsigned flag) {
   asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p),
-               "r"(__float_as_uint(v0)), "r"(flag), "r"(__float_as_uint(v1)), "r"(flag) : "memory");
+               "r"(__float_as_uint(v0)), "r"(flag), "r"(__float_as_uint(v1)), "r"(flag));
 }
 __device__ __forceinline__ float fz_get(const B2DevComm& c, const uint2* p, unsigned flag, int side) {
   unsigned v, f;
@@ -95,6 +98,7 @@ template <int NF>
 __device__ __forceinline__ void fz_push(const B2DevComm& c, const FusedArgs& a, const unsigned* s_tx,
                                         const SweOut4& o, int j, int i0) {
   const int nx = a.p.nx, ny = a.p.ny, fs = a.fstride;
+  if (!(i0 == 0 || (i0 <= nx - 2 && nx - 2 <= i0 + 3) || j == 1 || j == ny - 2)) return;   // no edge cell here
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
 #pragma unroll
@@ -147,56 +151,75 @@ __device__ __forceinline__ void fz_push(const B2DevComm& c, const FusedArgs& a, 
 }
 
 // ---- consumer: the first SWE_UNPACKERS CTAs poll the receive buffers and fill the halo cells ----
-template <int NF>
+// FLD(f) must be a compile-time selectable expression -> macro keeps the field pointers in registers
+template <int NF, typename GetField>
 __device__ __forceinline__ void fz_unpack(const B2DevComm& c, const FusedArgs& a, const unsigned* s_rx,
-                                          float* const (&fld)[4], int nunp) {
+                                          GetField fld, int nunp) {
   const int nx = a.p.nx, ny = a.p.ny, fs = a.fstride;
   const size_t P = (size_t)a.p.pitch;
   const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = nunp * blockDim.x;
-  if (a.nb[FS_W] >= 0) {
-    const uint2* src = fz_buf(c, c.rank, s_rx[FS_W] & 1u, FS_W);
-    const unsigned fl = s_rx[FS_W] + 1u;
-    for (int k = t; k < NF * (ny - 2); k += nt) {
-      const int f = k / (ny - 2), j = 1 + k - f * (ny - 2);
-      fld[f][(size_t)j * P] = fz_get(c, src + f * fs + j, fl, FS_W);
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    float* const F = fld(f);
+    if (a.nb[FS_W] >= 0) {
+      const uint2* src = fz_buf(c, c.rank, s_rx[FS_W] & 1u, FS_W) + f * fs;
+      const unsigned fl = s_rx[FS_W] + 1u;
+      for (int j = 1 + t; j <= ny - 2; j += nt) F[(size_t)j * P] = fz_get(c, src + j, fl, FS_W);
+    }
+    if (a.nb[FS_E] >= 0) {
+      const uint2* src = fz_buf(c, c.rank, s_rx[FS_E] & 1u, FS_E) + f * fs;
+      const unsigned fl = s_rx[FS_E] + 1u;
+      for (int j = 1 + t; j <= ny - 2; j += nt) F[(size_t)j * P + (nx - 1)] = fz_get(c, src + j, fl, FS_E);
+    }
+    if (a.nb[FS_S] >= 0) {
+      const uint2* src = fz_buf(c, c.rank, s_rx[FS_S] & 1u, FS_S) + f * fs;
+      const unsigned fl = s_rx[FS_S] + 1u;
+      for (int i = 1 + t; i <= nx - 2; i += nt) F[i] = fz_get(c, src + i, fl, FS_S);
+    }
+    if (a.nb[FS_N] >= 0) {
+      const uint2* src = fz_buf(c, c.rank, s_rx[FS_N] & 1u, FS_N) + f * fs;
+      const unsigned fl = s_rx[FS_N] + 1u;
+      for (int i = 1 + t; i <= nx - 2; i += nt) F[(size_t)(ny - 1) * P + i] = fz_get(c, src + i, fl, FS_N);
+    }
+    if (t == f) {     // corners of field f: one thread each
+      if (a.nb[FS_SW] >= 0)
+        F[0] = fz_get(c, fz_buf(c, c.rank, s_rx[FS_SW] & 1u, FS_SW) + f, s_rx[FS_SW] + 1u, FS_SW);
+      if (a.nb[FS_SE] >= 0)
+        F[nx - 1] = fz_get(c, fz_buf(c, c.rank, s_rx[FS_SE] & 1u, FS_SE) + f, s_rx[FS_SE] + 1u, FS_SE);
+      if (a.nb[FS_NW] >= 0)
+        F[(size_t)(ny - 1) * P] =
+            fz_get(c, fz_buf(c, c.rank, s_rx[FS_NW] & 1u, FS_NW) + f, s_rx[FS_NW] + 1u, FS_NW);
+      if (a.nb[FS_NE] >= 0)
+        F[(size_t)(ny - 1) * P + (nx - 1)] =
+            fz_get(c, fz_buf(c, c.rank, s_rx[FS_NE] & 1u, FS_NE) + f, s_rx[FS_NE] + 1u, FS_NE);
     }
   }
-  if (a.nb[FS_E] >= 0) {
-    const uint2* src = fz_buf(c, c.rank, s_rx[FS_E] & 1u, FS_E);
-    const unsigned fl = s_rx[FS_E] + 1u;
-    for (int k = t; k < NF * (ny - 2); k += nt) {
-      const int f = k / (ny - 2), j = 1 + k - f * (ny - 2);
-      fld[f][(size_t)j * P + (nx - 1)] = fz_get(c, src + f * fs + j, fl, FS_E);
-    }
-  }
-  if (a.nb[FS_S] >= 0) {
-    const uint2* src = fz_buf(c, c.rank, s_rx[FS_S] & 1u, FS_S);
-    const unsigned fl = s_rx[FS_S] + 1u;
-    for (int k = t; k < NF * (nx - 2); k += nt) {
-      const int f = k / (nx - 2), i = 1 + k - f * (nx - 2);
-      fld[f][i] = fz_get(c, src + f * fs + i, fl, FS_S);
-    }
-  }
-  if (a.nb[FS_N] >= 0) {
-    const uint2* src = fz_buf(c, c.rank, s_rx[FS_N] & 1u, FS_N);
-    const unsigned fl = s_rx[FS_N] + 1u;
-    for (int k = t; k < NF * (nx - 2); k += nt) {
-      const int f = k / (nx - 2), i = 1 + k - f * (nx - 2);
-      fld[f][(size_t)(ny - 1) * P + i] = fz_get(c, src + f * fs + i, fl, FS_N);
-    }
-  }
-  if (t < NF) {
-    const int f = t;
-    if (a.nb[FS_SW] >= 0)
-      fld[f][0] = fz_get(c, fz_buf(c, c.rank, s_rx[FS_SW] & 1u, FS_SW) + f, s_rx[FS_SW] + 1u, FS_SW);
-    if (a.nb[FS_SE] >= 0)
-      fld[f][nx - 1] = fz_get(c, fz_buf(c, c.rank, s_rx[FS_SE] & 1u, FS_SE) + f, s_rx[FS_SE] + 1u, FS_SE);
-    if (a.nb[FS_NW] >= 0)
-      fld[f][(size_t)(ny - 1) * P] =
-          fz_get(c, fz_buf(c, c.rank, s_rx[FS_NW] & 1u, FS_NW) + f, s_rx[FS_NW] + 1u, FS_NW);
-    if (a.nb[FS_NE] >= 0)
-      fld[f][(size_t)(ny - 1) * P + (nx - 1)] =
-          fz_get(c, fz_buf(c, c.rank, s_rx[FS_NE] & 1u, FS_NE) + f, s_rx[FS_NE] + 1u, FS_NE);
+}
+
+// one aligned group of 4 cells: stencil body (+ NVLink push of the edge cells it produced)
+template <int KID>
+__device__ __forceinline__ void fz_compute(const B2DevComm& c, const FusedArgs& a, const unsigned* s_tx,
+                                           int j, int g) {
+  const int i0 = g << 2, nx = a.p.nx;
+  bool m[4];
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { m[k] = (i0 + k >= 1) && (i0 + k <= nx - 2); any |= m[k]; }
+  if (!any) return;
+  [[maybe_unused]] SweOut4 o;
+  if constexpr (KID == 1) {
+    swe_k1_body(a.p, a.h, a.u, a.v, a.fe, a.fn, a.q, a.ke, j, i0, m, o);
+    fz_push<4>(c, a, s_tx, o, j, i0);
+  } else if constexpr (KID == 2) {
+    swe_k2_body(a.p, a.h, a.hn, a.u, a.v, a.dh, a.du, a.dv, a.fe, a.fn, a.q, a.ke, j, i0, m, o);
+    fz_push<3>(c, a, s_tx, o, j, i0);
+  } else if constexpr (KID == 3) {
+    swe_k3_body(a.p, a.u, a.fe, a.fn, j, i0, m, true, a.nb[FS_S] >= 0);
+  } else if constexpr (KID == 4) {
+    swe_k4_body(a.p, a.u, a.v, a.fe, a.fn, a.fe2, a.fn2, j, i0, m, o);
+    fz_push<2>(c, a, s_tx, o, j, i0);
+  } else {
+    swe_k5_body(a.p, a.v, a.fe2, a.fn2, j, i0, m);
   }
 }
 
@@ -215,43 +238,54 @@ __global__ void __launch_bounds__(SWE_THREADS) swe_fused(const B2DevComm c, cons
   const int nunp = (int)gridDim.x < SWE_UNPACKERS ? (int)gridDim.x : SWE_UNPACKERS;
 
   if (HAS_IN && (int)blockIdx.x < nunp) {
-    if constexpr (KID == 2) { float* const fld[4] = {a.fe, a.fn, a.q, a.ke}; fz_unpack<NF_IN>(c, a, s_rx, fld, nunp); }
-    if constexpr (KID == 3) { float* const fld[4] = {a.hn, a.u, a.v, nullptr}; fz_unpack<NF_IN>(c, a, s_rx, fld, nunp); }
-    if constexpr (KID == 5) { float* const fld[4] = {a.fe2, a.fn2, nullptr, nullptr}; fz_unpack<NF_IN>(c, a, s_rx, fld, nunp); }
+    if constexpr (KID == 2)
+      fz_unpack<NF_IN>(c, a, s_rx, [&](int f) { return f == 0 ? a.fe : f == 1 ? a.fn : f == 2 ? a.q : a.ke; }, nunp);
+    if constexpr (KID == 3)
+      fz_unpack<NF_IN>(c, a, s_rx, [&](int f) { return f == 0 ? a.hn : f == 1 ? a.u : a.v; }, nunp);
+    if constexpr (KID == 5)
+      fz_unpack<NF_IN>(c, a, s_rx, [&](int f) { return f == 0 ? a.fe2 : a.fn2; }, nunp);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicAdd(c.ticket + TK_READY, 1u);
   }
 
-  int j = 0, i0 = 0;
-  bool m[4];
-  const bool active = swe_map(a.p, j, i0, m);
-  // groups whose stencil touches a halo cell (or that own an edge cell)
+  // Persistent CTAs: grid = min(#tiles, SMs x 8); every CTA strides over 256-group tiles so the
+  // per-CTA protocol cost (counter loads, ready wait, finish atomic) is paid once, not per tile.
   const int nx = a.p.nx, ny = a.p.ny;
-  const bool isB = active && (i0 == 0 || (i0 <= nx - 1 && i0 + 4 >= nx - 2) || j == 1 || j == ny - 2);
-
-  auto compute = [&]() {
-    [[maybe_unused]] SweOut4 o;
-    if constexpr (KID == 1) {
-      swe_k1_body(a.p, a.h, a.u, a.v, a.fe, a.fn, a.q, a.ke, j, i0, m, o);
-      fz_push<4>(c, a, s_tx, o, j, i0);
-    } else if constexpr (KID == 2) {
-      swe_k2_body(a.p, a.h, a.hn, a.u, a.v, a.dh, a.du, a.dv, a.fe, a.fn, a.q, a.ke, j, i0, m, o);
-      fz_push<3>(c, a, s_tx, o, j, i0);
-    } else if constexpr (KID == 3) {
-      swe_k3_body(a.p, a.u, a.fe, a.fn, j, i0, m, true, a.nb[FS_S] >= 0);
-    } else if constexpr (KID == 4) {
-      swe_k4_body(a.p, a.u, a.v, a.fe, a.fn, a.fe2, a.fn2, j, i0, m, o);
-      fz_push<2>(c, a, s_tx, o, j, i0);
-    } else {
-      swe_k5_body(a.p, a.v, a.fe2, a.fn2, j, i0, m);
+  const int ngroups = a.p.pitch >> 2;
+  const long long total = (long long)(ny - 2) * ngroups;
+  const int gA = (nx - 2) >> 2;                 // group that owns column nx-2 (and sees halo nx-1)
+  // pass 1 (all cells when there is nothing to wait for; else the cells that touch no halo).
+  // Tiles of 256 groups are handed out dynamically: CTAs that spent time unpacking simply take
+  // fewer tiles, so the unpack never becomes the tail of the kernel.
+  // The next tile is fetched (one atomic) while the current one is being computed, so the
+  // scheduler latency is off the critical path.
+  __shared__ unsigned s_next;
+  constexpr int TILE_R = 4;                                   // 4 x 256 groups per tile
+  const long long tile_groups = (long long)TILE_R * SWE_THREADS;
+  const unsigned ntiles = (unsigned)((total + tile_groups - 1) / tile_groups);
+  if (threadIdx.x == 0) s_next = atomicAdd(c.ticket + TK_TILE, 1u);
+  __syncthreads();
+  unsigned tile = s_next;
+  while (tile < ntiles) {
+    __syncthreads();                                          // everyone has read s_next
+    unsigned prefetched = 0;
+    if (threadIdx.x == 0) prefetched = atomicAdd(c.ticket + TK_TILE, 1u);
+#pragma unroll
+    for (int r = 0; r < TILE_R; ++r) {
+      const unsigned idx = tile * (unsigned)tile_groups + (unsigned)r * SWE_THREADS + threadIdx.x;
+      if (idx < (unsigned)total) {
+        const unsigned rr = idx / (unsigned)ngroups;
+        const int row = (int)rr + 1, g = (int)(idx - rr * (unsigned)ngroups);
+        const bool isB = (g == 0 || g == gA || row == 1 || row == ny - 2);
+        if (!(HAS_IN && isB)) fz_compute<KID>(c, a, s_tx, row, g);
+      }
     }
-  };
-
-  if (!HAS_IN) {
-    if (active) compute();
-  } else {
-    if (active && !isB) compute();                       // pass 1: overlaps the exchange
+    if (threadIdx.x == 0) s_next = prefetched;
+    __syncthreads();
+    tile = s_next;
+  }
+  if (HAS_IN) {
     if (threadIdx.x == 0) {                              // halos in place?
       const unsigned target = (unsigned)nunp;
       unsigned long long t0 = 0;
@@ -266,7 +300,24 @@ __global__ void __launch_bounds__(SWE_THREADS) swe_fused(const B2DevComm c, cons
       __threadfence();
     }
     __syncthreads();
-    if (isB) compute();                                  // pass 2: cells next to the boundary
+    // pass 2: dense sweep over the groups next to the boundary --
+    //   [0, 2(ny-2))            : rows 1..ny-2, groups {0, gA}
+    //   [2(ny-2), +2(ngroups-2)): rows 1 and ny-2, every other group
+    const int ncol = 2 * (ny - 2), nrow_items = ngroups - 2;
+    const int nB = ncol + 2 * nrow_items;
+    for (int b = blockIdx.x * SWE_THREADS + threadIdx.x; b < nB; b += gridDim.x * SWE_THREADS) {
+      int row, g;
+      if (b < ncol) {
+        row = 1 + (b >> 1);
+        g = (b & 1) ? gA : 0;
+      } else {
+        const int r = b - ncol;
+        row = (r < nrow_items) ? 1 : ny - 2;
+        g = (r < nrow_items ? r : r - nrow_items) + 1;
+        if (g >= gA) ++g;
+      }
+      fz_compute<KID>(c, a, s_tx, row, g);
+    }
   }
 
   // last CTA to finish advances the message counters
@@ -276,6 +327,7 @@ __global__ void __launch_bounds__(SWE_THREADS) swe_fused(const B2DevComm c, cons
     const unsigned old = atomicAdd(c.ticket + TK_FIN, 1u);
     if (old == gridDim.x - 1) {
       b2_st_volatile(c.ticket + TK_FIN, 0u);
+      b2_st_volatile(c.ticket + TK_TILE, 0u);
       for (int k = 0; k < FS_NSIDES; ++k)
         if (a.nb[k] >= 0) {
           if (HAS_IN) b2_st_volatile(c.ticket + TK_RX + k, s_rx[k] + 1u);
@@ -287,9 +339,18 @@ __global__ void __launch_bounds__(SWE_THREADS) swe_fused(const B2DevComm c, cons
   }
 }
 
-static unsigned fused_blocks(const B2SweParams& p) {
+template <int KID>
+static unsigned fused_blocks(const B2Comm* c, const B2SweParams& p) {
+  static int occ = 0;                                     // resident CTAs per SM for this kernel
+  if (occ == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, swe_fused<KID>, SWE_THREADS, 0) != cudaSuccess ||
+        occ < 1)
+      occ = 1;
+  }
   const long long n = (long long)(p.ny - 2) * (p.pitch / 4);
-  return (unsigned)((n + SWE_THREADS - 1) / SWE_THREADS);
+  const long long tiles = (n + SWE_THREADS - 1) / SWE_THREADS;
+  const long long cap = (long long)c->sm_count * occ;    // persistent: exactly one resident wave
+  return (unsigned)(tiles < cap ? tiles : cap);
 }
 
 extern "C" int b2_swe_multistep(B2Comm* c, const B2SweParams* p0, const B2SweState* st,
@@ -301,8 +362,12 @@ extern "C" int b2_swe_multistep_fused(B2Comm* c, const B2SweParams* p0, const B2
                                       const B2HaloDesc* topo, int nsteps, int first_step,
                                       cudaStream_t s) {
   if (!(p0->viscosity > 0.f)) return b2_swe_multistep(c, p0, st, topo, nsteps, first_step, s);
-  if (p0->pitch % 4 != 0 || p0->pitch < p0->nx || p0->ny < 4 || p0->nx < 4) {
-    b2_set_error("swe(fused): need ny,nx >= 4 and a row pitch that is a multiple of 4 and >= nx");
+  if ((long long)p0->ny * (p0->pitch / 4) >= (1ll << 31)) {
+    b2_set_error("swe(fused): grid too large for 32-bit group indices");
+    return B2_ERR_BAD_ARG;
+  }
+  if (p0->pitch % 4 != 0 || p0->pitch < p0->nx || p0->ny < 4 || p0->nx < 10) {
+    b2_set_error("swe(fused): need ny >= 4, nx >= 10 and a row pitch that is a multiple of 4 and >= nx");
     return B2_ERR_BAD_ARG;
   }
   FusedArgs a;
@@ -328,17 +393,18 @@ extern "C" int b2_swe_multistep_fused(B2Comm* c, const B2SweParams* p0, const B2
   a.fe = st->fe; a.fn = st->fn; a.q = st->q; a.ke = st->ke; a.fe2 = st->fe2; a.fn2 = st->fn2;
   float* h = st->h0;
   float* hn = st->h1;
-  const unsigned grid = fused_blocks(a.p);
+  const unsigned g1 = fused_blocks<1>(c, a.p), g2 = fused_blocks<2>(c, a.p), g3 = fused_blocks<3>(c, a.p),
+                 g4 = fused_blocks<4>(c, a.p), g5 = fused_blocks<5>(c, a.p);
   cudaError_t err = cudaSuccess;
   for (int it = 0; it < nsteps; ++it) {
     a.p.first_step = (first_step && it == 0) ? 1 : 0;
     a.h = h;
     a.hn = hn;
-    swe_fused<1><<<grid, SWE_THREADS, 0, s>>>(c->dev, a);
-    swe_fused<2><<<grid, SWE_THREADS, 0, s>>>(c->dev, a);
-    swe_fused<3><<<grid, SWE_THREADS, 0, s>>>(c->dev, a);
-    swe_fused<4><<<grid, SWE_THREADS, 0, s>>>(c->dev, a);
-    swe_fused<5><<<grid, SWE_THREADS, 0, s>>>(c->dev, a);
+    swe_fused<1><<<g1, SWE_THREADS, 0, s>>>(c->dev, a);
+    swe_fused<2><<<g2, SWE_THREADS, 0, s>>>(c->dev, a);
+    swe_fused<3><<<g3, SWE_THREADS, 0, s>>>(c->dev, a);
+    swe_fused<4><<<g4, SWE_THREADS, 0, s>>>(c->dev, a);
+    swe_fused<5><<<g5, SWE_THREADS, 0, s>>>(c->dev, a);
     for (int k = 0; k < 5; ++k) b2_count_launch(c);
     if ((err = cudaGetLastError()) != cudaSuccess) break;
     float* t = h; h = hn; hn = t;
