@@ -2,12 +2,12 @@
 // reference's demo application (examples/shallow_water.py:270-403).  The
 // reference leaves this arithmetic to XLA (dozens of fused elementwise kernels
 // plus pad / dynamic-update-slice copies per step, separated by 48 blocking MPI
-// custom calls).  Here one model step is five stencil launches and four fused
-// halo exchanges (b2_halo.cu):
+// custom calls).  Here one model step is five stencil launches and three fused
+// multi-field halo exchanges (b2_halo.cu):
 //
 //   K1 fluxes      (h,u,v)                 -> fe, fn, q, ke        [exchange fe,fn,q,ke]
 //   K2 tendencies  (h,fe,fn,q,ke,d*_old)   -> dh,du,dv, h',u,v     [exchange h',u,v]
-//   K3 friction-u flux   (u)               -> fe, fn               [exchange fe,fn]
+//   K3 friction-u flux   (u)               -> fe, fn  (+ their west/south halo, computed locally)
 //   K4 friction-u apply + friction-v flux  -> u, fe2, fn2          [exchange fe2,fn2]
 //   K5 friction-v apply                    -> v
 //
@@ -60,11 +60,11 @@ swe_k2_tendencies(B2SweParams p, const float* __restrict__ h, float* __restrict_
 
 __global__ void __launch_bounds__(SWE_THREADS)
 swe_k3_friction_flux_u(B2SweParams p, const float* __restrict__ u, float* __restrict__ fe,
-                       float* __restrict__ fn) {
+                       float* __restrict__ fn, int local_halo, int has_south) {
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
-  swe_k3_body(p, u, fe, fn, j, i0, m, false, false);
+  swe_k3_body(p, u, fe, fn, j, i0, m, local_halo != 0, has_south != 0);
 }
 
 __global__ void __launch_bounds__(SWE_THREADS)
@@ -128,10 +128,13 @@ int b2_swe_tendencies(B2Comm* c, const B2SweParams* p, const float* h, float* h_
   return swe_done(c, "swe_tendencies");
 }
 
+// local_halo != 0: also fill the west halo column of fe and (if has_south) the south halo row of
+// fn from this rank's own u halo -- the only halo cells of (fe, fn) the next kernel reads -- so
+// that no exchange of (fe, fn) is needed (bit-identical values, see b2_swe_body.cuh).
 int b2_swe_friction_flux_u(B2Comm* c, const B2SweParams* p, const float* u, float* fe, float* fn,
-                           cudaStream_t s) {
+                           int local_halo, int has_south, cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
-  swe_k3_friction_flux_u<<<swe_blocks(p), SWE_THREADS, 0, s>>>(*p, u, fe, fn);
+  swe_k3_friction_flux_u<<<swe_blocks(p), SWE_THREADS, 0, s>>>(*p, u, fe, fn, local_halo, has_south);
   return swe_done(c, "swe_friction_flux_u");
 }
 
@@ -187,14 +190,12 @@ int b2_swe_multistep(B2Comm* c, const B2SweParams* p0, const B2SweState* st, con
     d.field[2] = st->v; d.kind[2] = 2;
     if ((rc = b2_halo_exchange(c, &d, s))) break;
     if (p.viscosity > 0.f) {
-      if ((rc = b2_swe_friction_flux_u(c, &p, st->u, st->fe, st->fn, s))) break;
-      d.nfields = 2;
-      d.field[0] = st->fe; d.kind[0] = 1;
-      d.field[1] = st->fn; d.kind[1] = 2;
-      if ((rc = b2_halo_exchange(c, &d, s))) break;
+      // the halo of the friction-u fluxes is produced locally: one exchange less than the reference
+      if ((rc = b2_swe_friction_flux_u(c, &p, st->u, st->fe, st->fn, 1, topo->south >= 0, s))) break;
       if ((rc = b2_swe_friction_u_flux_v(c, &p, st->u, st->v, st->fe, st->fn, st->fe2, st->fn2, s))) break;
-      d.field[0] = st->fe2;
-      d.field[1] = st->fn2;
+      d.nfields = 2;
+      d.field[0] = st->fe2; d.kind[0] = 1;
+      d.field[1] = st->fn2; d.kind[1] = 2;
       if ((rc = b2_halo_exchange(c, &d, s))) break;
       if ((rc = b2_swe_friction_v(c, &p, st->v, st->fe2, st->fn2, s))) break;
     }

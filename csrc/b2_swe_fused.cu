@@ -37,17 +37,10 @@
 extern "C" void b2_set_error(const char* fmt, ...);
 extern "C" void b2_count_launch(B2Comm* c);
 
+#include "b2_halo_ll.cuh"
 #include "b2_swe_body.cuh"
 
 #define SWE_UNPACKERS 16
-enum { FS_W = 0, FS_E, FS_S, FS_N, FS_SW, FS_SE, FS_NW, FS_NE, FS_NSIDES };
-
-// ticket words used by the fused path (local device memory)
-#define TK_READY 5     // += 1 per unpacker CTA, reset to 0 by the last CTA of the kernel
-#define TK_FIN 6       // finish counter
-#define TK_TILE 7      // dynamic tile scheduler (reset by the last CTA)
-#define TK_RX 32       // [8] messages received per side
-#define TK_TX 40       // [8] messages sent per side
 
 struct B2SweState {
   float *h0, *h1, *u, *v, *dh, *du, *dv, *fe, *fn, *q, *ke, *fe2, *fn2;
@@ -59,39 +52,6 @@ struct FusedArgs {
   int nb[FS_NSIDES];     // rank behind each side (-1 = none)
   int fstride;           // elements per field in a receive buffer
 };
-
-__device__ __forceinline__ uint2* fz_buf(const B2DevComm& c, int rank, unsigned parity, int side) {
-  return (uint2*)(c.heap[rank] + c.lay.halo_ll_off +
-                  ((size_t)parity * FS_NSIDES + side) * c.lay.halo_ll_cap);
-}
-__device__ __forceinline__ void fz_put(uint2* p, float v, unsigned flag) {
-  // no "memory" clobber: the value comes from registers and nothing in this kernel reads the
-  // (remote) target, so the compiler stays free to overlap the next group's loads with the push
-  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)),
-               "r"(flag));
-}
-__device__ __forceinline__ void fz_put2(uint2* p, float v0, float v1, unsigned flag) {
-  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p),
-               "r"(__float_as_uint(v0)), "r"(flag), "r"(__float_as_uint(v1)), "r"(flag));
-}
-__device__ __forceinline__ float fz_get(const B2DevComm& c, const uint2* p, unsigned flag, int side) {
-  unsigned v, f;
-  unsigned long long t0 = 0;
-  unsigned spins = 0;
-  while (true) {
-    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
-    if (f == flag) break;
-    if ((++spins & 0xfffu) == 0) {
-      unsigned long long now = b2_gtime();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > c.timeout_ns) b2_fatal(c, B2_ERR_TIMEOUT, B2_OPC_HALO, side, flag, f, 5);
-    }
-  }
-  return __uint_as_float(v);
-}
-
-// my message towards side k lands on the opposite side of the neighbour
-__device__ __constant__ int kOpp[FS_NSIDES] = {FS_E, FS_W, FS_N, FS_S, FS_NE, FS_NW, FS_SE, FS_SW};
 
 // ---- producer: push the edge cells this thread just computed --------------------------------
 template <int NF>

@@ -84,8 +84,9 @@ class ShallowWaterModel:
         if backend == "native" and self.device.type != "cuda":
             raise ValueError("backend='native' needs a CUDA device")
         self.backend = backend
-        # halo exchange fused into the stencil kernels (csrc/b2_swe_fused.cu) unless disabled
-        self.fused = env_flag("MPI4JAX_B200_SWE_FUSED", True) if fused is None else bool(fused)
+        # fused=True: halo exchange fused into the stencil kernels (csrc/b2_swe_fused.cu);
+        # default is the stand-alone exchange kernel, which currently measures faster (profiles/)
+        self.fused = env_flag("MPI4JAX_B200_SWE_FUSED", False) if fused is None else bool(fused)
         size, rank = comm.Get_size(), comm.Get_rank()
         if size not in SUPPORTED_NPROC:
             raise RuntimeError(

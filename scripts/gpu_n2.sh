@@ -15,3 +15,4 @@ echo "bench2 exit $?" >> gpurun_out/bench_n2.err
 tail -n 4 gpurun_out/pytest_a_n1.log gpurun_out/pytest_multirank.log gpurun_out/bench_n1.err gpurun_out/bench_n2.err
 grep -E "halo|swe|perf|FAIL" gpurun_out/diag.log | tail -12
 cat gpurun_out/bench_n1.json gpurun_out/bench_n2.json | cut -c1-600
+python scripts/swe_small_bench.py 2>&1 | tee gpurun_out/swe_small.log | grep nx=
