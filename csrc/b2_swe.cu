@@ -2,13 +2,13 @@
 // reference's demo application (examples/shallow_water.py:270-403).  The
 // reference leaves this arithmetic to XLA (dozens of fused elementwise kernels
 // plus pad / dynamic-update-slice copies per step, separated by 48 blocking MPI
-// custom calls).  Here one model step is five stencil launches and three fused
+// custom calls).  Here one model step is four stencil launches and three fused
 // multi-field halo exchanges (b2_halo.cu):
 //
 //   K1 fluxes      (h,u,v)                 -> fe, fn, q, ke        [exchange fe,fn,q,ke]
 //   K2 tendencies  (h,fe,fn,q,ke,d*_old)   -> dh,du,dv, h',u,v     [exchange h',u,v]
-//   K3 friction-u flux   (u)               -> fe, fn  (+ their west/south halo, computed locally)
-//   K4 friction-u apply + friction-v flux  -> u, fe2, fn2          [exchange fe2,fn2]
+//   K34 friction-u (fluxes inline from u, incl. their halo) + friction-v flux -> u, fe2, fn2
+//                                                                   [exchange fe2,fn2]
 //   K5 friction-v apply                    -> v
 //
 // The physics, including the order of boundary updates, the edge-padded `hc`
@@ -79,6 +79,16 @@ swe_k4_friction_u_flux_v(B2SweParams p, float* __restrict__ u, const float* __re
 }
 
 __global__ void __launch_bounds__(SWE_THREADS)
+swe_k34_friction_u(B2SweParams p, float* __restrict__ u, const float* __restrict__ v,
+                   float* __restrict__ fe2, float* __restrict__ fn2, int has_south) {
+  int j, i0;
+  bool m[4];
+  if (!swe_map(p, j, i0, m)) return;
+  SweOut4 o;
+  swe_k34_body(p, u, v, fe2, fn2, j, i0, m, has_south != 0, o);
+}
+
+__global__ void __launch_bounds__(SWE_THREADS)
 swe_k5_friction_v(B2SweParams p, float* __restrict__ v, const float* __restrict__ fe2,
                   const float* __restrict__ fn2) {
   int j, i0;
@@ -146,6 +156,14 @@ int b2_swe_friction_u_flux_v(B2Comm* c, const B2SweParams* p, float* u, const fl
   return swe_done(c, "swe_friction_u_flux_v");
 }
 
+// friction-u flux + apply + friction-v flux in one kernel (no fe/fn round trip through HBM)
+int b2_swe_friction_u_fused(B2Comm* c, const B2SweParams* p, float* u, const float* v, float* fe2,
+                            float* fn2, int has_south, cudaStream_t s) {
+  if (int rc = swe_check(p)) return rc;
+  swe_k34_friction_u<<<swe_blocks(p), SWE_THREADS, 0, s>>>(*p, u, v, fe2, fn2, has_south);
+  return swe_done(c, "swe_friction_u_fused");
+}
+
 int b2_swe_friction_v(B2Comm* c, const B2SweParams* p, float* v, const float* fe2, const float* fn2,
                       cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
@@ -153,7 +171,7 @@ int b2_swe_friction_v(B2Comm* c, const B2SweParams* p, float* v, const float* fe
   return swe_done(c, "swe_friction_v");
 }
 
-// One call = `nsteps` model steps (5 stencil launches + 4 fused halo exchanges each), all
+// One call = `nsteps` model steps (4 stencil launches + 3 fused halo exchanges each), all
 // enqueued on `s` without touching the host again: the whole time loop of the reference's
 // `do_multistep` (examples/shallow_water.py:406-411) becomes a launch sequence that CUDA-graph
 // capture turns into a single replayable graph.  `h0`/`h1` ping-pong (their wall rows are
@@ -190,9 +208,9 @@ int b2_swe_multistep(B2Comm* c, const B2SweParams* p0, const B2SweState* st, con
     d.field[2] = st->v; d.kind[2] = 2;
     if ((rc = b2_halo_exchange(c, &d, s))) break;
     if (p.viscosity > 0.f) {
-      // the halo of the friction-u fluxes is produced locally: one exchange less than the reference
-      if ((rc = b2_swe_friction_flux_u(c, &p, st->u, st->fe, st->fn, 1, topo->south >= 0, s))) break;
-      if ((rc = b2_swe_friction_u_flux_v(c, &p, st->u, st->v, st->fe, st->fn, st->fe2, st->fn2, s))) break;
+      // friction-u fluxes are evaluated inline from u (incl. their halo, from u's fresh halo):
+      // no K3 launch, no (fe, fn) exchange, no HBM round trip of the fluxes
+      if ((rc = b2_swe_friction_u_fused(c, &p, st->u, st->v, st->fe2, st->fn2, topo->south >= 0, s))) break;
       d.nfields = 2;
       d.field[0] = st->fe2; d.kind[0] = 1;
       d.field[1] = st->fn2; d.kind[1] = 2;

@@ -223,6 +223,50 @@ __device__ __forceinline__ void swe_k4_body(const B2SweParams& p, float* __restr
   st4(fn2, off, make_float4(FN2[0], FN2[1], FN2[2], FN2[3]));
 }
 
+// K3+K4 in one pass: the friction-u fluxes are re-evaluated from u's 5-point stencil instead of
+// being written to and re-read from HBM (saves one launch and 5 of 37 array passes per step).
+//   fe[c]    = nu (u[c+1] - u[c]) / dx      fe[c-1]  = nu (u[c] - u[c-1]) / dx
+//   fn[c]    = nu (u[c+nx] - u[c]) / dy     fn[c-nx] = nu (u[c] - u[c-nx]) / dy
+// with the reference's boundary values: fn = 0 on row ny-2 of the north-wall ranks ("v" rule),
+// fn's south halo row = 0 on south-wall ranks (never received), u's halo supplying the west /
+// south halo fluxes elsewhere -- the same expressions on the same operands as the separate
+// K3 -> exchange -> K4 sequence, hence the same bits.
+__device__ __forceinline__ void swe_k34_body(const B2SweParams& p, float* __restrict__ u,
+                                             const float* __restrict__ v, float* __restrict__ fe2,
+                                             float* __restrict__ fn2, int j, int i0, const bool m[4],
+                                             bool has_south, SweOut4& o) {
+  const int P = p.pitch;
+  const size_t off = (size_t)j * P + i0;
+  const Row6 uc = ld_row<true, true>(u, j, i0, P);
+  const float4 un4 = ld4(u, off + P), us4 = ld4(u, off - P);
+  const Row6 vc = ld_row<false, true>(v, j, i0, P);
+  const float4 vn = ld4(v, off + P);
+  const float U[6] = {uc.w, uc.c0, uc.c1, uc.c2, uc.c3, uc.e};
+  const float UN[4] = {un4.x, un4.y, un4.z, un4.w}, US[4] = {us4.x, us4.y, us4.z, us4.w};
+  const float V[5] = {vc.c0, vc.c1, vc.c2, vc.c3, vc.e}, VN[4] = {vn.x, vn.y, vn.z, vn.w};
+  const bool fn_c_zero = p.north_wall && j == p.ny - 2;
+  const bool fn_s_zero = (j == 1) && !has_south;
+  float Un[4], FE2[4], FN2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float uk = U[k + 1];
+    const float fe_c = p.viscosity * (U[k + 2] - uk) / p.dx;
+    const float fe_w = p.viscosity * (uk - U[k]) / p.dx;
+    const float fn_c = fn_c_zero ? 0.f : p.viscosity * (UN[k] - uk) / p.dy;
+    const float fn_s = fn_s_zero ? 0.f : p.viscosity * (uk - US[k]) / p.dy;
+    const float un = uk + p.dt * ((fe_c - fe_w) / p.dx + (fn_c - fn_s) / p.dy);
+    Un[k] = m[k] ? un : uk;
+    // NOTE: `v - u` mirrors the reference (examples/shallow_water.py:387-392)
+    FE2[k] = m[k] ? p.viscosity * (V[k + 1] - un) / p.dx : 0.f;
+    FN2[k] = m[k] ? p.viscosity * (VN[k] - un) / p.dy : 0.f;
+    if (p.north_wall && j == p.ny - 2) FN2[k] = 0.f;
+    o.a[0][k] = FE2[k]; o.a[1][k] = FN2[k];
+  }
+  st4(u, off, make_float4(Un[0], Un[1], Un[2], Un[3]));
+  st4(fe2, off, make_float4(FE2[0], FE2[1], FE2[2], FE2[3]));
+  st4(fn2, off, make_float4(FN2[0], FN2[1], FN2[2], FN2[3]));
+}
+
 __device__ __forceinline__ void swe_k5_body(const B2SweParams& p, float* __restrict__ v,
                                             const float* __restrict__ fe2,
                                             const float* __restrict__ fn2, int j, int i0,

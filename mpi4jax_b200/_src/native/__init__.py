@@ -166,6 +166,7 @@ _SIGNATURES = {
     "b2_swe_tendencies": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 11 + [c_void_p]),
     "b2_swe_friction_flux_u": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
     "b2_swe_friction_u_flux_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 6 + [c_void_p]),
+    "b2_swe_friction_u_fused": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 4 + [c_int, c_void_p]),
     "b2_swe_friction_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_void_p]),
     "b2_swe_multistep_fused": (
         c_int,
