@@ -387,8 +387,13 @@ extern "C" int b2_halo_exchange(B2Comm* c, const B2HaloDesc* d, cudaStream_t str
     const char* e = getenv("MPI4JAX_B200_HALO_LL");
     use_ll = !(e && (e[0] == '0' || e[0] == 'f' || e[0] == 'F'));
   }
-  if (use_ll && (size_t)d->nfields * fs * sizeof(uint2) <= c->dev.lay.halo_ll_cap)
-    b2_k_halo_ll<<<HALO_LL_CTAS, HALO_THREADS, 0, stream>>>(c->dev, *d, fs);
+  if (use_ll && (size_t)d->nfields * fs * sizeof(uint2) <= c->dev.lay.halo_ll_cap) {
+    // about one element per thread and side: the exchange is pure latency, so spread it wide
+    int ctas = (d->nfields * mx + HALO_THREADS - 1) / HALO_THREADS;
+    if (ctas < HALO_LL_CTAS) ctas = HALO_LL_CTAS;
+    if (ctas > 96) ctas = 96;
+    b2_k_halo_ll<<<ctas, HALO_THREADS, 0, stream>>>(c->dev, *d, fs);
+  }
   else
     b2_k_halo<<<HALO_CTAS, HALO_THREADS, 0, stream>>>(c->dev, *d);
   b2_count_launch(c);
