@@ -1,0 +1,317 @@
+// mpi4jax_b200 -- row-parallel linear layer: GEMM + allreduce in ONE kernel.
+//
+//   out = allreduce_SUM_over_ranks( X_r (M x K_r, bf16)  @  W_r^T (W_r: N x K_r, bf16) )
+//
+// This is the tensor-parallel pattern the reference only has as a user-level test
+// (column-sharded mat-vec followed by mpi4jax.allreduce,
+// tests/collective_ops/test_allreduce_matvec.py:41-65).  There the product is one XLA op and
+// the reduction a blocking MPI call afterwards; here both are one sm_100a kernel:
+//
+//   * 5th-gen tensor cores: `tcgen05.mma.cta_group::1.kind::f16` (128x128x16 UMMA, bf16 in,
+//     fp32 accumulate) issued by ONE thread per CTA, operands staged by TMA
+//     (`cp.async.bulk.tensor.2d`, 128-byte swizzle) through a 4-stage mbarrier ring, the
+//     accumulator lives in TMEM (128 columns) and is read back with `tcgen05.ld`;
+//   * the epilogue does not write the partial product anywhere locally: every fp32 fragment is
+//     pushed with `multimem.red.add.v4.f32` into a multicast-mapped accumulator, i.e. the
+//     NVSwitch adds it into the copy held by EVERY rank (in-switch all-reduce, one NVLink
+//     traversal, overlapped tile by tile with the MMAs of the following tiles);
+//   * a block-paired cross-GPU barrier, then each CTA converts its (now complete) tiles from
+//     the local accumulator copy to bf16 and re-zeroes them for the next call.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (one TMEM lane quarter each).  Persistent: grid =
+// min(#tiles, #SMs), every CTA walks tiles blockIdx.x, +gridDim.x, ...
+// Shapes: M, N multiples of 128, K multiple of 64 (checked by the host wrapper).
+#include <cstdio>
+#include <cstring>
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "b2_device.cuh"
+#include "b2_runtime.h"
+
+extern "C" void b2_set_error(const char* fmt, ...);
+extern "C" void b2_count_launch(B2Comm* c);
+extern "C" int b2_tensor_map_2d_bf16(CUtensorMap* out, const void* ptr, unsigned long long rows,
+                                     unsigned long long cols, unsigned box_rows, unsigned box_cols);
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2, B_STAGE_BYTES = BN * BK * 2;
+constexpr uint32_t TMEM_COLS = 128;
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1,
+// B=bf16 [10,13)=1, A and B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+
+struct GemmArgs {
+  int M, N, K;
+  __nv_bfloat16* out;
+  float* acc_mc;       // multicast alias of the accumulator segment (fused path)
+  float* acc_local;    // this rank's copy
+  size_t acc_half;     // floats per parity
+  int fused;
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t tx) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// K-major operand tile in shared memory, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+// start address >> 4 at [0,14), LBO (unused for swizzled K-major) at [16,30), SBO = 8 rows x 128 B
+// = 1024 B >> 4 at [32,46), version = 1 at [46,48), layout SWIZZLE_128B = 2 at [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+      "r"(IDESC), "r"(accum));
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+      "%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mc_red_add4(float* mc, uint32_t a, uint32_t b, uint32_t c2, uint32_t d) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(a), "r"(b),
+               "r"(c2), "r"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const B2DevComm c, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base, smem_b = smem_base + STAGES * A_STAGE_BYTES;
+  auto bar = [](uint64_t* p) { return (uint32_t)__cvta_generic_to_shared(p); };
+
+  unsigned ticket = 0, e = 0;
+  if (g.fused) {
+    ticket = b2_ticket_read(c.ticket);
+    e = b2_ld_volatile(c.epoch + blockIdx.x);
+  }
+  const size_t par = (size_t)(ticket & 1u) * g.acc_half;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar(&full_bar[s]), 1); mbar_init(bar(&empty_bar[s]), 1); }
+    mbar_init(bar(&tmem_full_bar), 1);
+    mbar_init(bar(&tmem_empty_bar), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(&tmem_base_s)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int num_n = g.N / BN, tiles = (g.M / BM) * num_n, num_kb = g.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar(&empty_bar[stage]), phase ^ 1u);
+        mbar_expect_tx(bar(&full_bar[stage]), A_STAGE_BYTES + B_STAGE_BYTES);
+        tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, bar(&full_bar[stage]), kb * BK, m_blk * BM);
+        tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tma_b, bar(&full_bar[stage]), kb * BK, n_blk * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer (one thread) =====
+    uint32_t stage = 0, phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      mbar_wait(bar(&tmem_empty_bar), acc_phase ^ 1u);        // epilogue drained the accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar(&full_bar[stage]), phase);               // TMA landed this stage
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint64_t adesc = umma_desc(smem_a + stage * A_STAGE_BYTES);
+        const uint64_t bdesc = umma_desc(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)                  // +32 B per UMMA_K inside the swizzle atom
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0);
+        umma_commit(bar(&empty_bar[stage]));                   // frees the smem stage when the MMAs retire
+        if (kb == num_kb - 1) umma_commit(bar(&tmem_full_bar)); // accumulator complete
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      acc_phase ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> multimem.red (fused) / bf16 store (single rank) =====
+    const int q = warp & 3;                                     // TMEM lane quarter of this warp
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(bar(&tmem_full_bar), acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const size_t row = (size_t)m_blk * BM + q * 32 + lane;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+        const size_t col = (size_t)n_blk * BN + ch * 32;
+        if (g.fused) {
+          float* dst = g.acc_mc + par + row * g.N + col;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) mc_red_add4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+          __nv_bfloat16* dst = g.out + row * g.N + col;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(dst + i) = pk;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(&tmem_empty_bar));         // 4 arrivals free the accumulator
+      acc_phase ^= 1u;
+    }
+  }
+
+  // ===== fused tail: every rank's partial tiles have been added by the switch =====
+  if (g.fused) {
+    b2_barrier_all(c, ++e, B2_OPC_ALLREDUCE);
+    float* mine = g.acc_local + par;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int i = threadIdx.x; i < BM * BN / 4; i += GEMM_THREADS) {
+        const int r = i / (BN / 4), c4 = i % (BN / 4);
+        const size_t off = ((size_t)m_blk * BM + r) * g.N + (size_t)n_blk * BN + c4 * 4;
+        const uint4 raw = b2_ld_peer16(mine + off);               // strong load: written by the switch
+        __nv_bfloat162 lo = __floats2bfloat162_rn(__uint_as_float(raw.x), __uint_as_float(raw.y));
+        __nv_bfloat162 hi = __floats2bfloat162_rn(__uint_as_float(raw.z), __uint_as_float(raw.w));
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(g.out + off) = pk;
+        b2_st16(mine + off, make_uint4(0, 0, 0, 0));             // accumulator is zero between calls
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+  if (g.fused) {
+    if (threadIdx.x == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
+    b2_finish_bump(c.ticket, c.ticket + 1, 1u, gridDim.x);
+  }
+}
+
+}  // namespace
+
+// out (M x N, bf16) = sum over ranks of A (M x K, bf16, row-major) @ B^T (B: N x K, bf16, row-major).
+// acc/acc_mc: zero-initialised symmetric fp32 accumulator segment (2 x M*N floats) and its
+// multicast object; pass null (or use a 1-rank communicator) for a purely local GEMM.
+extern "C" int b2_gemm_allreduce(B2Comm* c, const void* A, const void* B, void* out, int M, int N, int K,
+                                 B2Seg* acc, B2Mc* acc_mc, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || M % BM || N % BN || K % BK) {
+    b2_set_error("gemm_allreduce: need M %% %d == 0, N %% %d == 0, K %% %d == 0 (got %d, %d, %d)", BM, BN,
+                 BK, M, N, K);
+    return B2_ERR_BAD_ARG;
+  }
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.M = M; g.N = N; g.K = K;
+  g.out = (__nv_bfloat16*)out;
+  g.fused = (c->dev.size > 1) ? 1 : 0;
+  if (g.fused) {
+    if (!acc || !acc_mc || !acc_mc->ptr) {
+      b2_set_error("gemm_allreduce: multi-rank call needs a multicast-bound accumulator segment");
+      return B2_ERR_BAD_ARG;
+    }
+    const size_t half_floats = (acc->bytes / 2) / sizeof(float) / 1024 * 1024;
+    if ((size_t)M * N > half_floats) {
+      b2_set_error("gemm_allreduce: accumulator segment too small (%zu floats < %zu)", half_floats,
+                   (size_t)M * N);
+      return B2_ERR_BAD_ARG;
+    }
+    g.acc_local = (float*)acc->ptr[c->dev.rank];
+    g.acc_mc = (float*)acc_mc->ptr;
+    g.acc_half = half_floats;
+  }
+  CUtensorMap ta, tb;
+  if (b2_tensor_map_2d_bf16(&ta, A, (unsigned long long)M, (unsigned long long)K, BM, BK) ||
+      b2_tensor_map_2d_bf16(&tb, B, (unsigned long long)N, (unsigned long long)K, BN, BK))
+    return B2_ERR_BAD_ARG;
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(b2_k_gemm_allreduce, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) {
+      b2_set_error("gemm_allreduce: cannot reserve %zu bytes of shared memory: %s", smem,
+                   cudaGetErrorString(e));
+      return 1000 + (int)e;
+    }
+    attr_set = true;
+  }
+  const int tiles = (M / BM) * (N / BN);
+  int grid = tiles < c->sm_count ? tiles : c->sm_count;
+  if (grid > B2_MAX_BLOCKS) grid = B2_MAX_BLOCKS;
+  b2_k_gemm_allreduce<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, c->dev, g);
+  b2_count_launch(c);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    b2_set_error("gemm_allreduce: kernel launch failed: %s", cudaGetErrorString(err));
+    return 1000 + (int)err;
+  }
+  return 0;
+}

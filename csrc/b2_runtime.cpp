@@ -36,6 +36,7 @@ extern "C" void b2_set_error(const char* fmt, ...);
   X(cuMulticastBindMem)                \
   X(cuMulticastGetGranularity)         \
   X(cuDeviceGetAttribute)              \
+  X(cuTensorMapEncodeTiled)            \
   X(cuGetErrorString)
 
 #define B2_DECL(name) static decltype(&name) p_##name = nullptr;
@@ -487,6 +488,33 @@ extern "C" int b2_comm_destroy(B2Comm* c) {
   if (c->dev.epoch) cudaFree(c->dev.epoch);
   if (c->err_host) cudaFreeHost((void*)c->err_host);
   delete c;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// TMA descriptor for a row-major (rows x cols) bf16 matrix, box = box_rows x box_cols,
+// 128-byte swizzle (what the tcgen05 K-major SWIZZLE_128B shared-memory descriptor expects)
+// ---------------------------------------------------------------------------
+extern "C" int b2_tensor_map_2d_bf16(CUtensorMap* out, const void* ptr, unsigned long long rows,
+                                     unsigned long long cols, unsigned box_rows, unsigned box_cols) {
+  if (!load_driver()) return 1;
+  if (((uintptr_t)ptr & 15) != 0 || (cols * 2) % 16 != 0 || box_cols * 2 != 128) {
+    b2_set_error("tensor map: need a 16-byte aligned base, a row pitch that is a multiple of 16 bytes "
+                 "and a 128-byte box row");
+    return 1;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = p_cuTensorMapEncodeTiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b2_set_error("cuTensorMapEncodeTiled failed: %s", drv_err(r));
+    return 1;
+  }
   return 0;
 }
 

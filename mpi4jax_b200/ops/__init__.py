@@ -6,3 +6,4 @@ from .._src import (  # noqa: F401
     send, send_with_grad, sendrecv,
 )
 from .halo import halo_exchange  # noqa: F401
+from .linear import linear_allreduce  # noqa: F401
