@@ -47,6 +47,11 @@ class ParallelMLP:
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.mode == "tp":
             h = torch.tanh(x @ self.w1)                       # column-parallel
+            if h.is_cuda and h.dtype == torch.bfloat16:
+                # row-parallel GEMM and its allreduce as ONE tcgen05 + multimem.red kernel
+                from ..ops.linear import linear_allreduce
+
+                return linear_allreduce(h, self.w2.t(), comm=self.comm)
             return ops.allreduce(h @ self.w2, SUM, comm=self.comm)   # row-parallel + sum
         w1 = ops.bcast(self.w1, 0, comm=self.comm)            # parameters live on the root
         w2 = ops.bcast(self.w2, 0, comm=self.comm)
