@@ -11,16 +11,20 @@
 //     fp32 accumulate) issued by ONE thread per CTA, operands staged by TMA
 //     (`cp.async.bulk.tensor.2d`, 128-byte swizzle) through a 4-stage mbarrier ring, the
 //     accumulator lives in TMEM (128 columns) and is read back with `tcgen05.ld`;
-//   * the epilogue does not write the partial product anywhere locally: every fp32 fragment is
-//     pushed with `multimem.red.add.v4.f32` into a multicast-mapped accumulator, i.e. the
-//     NVSwitch adds it into the copy held by EVERY rank (in-switch all-reduce, one NVLink
-//     traversal, overlapped tile by tile with the MMAs of the following tiles);
-//   * a block-paired cross-GPU barrier, then each CTA converts its (now complete) tiles from
-//     the local accumulator copy to bf16 and re-zeroes them for the next call.
+//     two accumulator stages (2 x 128 TMEM columns) let the MMA warp run one tile ahead;
+//   * the epilogue warps turn a finished tile into bf16, store it into this rank's SYMMETRIC
+//     staging buffer and then all-reduce that tile right there, tile by tile, while the MMA warp
+//     is already multiplying the next tile: block-paired cross-GPU barrier (the same tile is
+//     owned by the same CTA index on every rank), `multimem.ld_reduce.add.acc::f32.v4.bf16x2` of
+//     this rank's 1/P row-slice of the tile (summed in fp32 INSIDE the NVSwitch), `multimem.st`
+//     of the result to every rank, second barrier, copy of the finished tile to the output.
+//     NVLink traffic equals that of a stand-alone bf16 allreduce, but it is hidden behind the
+//     tensor-core work of the following tiles (first version pushed fp32 fragments to all ranks
+//     with `multimem.red`: correct but P x the traffic as uncoalesced atomics, 10x slower).
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (one TMEM lane quarter each).  Persistent: grid =
-// min(#tiles, #SMs), every CTA walks tiles blockIdx.x, +gridDim.x, ...
+// allocator, warps 4-7 = epilogue + per-tile collective (one TMEM lane quarter each).
+// Persistent: grid = min(#tiles, #SMs), every CTA walks tiles blockIdx.x, +gridDim.x, ...
 // Shapes: M, N multiples of 128, K multiple of 64 (checked by the host wrapper).
 #include <cstdio>
 #include <cstring>
@@ -41,7 +45,7 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr int GEMM_THREADS = 256;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2, B_STAGE_BYTES = BN * BK * 2;
-constexpr uint32_t TMEM_COLS = 128;
+constexpr uint32_t TMEM_COLS = 256;     // two fp32 accumulator stages of 128 columns
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1,
 // B=bf16 [10,13)=1, A and B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -50,10 +54,7 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >
 struct GemmArgs {
   int M, N, K;
   __nv_bfloat16* out;
-  float* acc_mc;       // multicast alias of the accumulator segment (fused path)
-  float* acc_local;    // this rank's copy
-  size_t acc_half;     // floats per parity
-  int fused;
+  int fused;           // > 1 rank: per-tile NVLS allreduce through the staging segment
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t cnt) {
@@ -110,16 +111,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mc_red_add4(float* mc, uint32_t a, uint32_t b, uint32_t c2, uint32_t d) {
-  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(a), "r"(b),
-               "r"(c2), "r"(d) : "memory");
+__device__ __forceinline__ uint4 mc_ld_reduce_bf16(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st16(void* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w) : "memory");
+}
+// cross-GPU barrier executed by the 128 epilogue threads only (named barrier 1), CTA b <-> CTA b
+__device__ __forceinline__ void epi_barrier_all(const B2DevComm& c, unsigned e, int et) {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (et < c.size) {
+    unsigned* remote = (unsigned*)(c.heap[et] + c.lay.flags_off) + (size_t)blockIdx.x * B2_MAX_RANKS + c.rank;
+    b2_st_release_sys(remote, e);
+    const unsigned* local =
+        (const unsigned*)(c.heap[c.rank] + c.lay.flags_off) + (size_t)blockIdx.x * B2_MAX_RANKS + et;
+    b2_wait_ge(c, local, e, B2_OPC_ALLREDUCE, et);
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const B2DevComm c, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,12 +151,11 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     ticket = b2_ticket_read(c.ticket);
     e = b2_ld_volatile(c.epoch + blockIdx.x);
   }
-  const size_t par = (size_t)(ticket & 1u) * g.acc_half;
+  const size_t par = (size_t)(ticket & 1u) * c.stage_half;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar(&full_bar[s]), 1); mbar_init(bar(&empty_bar[s]), 1); }
-    mbar_init(bar(&tmem_full_bar), 1);
-    mbar_init(bar(&tmem_empty_bar), 4);
+    for (int a = 0; a < 2; ++a) { mbar_init(bar(&tmem_full_bar[a]), 1); mbar_init(bar(&tmem_empty_bar[a]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -167,101 +185,95 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer (one thread) =====
-    uint32_t stage = 0, phase = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      mbar_wait(bar(&tmem_empty_bar), acc_phase ^ 1u);        // epilogue drained the accumulator
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1u, aph = (it >> 1) & 1u;        // accumulator stage / its phase
+      mbar_wait(bar(&tmem_empty_bar[as]), aph ^ 1u);            // epilogue drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint32_t tmem_d = tmem_base + as * 128u;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(bar(&full_bar[stage]), phase);               // TMA landed this stage
+        mbar_wait(bar(&full_bar[stage]), phase);                // TMA landed this stage
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint64_t adesc = umma_desc(smem_a + stage * A_STAGE_BYTES);
         const uint64_t bdesc = umma_desc(smem_b + stage * B_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k)                  // +32 B per UMMA_K inside the swizzle atom
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0);
-        umma_commit(bar(&empty_bar[stage]));                   // frees the smem stage when the MMAs retire
-        if (kb == num_kb - 1) umma_commit(bar(&tmem_full_bar)); // accumulator complete
+        for (int k = 0; k < BK / UMMA_K; ++k)                   // +32 B per UMMA_K inside the swizzle atom
+          umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0);
+        umma_commit(bar(&empty_bar[stage]));                    // frees the smem stage when the MMAs retire
+        if (kb == num_kb - 1) umma_commit(bar(&tmem_full_bar[as])); // accumulator complete
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      acc_phase ^= 1u;
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> multimem.red (fused) / bf16 store (single rank) =====
+    // ===== epilogue: TMEM -> bf16 -> (staging + per-tile NVLS allreduce | output) =====
     const int q = warp & 3;                                     // TMEM lane quarter of this warp
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int et = threadIdx.x - 128;                           // 0..127 within the epilogue group
+    __nv_bfloat16* stage_local = (__nv_bfloat16*)(c.stage[c.rank] + par);
+    __nv_bfloat16* stage_mc = (__nv_bfloat16*)(c.stage_mc + par);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      mbar_wait(bar(&tmem_full_bar), acc_phase);
+      mbar_wait(bar(&tmem_full_bar[as]), aph);
       asm volatile("tcgen05.fence::after_thread_sync;");
       const size_t row = (size_t)m_blk * BM + q * 32 + lane;
+      __nv_bfloat16* dst_base = (g.fused ? stage_local : g.out) + row * g.N + (size_t)n_blk * BN;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-        const size_t col = (size_t)n_blk * BN + ch * 32;
-        if (g.fused) {
-          float* dst = g.acc_mc + par + row * g.N + col;
+        tmem_ld32(tmem_base + as * 128u + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+        __nv_bfloat16* dst = dst_base + ch * 32;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) mc_red_add4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-          __nv_bfloat16* dst = g.out + row * g.N + col;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(dst + i) = pk;
-          }
+        for (int i = 0; i < 32; i += 8) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+          __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+          pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(dst + i) = pk;
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(&tmem_empty_bar));         // 4 arrivals free the accumulator
-      acc_phase ^= 1u;
-    }
-  }
-
-  // ===== fused tail: every rank's partial tiles have been added by the switch =====
-  if (g.fused) {
-    b2_barrier_all(c, ++e, B2_OPC_ALLREDUCE);
-    float* mine = g.acc_local + par;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
-      for (int i = threadIdx.x; i < BM * BN / 4; i += GEMM_THREADS) {
-        const int r = i / (BN / 4), c4 = i % (BN / 4);
-        const size_t off = ((size_t)m_blk * BM + r) * g.N + (size_t)n_blk * BN + c4 * 4;
-        const uint4 raw = b2_ld_peer16(mine + off);               // strong load: written by the switch
-        __nv_bfloat162 lo = __floats2bfloat162_rn(__uint_as_float(raw.x), __uint_as_float(raw.y));
-        __nv_bfloat162 hi = __floats2bfloat162_rn(__uint_as_float(raw.z), __uint_as_float(raw.w));
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(g.out + off) = pk;
-        b2_st16(mine + off, make_uint4(0, 0, 0, 0));             // accumulator is zero between calls
+      if (lane == 0) mbar_arrive(bar(&tmem_empty_bar[as]));     // accumulator free: MMA warp runs ahead
+      if (g.fused) {
+        // --- all-reduce THIS tile across the ranks while the next tile is being multiplied ---
+        epi_barrier_all(c, ++e, et);                            // every rank staged its partial tile
+        // my slice: rows [r0, r1) of the tile; a row is BN bf16 = 256 B = 16 vectors
+        const int per = (BM + c.size - 1) / c.size;
+        const int r0 = per * c.rank < BM ? per * c.rank : BM, r1 = r0 + per < BM ? r0 + per : BM;
+        for (int i = et; i < (r1 - r0) * (BN / 8); i += 128) {
+          const int r = r0 + i / (BN / 8), v8 = i % (BN / 8);
+          const size_t off = ((size_t)m_blk * BM + r) * g.N + (size_t)n_blk * BN + v8 * 8;
+          mc_st16(stage_mc + off, mc_ld_reduce_bf16(stage_mc + off));   // in-switch fp32 sum, broadcast
+        }
+        epi_barrier_all(c, ++e, et);                            // all slices of the tile have landed
+        for (int i = et; i < BM * (BN / 8); i += 128) {
+          const int r = i / (BN / 8), v8 = i % (BN / 8);
+          const size_t off = ((size_t)m_blk * BM + r) * g.N + (size_t)n_blk * BN + v8 * 8;
+          b2_st16(g.out + off, b2_ld_peer16(stage_local + off));
+        }
       }
     }
+    if (g.fused && et == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
   }
+
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
-  if (g.fused) {
-    if (threadIdx.x == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
-    b2_finish_bump(c.ticket, c.ticket + 1, 1u, gridDim.x);
-  }
+  if (g.fused) b2_finish_bump(c.ticket, c.ticket + 1, 1u, gridDim.x);
 }
 
 }  // namespace
 
 // out (M x N, bf16) = sum over ranks of A (M x K, bf16, row-major) @ B^T (B: N x K, bf16, row-major).
-// acc/acc_mc: zero-initialised symmetric fp32 accumulator segment (2 x M*N floats) and its
-// multicast object; pass null (or use a 1-rank communicator) for a purely local GEMM.
+// Multi-rank calls stage the bf16 partial tiles in the communicator's multicast-bound staging
+// segment (M*N*2 bytes per parity; grown by the Python layer like for any other collective).
 extern "C" int b2_gemm_allreduce(B2Comm* c, const void* A, const void* B, void* out, int M, int N, int K,
-                                 B2Seg* acc, B2Mc* acc_mc, cudaStream_t stream) {
+                                 cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || M % BM || N % BN || K % BK) {
     b2_set_error("gemm_allreduce: need M %% %d == 0, N %% %d == 0, K %% %d == 0 (got %d, %d, %d)", BM, BN,
                  BK, M, N, K);
@@ -273,19 +285,15 @@ extern "C" int b2_gemm_allreduce(B2Comm* c, const void* A, const void* B, void* 
   g.out = (__nv_bfloat16*)out;
   g.fused = (c->dev.size > 1) ? 1 : 0;
   if (g.fused) {
-    if (!acc || !acc_mc || !acc_mc->ptr) {
-      b2_set_error("gemm_allreduce: multi-rank call needs a multicast-bound accumulator segment");
+    if (c->dev.stage_mc == nullptr) {
+      b2_set_error("gemm_allreduce: multi-rank call needs a multicast-bound staging segment (NVLS)");
       return B2_ERR_BAD_ARG;
     }
-    const size_t half_floats = (acc->bytes / 2) / sizeof(float) / 1024 * 1024;
-    if ((size_t)M * N > half_floats) {
-      b2_set_error("gemm_allreduce: accumulator segment too small (%zu floats < %zu)", half_floats,
-                   (size_t)M * N);
+    if ((size_t)M * N * 2 + 4096 > c->dev.stage_half) {
+      b2_set_error("gemm_allreduce: staging too small (need %zu bytes, have %zu)", (size_t)M * N * 2 + 4096,
+                   c->dev.stage_half);
       return B2_ERR_BAD_ARG;
     }
-    g.acc_local = (float*)acc->ptr[c->dev.rank];
-    g.acc_mc = (float*)acc_mc->ptr;
-    g.acc_half = half_floats;
   }
   CUtensorMap ta, tb;
   if (b2_tensor_map_2d_bf16(&ta, A, (unsigned long long)M, (unsigned long long)K, BM, BK) ||

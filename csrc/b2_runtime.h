@@ -136,7 +136,7 @@ int b2_sendrecv(B2Comm* c, const void* sendbuf, size_t send_bytes, int dest, int
 
 // --- tensor-parallel linear: tcgen05 GEMM + in-switch allreduce in one kernel (b2_gemm.cu) ---
 int b2_gemm_allreduce(B2Comm* c, const void* A, const void* B, void* out, int M, int N, int K,
-                      B2Seg* acc, B2Mc* acc_mc, cudaStream_t stream);
+                      cudaStream_t stream);
 
 // --- fused halo exchange + shallow-water stencils (see b2_halo.cu, b2_swe.cu) --
 struct B2HaloDesc {

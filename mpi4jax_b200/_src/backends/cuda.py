@@ -241,7 +241,6 @@ class NativeComm:
             raise MPIError(f"native communicator creation failed: {native.last_error()}")
         self.stage: Optional[_Segment] = None
         self._stage_half = 0
-        self._acc: Optional[_Segment] = None
         self._retired: list = []
         self._status_pool: list = []
         self._grow_stage(_MIN_STAGE)
@@ -321,9 +320,6 @@ class NativeComm:
         if self.stage is not None:
             self.stage.destroy()
             self.stage = None
-        if self._acc is not None:
-            self._acc.destroy()
-            self._acc = None
         if self.ctl is not None:
             self.ctl.destroy()
             self.ctl = None
@@ -470,24 +466,12 @@ class NativeComm:
         M, K = x.shape
         N = weight.shape[0]
         out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
-        acc = None
         if self.comm.size > 1:
-            if not self.want_mc:
+            if not self.has_nvls:
                 raise MPIError("gemm_allreduce needs NVLS multicast support")
-            need = 2 * M * N * 4 + (1 << 16)
-            if self._acc is None or self._acc.bytes < need:
-                if torch.cuda.is_current_stream_capturing():
-                    raise RuntimeError("gemm_allreduce: accumulator growth during CUDA-graph capture; "
-                                       "run once eagerly first")
-                torch.cuda.synchronize()
-                old, self._acc = self._acc, _Segment(self.comm, self.device, need, "vmm", want_mc=True)
-                if old is not None:
-                    old.destroy()
-                if self._acc.mc is None:
-                    raise MPIError("gemm_allreduce: could not create the multicast accumulator")
-            acc = self._acc
+            self.ensure_stage(codes.OPC_ALLREDUCE, M * N * 2)
         rc = _lib().b2_gemm_allreduce(self.handle, x.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K,
-                                      acc.seg if acc else None, acc.mc if acc else None, self._stream())
+                                      self._stream())
         self._check(rc, "Allreduce")
         return out
 

@@ -161,7 +161,7 @@ _SIGNATURES = {
         [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_size_t, c_int, c_int,
          POINTER(B2StatusRecord), c_void_p],
     ),
-    "b2_gemm_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2_gemm_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2_halo_exchange": (c_int, [c_void_p, POINTER(B2HaloDesc), c_void_p]),
     "b2_swe_fluxes": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 7 + [c_void_p]),
     "b2_swe_tendencies": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 11 + [c_void_p]),

@@ -4,8 +4,8 @@
 K-shard of both operands -- the tensor-parallel pattern of the reference's matvec tests
 (/root/reference/tests/collective_ops/test_allreduce_matvec.py:41-65).  On CUDA with bf16
 operands and tile-aligned shapes it runs as ONE hand-written sm_100a kernel (tcgen05 MMAs,
-TMA-fed, accumulator in TMEM, partial tiles added across GPUs by the NVSwitch through
-``multimem.red``, csrc/b2_gemm.cu); otherwise it falls back to ``torch.matmul`` + ``allreduce``.
+TMA-fed, accumulators in TMEM, every finished tile all-reduced in the NVSwitch with
+``multimem.ld_reduce`` / ``multimem.st`` while the next tile is being multiplied, csrc/b2_gemm.cu); otherwise it falls back to ``torch.matmul`` + ``allreduce``.
 Differentiable: the adjoint of the allreduce is the identity on the replicated cotangent, so
 ``grad_x = g @ weight`` and ``grad_weight = g.T @ x`` are plain local GEMMs.
 """
@@ -32,7 +32,7 @@ def _fusable(x: torch.Tensor, w: torch.Tensor) -> bool:
 def _forward(x: torch.Tensor, w: torch.Tensor, comm: Comm) -> torch.Tensor:
     if _fusable(x, w):
         nc = comm._native_comm()
-        if comm.Get_size() == 1 or nc.want_mc:
+        if comm.Get_size() == 1 or nc.has_nvls:
             return nc.gemm_allreduce(x.contiguous(), w.contiguous())
     return _dispatch.allreduce(comm, (x @ w.t()).contiguous(), SUM.code)
 
