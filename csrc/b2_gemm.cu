@@ -211,6 +211,8 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     __nv_bfloat16* stage_local = (__nv_bfloat16*)(c.stage[c.rank] + par);
     __nv_bfloat16* stage_mc = (__nv_bfloat16*)(c.stage_mc + par);
     uint32_t it = 0;
+    constexpr int GROUP = 4;                                    // tiles per collective round
+    int pend[GROUP], np = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -239,21 +241,53 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(&tmem_empty_bar[as]));     // accumulator free: MMA warp runs ahead
       if (g.fused) {
-        // --- all-reduce THIS tile across the ranks while the next tile is being multiplied ---
-        epi_barrier_all(c, ++e, et);                            // every rank staged its partial tile
-        // my slice: rows [r0, r1) of the tile; a row is BN bf16 = 256 B = 16 vectors
-        const int per = (BM + c.size - 1) / c.size;
-        const int r0 = per * c.rank < BM ? per * c.rank : BM, r1 = r0 + per < BM ? r0 + per : BM;
-        for (int i = et; i < (r1 - r0) * (BN / 8); i += 128) {
-          const int r = r0 + i / (BN / 8), v8 = i % (BN / 8);
-          const size_t off = ((size_t)m_blk * BM + r) * g.N + (size_t)n_blk * BN + v8 * 8;
-          mc_st16(stage_mc + off, mc_ld_reduce_bf16(stage_mc + off));   // in-switch fp32 sum, broadcast
-        }
-        epi_barrier_all(c, ++e, et);                            // all slices of the tile have landed
-        for (int i = et; i < BM * (BN / 8); i += 128) {
-          const int r = i / (BN / 8), v8 = i % (BN / 8);
-          const size_t off = ((size_t)m_blk * BM + r) * g.N + (size_t)n_blk * BN + v8 * 8;
-          b2_st16(g.out + off, b2_ld_peer16(stage_local + off));
+        // --- all-reduce finished tiles across the ranks while the next tiles are being multiplied.
+        // GROUP tiles share one pair of cross-GPU barriers; all loads of a batch are issued before
+        // the first dependent store so the NVLink / L2 round trips overlap instead of adding up.
+        pend[np++] = tile;
+        const bool last = tile + (int)gridDim.x >= tiles;
+        if (np == GROUP || last) {
+          epi_barrier_all(c, ++e, et);                          // every rank staged these partial tiles
+          const int per = (BM + c.size - 1) / c.size;           // my row-slice of every tile
+          const int r0 = per * c.rank < BM ? per * c.rank : BM, r1 = r0 + per < BM ? r0 + per : BM;
+          const int slice_vec = (r1 - r0) * (BN / 8), nred = np * slice_vec;
+          for (int base = et; base < nred; base += 128 * 4) {
+            uint4 v[4];
+            size_t offs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = base + u * 128;
+              if (i < nred) {
+                const int slot = i / slice_vec, w = i - slot * slice_vec;
+                const int tl = pend[slot], r = r0 + w / (BN / 8), v8 = w % (BN / 8);
+                offs[u] = ((size_t)(tl / num_n) * BM + r) * g.N + (size_t)(tl % num_n) * BN + v8 * 8;
+                v[u] = mc_ld_reduce_bf16(stage_mc + offs[u]);   // fp32 sum inside the NVSwitch
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (base + u * 128 < nred) mc_st16(stage_mc + offs[u], v[u]);   // broadcast to every rank
+          }
+          epi_barrier_all(c, ++e, et);                          // all slices of these tiles have landed
+          const int ncp = np * BM * (BN / 8);
+          for (int base = et; base < ncp; base += 128 * 8) {
+            uint4 v[8];
+            size_t offs[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int i = base + u * 128;
+              if (i < ncp) {
+                const int slot = i / (BM * (BN / 8)), w = i - slot * (BM * (BN / 8));
+                const int tl = pend[slot], r = w / (BN / 8), v8 = w % (BN / 8);
+                offs[u] = ((size_t)(tl / num_n) * BM + r) * g.N + (size_t)(tl % num_n) * BN + v8 * 8;
+                v[u] = b2_ld_peer16(stage_local + offs[u]);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (base + u * 128 < ncp) b2_st16(g.out + offs[u], v[u]);
+          }
+          np = 0;
         }
       }
     }
