@@ -7,11 +7,11 @@
 // tests/collective_ops/test_allreduce_matvec.py:41-65).  There the product is one XLA op and
 // the reduction a blocking MPI call afterwards; here both are one sm_100a kernel:
 //
-//   * 5th-gen tensor cores: `tcgen05.mma.cta_group::1.kind::f16` (128x128x16 UMMA, bf16 in,
+//   * 5th-gen tensor cores: `tcgen05.mma.cta_group::1.kind::f16` (128x256x16 UMMA, bf16 in,
 //     fp32 accumulate) issued by ONE thread per CTA, operands staged by TMA
 //     (`cp.async.bulk.tensor.2d`, 128-byte swizzle) through a 4-stage mbarrier ring, the
-//     accumulator lives in TMEM (128 columns) and is read back with `tcgen05.ld`;
-//     two accumulator stages (2 x 128 TMEM columns) let the MMA warp run one tile ahead;
+//     accumulator lives in TMEM and is read back with `tcgen05.ld`; two accumulator stages
+//     (2 x 256 columns = the whole TMEM) let the MMA warp run one tile ahead of the epilogue;
 //   * the epilogue warps turn a finished tile into bf16, store it into this rank's SYMMETRIC
 //     staging buffer and then all-reduce that tile right there, tile by tile, while the MMA warp
 //     is already multiplying the next tile: block-paired cross-GPU barrier (the same tile is
@@ -42,14 +42,15 @@ extern "C" int b2_tensor_map_2d_bf16(CUtensorMap* out, const void* ptr, unsigned
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int BM = 128, BK = 64, STAGES = 4, UMMA_K = 16;   // BN (128 or 256) is a template parameter
 constexpr int GEMM_THREADS = 256;
-constexpr uint32_t A_STAGE_BYTES = BM * BK * 2, B_STAGE_BYTES = BN * BK * 2;
-constexpr uint32_t TMEM_COLS = 256;     // two fp32 accumulator stages of 128 columns
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1,
 // B=bf16 [10,13)=1, A and B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                           ((uint32_t)(BM >> 4) << 24);
+template <int BN>
+constexpr uint32_t idesc_bf16() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 
 struct GemmArgs {
   int M, N, K;
@@ -88,11 +89,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accum) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accum) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
-      "r"(IDESC), "r"(accum));
+      "r"(idesc), "r"(accum));
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -134,9 +136,11 @@ __device__ __forceinline__ void epi_barrier_all(const B2DevComm& c, unsigned e, 
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
+template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const B2DevComm c, const GemmArgs g) {
+  constexpr uint32_t B_STAGE_BYTES = BN * BK * 2, TMEM_COLS = 2 * BN, IDESC = idesc_bf16<BN>();
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -190,7 +194,7 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;        // accumulator stage / its phase
       mbar_wait(bar(&tmem_empty_bar[as]), aph ^ 1u);            // epilogue drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint32_t tmem_d = tmem_base + as * 128u;
+      const uint32_t tmem_d = tmem_base + as * (uint32_t)BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(bar(&full_bar[stage]), phase);                // TMA landed this stage
         asm volatile("tcgen05.fence::after_thread_sync;");
@@ -198,7 +202,7 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const uint64_t bdesc = umma_desc(smem_b + stage * B_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k)                   // +32 B per UMMA_K inside the swizzle atom
-          umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0);
+          umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) != 0);
         umma_commit(bar(&empty_bar[stage]));                    // frees the smem stage when the MMAs retire
         if (kb == num_kb - 1) umma_commit(bar(&tmem_full_bar[as])); // accumulator complete
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -223,7 +227,7 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + as * 128u + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+        tmem_ld32(tmem_base + as * (uint32_t)BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
         __nv_bfloat16* dst = dst_base + ch * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -308,8 +312,8 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 // segment (M*N*2 bytes per parity; grown by the Python layer like for any other collective).
 extern "C" int b2_gemm_allreduce(B2Comm* c, const void* A, const void* B, void* out, int M, int N, int K,
                                  cudaStream_t stream) {
-  if (M <= 0 || N <= 0 || K <= 0 || M % BM || N % BN || K % BK) {
-    b2_set_error("gemm_allreduce: need M %% %d == 0, N %% %d == 0, K %% %d == 0 (got %d, %d, %d)", BM, BN,
+  if (M <= 0 || N <= 0 || K <= 0 || M % BM || N % 128 || K % BK) {
+    b2_set_error("gemm_allreduce: need M %% %d == 0, N %% %d == 0, K %% %d == 0 (got %d, %d, %d)", BM, 128,
                  BK, M, N, K);
     return B2_ERR_BAD_ARG;
   }
@@ -329,26 +333,29 @@ extern "C" int b2_gemm_allreduce(B2Comm* c, const void* A, const void* B, void* 
       return B2_ERR_BAD_ARG;
     }
   }
+  const int BN = (N % 256 == 0) ? 256 : 128;      // 128x256 tiles halve the MMA count per FLOP
   CUtensorMap ta, tb;
   if (b2_tensor_map_2d_bf16(&ta, A, (unsigned long long)M, (unsigned long long)K, BM, BK) ||
       b2_tensor_map_2d_bf16(&tb, B, (unsigned long long)N, (unsigned long long)K, BN, BK))
     return B2_ERR_BAD_ARG;
-  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(b2_k_gemm_allreduce, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + (size_t)BN * BK * 2) + 1024;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[BN == 256]) {
+    cudaError_t e = BN == 256
+        ? cudaFuncSetAttribute(b2_k_gemm_allreduce<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        : cudaFuncSetAttribute(b2_k_gemm_allreduce<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       b2_set_error("gemm_allreduce: cannot reserve %zu bytes of shared memory: %s", smem,
                    cudaGetErrorString(e));
       return 1000 + (int)e;
     }
-    attr_set = true;
+    attr_set[BN == 256] = true;
   }
   const int tiles = (M / BM) * (N / BN);
   int grid = tiles < c->sm_count ? tiles : c->sm_count;
   if (grid > B2_MAX_BLOCKS) grid = B2_MAX_BLOCKS;
-  b2_k_gemm_allreduce<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, c->dev, g);
+  if (BN == 256) b2_k_gemm_allreduce<256><<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, c->dev, g);
+  else b2_k_gemm_allreduce<128><<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, c->dev, g);
   b2_count_launch(c);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
