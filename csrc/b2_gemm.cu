@@ -48,7 +48,7 @@ constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1,
 // B=bf16 [10,13)=1, A and B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
 template <int BN>
-constexpr uint32_t idesc_bf16() {
+__host__ __device__ constexpr uint32_t idesc_bf16() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
