@@ -207,9 +207,11 @@ static void pick_chunks(const B2Comm* c, size_t nbytes, size_t* chunk_out, int* 
   const size_t min_chunk = round_up(16 * 1024, unit);
   const size_t max_chunk = round_up(512 * 1024, unit);
   const size_t target = (size_t)c->max_blocks;
-  // aim for ~4 chunks per CTA: CTAs then sit at different phases (copy-in / reduce-scatter /
-  // all-gather / copy-out), which overlaps local HBM traffic with both NVLink directions
-  size_t chunk = round_up((nbytes + 4 * target - 1) / (4 * target), unit);
+  // large messages: ~4 chunks per CTA, so that CTAs sit at different phases (copy-in / reduce-
+  // scatter / all-gather / copy-out) and local HBM traffic overlaps both NVLink directions;
+  // below 64 MiB one chunk per CTA is faster (latency regime; measured, profiles/README.md)
+  const size_t per_cta = nbytes >= ((size_t)64 << 20) ? 4 : 1;
+  size_t chunk = round_up((nbytes + per_cta * target - 1) / (per_cta * target), unit);
   if (chunk < min_chunk) chunk = min_chunk;
   if (chunk > max_chunk) chunk = max_chunk;
   size_t nchunks = (nbytes + chunk - 1) / chunk;
