@@ -45,7 +45,7 @@ swe_k1_fluxes(B2SweParams p, const float* __restrict__ h, const float* __restric
   swe_k1_body(p, h, u, v, fe, fn, q, ke, j, i0, m, o);
 }
 
-__global__ void __launch_bounds__(SWE_THREADS)
+__global__ void __launch_bounds__(SWE_THREADS, 3)
 swe_k2_tendencies(B2SweParams p, const float* __restrict__ h, float* __restrict__ h_new,
                   float* __restrict__ u, float* __restrict__ v, float* __restrict__ dh,
                   float* __restrict__ du, float* __restrict__ dv, const float* __restrict__ fe,

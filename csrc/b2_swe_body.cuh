@@ -10,6 +10,7 @@
 struct B2SweParams {
   int ny, nx, pitch;
   float dx, dy, dt, gravity, viscosity;
+  float rdx, rdy;             // 1/dx, 1/dy: x * (1/dx) instead of x / dx (<= 1 ulp apart, ~8x cheaper)
   float ab_a, ab_b;           // Adams-Bashforth weights
   int first_step;
   int south_wall, north_wall; // this rank touches the y walls (hc edge padding)
@@ -87,7 +88,7 @@ __device__ __forceinline__ void swe_k1_body(const B2SweParams& p, const float* _
     const float uk = U[k + 1], vk = V[k];
     FE[k] = 0.5f * (H[k] + H[k + 1]) * uk;
     FN[k] = 0.5f * (H[k] + HN[k]) * vk;
-    const float rel = (V[k + 1] - vk) / p.dx - (UN[k] - uk) / p.dy;
+    const float rel = (V[k + 1] - vk) * p.rdx - (UN[k] - uk) * p.rdy;
     Q[k] = (cor + rel) * (1.0f / (0.25f * (H[k] + H[k + 1] + HN[k] + HN[k + 1])));
     KE[k] = 0.5f * (0.5f * (uk * uk + U[k] * U[k]) + 0.5f * (vk * vk + VS[k] * VS[k]));
     if (!m[k]) FE[k] = FN[k] = Q[k] = KE[k] = 0.f;   // halo / pad lanes: refreshed by the exchange
@@ -130,13 +131,13 @@ __device__ __forceinline__ void swe_k2_body(const B2SweParams& p, const float* _
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float fe_c = FE[k + 1], fe_w = FE[k], fn_c = FN[k], q_c = Q[k + 1];
-    const float dh_new = -(fe_c - fe_w) / p.dx - (fn_c - FNS[k]) / p.dy;
-    float du_new = -p.gravity * (H[k + 1] - H[k]) / p.dx +
+    const float dh_new = -(fe_c - fe_w) * p.rdx - (fn_c - FNS[k]) * p.rdy;
+    float du_new = -p.gravity * (H[k + 1] - H[k]) * p.rdx +
                    0.5f * (q_c * 0.5f * (fn_c + FN[k + 1]) + QS[k] * 0.5f * (FNS[k] + FNS[k + 1]));
-    float dv_new = -p.gravity * (HN[k] - H[k]) / p.dy -
+    float dv_new = -p.gravity * (HN[k] - H[k]) * p.rdy -
                    0.5f * (q_c * 0.5f * (fe_c + FEN[k + 1]) + Q[k] * 0.5f * (fe_w + FEN[k]));
-    du_new += -(KE[k + 1] - KE[k]) / p.dx;
-    dv_new += -(KEN[k] - KE[k]) / p.dy;
+    du_new += -(KE[k + 1] - KE[k]) * p.rdx;
+    dv_new += -(KEN[k] - KE[k]) * p.rdy;
     if (p.first_step) {
       Un[k] = Uo[k] + p.dt * du_new;
       Vn[k] = Vo[k] + p.dt * dv_new;
@@ -175,8 +176,8 @@ __device__ __forceinline__ void swe_k3_body(const B2SweParams& p, const float* _
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const bool mf = m[k] || (local_halo && i0 + k == 0);
-    FE[k] = mf ? p.viscosity * (U[k + 1] - U[k]) / p.dx : 0.f;
-    FN[k] = m[k] ? p.viscosity * (UN[k] - U[k]) / p.dy : 0.f;
+    FE[k] = mf ? p.viscosity * (U[k + 1] - U[k]) * p.rdx : 0.f;
+    FN[k] = m[k] ? p.viscosity * (UN[k] - U[k]) * p.rdy : 0.f;
     if (p.north_wall && j == p.ny - 2) FN[k] = 0.f;
   }
   const size_t off = (size_t)j * P + i0;
@@ -187,7 +188,7 @@ __device__ __forceinline__ void swe_k3_body(const B2SweParams& p, const float* _
     const float US[4] = {us.x, us.y, us.z, us.w};
     float F0[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) F0[k] = m[k] ? p.viscosity * (U[k] - US[k]) / p.dy : 0.f;
+    for (int k = 0; k < 4; ++k) F0[k] = m[k] ? p.viscosity * (U[k] - US[k]) * p.rdy : 0.f;
     st4(fn, (size_t)i0, make_float4(F0[0], F0[1], F0[2], F0[3]));
   }
 }
@@ -210,11 +211,11 @@ __device__ __forceinline__ void swe_k4_body(const B2SweParams& p, float* __restr
   float Un[4], FE2[4], FN2[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float un = Uo[k] + p.dt * ((FE[k + 1] - FE[k]) / p.dx + (FN[k] - FNS[k]) / p.dy);
+    const float un = Uo[k] + p.dt * ((FE[k + 1] - FE[k]) * p.rdx + (FN[k] - FNS[k]) * p.rdy);
     Un[k] = m[k] ? un : Uo[k];
     // NOTE: `v - u` mirrors the reference (examples/shallow_water.py:387-392)
-    FE2[k] = m[k] ? p.viscosity * (V[k + 1] - un) / p.dx : 0.f;
-    FN2[k] = m[k] ? p.viscosity * (VN[k] - un) / p.dy : 0.f;
+    FE2[k] = m[k] ? p.viscosity * (V[k + 1] - un) * p.rdx : 0.f;
+    FN2[k] = m[k] ? p.viscosity * (VN[k] - un) * p.rdy : 0.f;
     if (p.north_wall && j == p.ny - 2) FN2[k] = 0.f;
     o.a[0][k] = FE2[k]; o.a[1][k] = FN2[k];
   }
@@ -250,15 +251,15 @@ __device__ __forceinline__ void swe_k34_body(const B2SweParams& p, float* __rest
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float uk = U[k + 1];
-    const float fe_c = p.viscosity * (U[k + 2] - uk) / p.dx;
-    const float fe_w = p.viscosity * (uk - U[k]) / p.dx;
-    const float fn_c = fn_c_zero ? 0.f : p.viscosity * (UN[k] - uk) / p.dy;
-    const float fn_s = fn_s_zero ? 0.f : p.viscosity * (uk - US[k]) / p.dy;
-    const float un = uk + p.dt * ((fe_c - fe_w) / p.dx + (fn_c - fn_s) / p.dy);
+    const float fe_c = p.viscosity * (U[k + 2] - uk) * p.rdx;
+    const float fe_w = p.viscosity * (uk - U[k]) * p.rdx;
+    const float fn_c = fn_c_zero ? 0.f : p.viscosity * (UN[k] - uk) * p.rdy;
+    const float fn_s = fn_s_zero ? 0.f : p.viscosity * (uk - US[k]) * p.rdy;
+    const float un = uk + p.dt * ((fe_c - fe_w) * p.rdx + (fn_c - fn_s) * p.rdy);
     Un[k] = m[k] ? un : uk;
     // NOTE: `v - u` mirrors the reference (examples/shallow_water.py:387-392)
-    FE2[k] = m[k] ? p.viscosity * (V[k + 1] - un) / p.dx : 0.f;
-    FN2[k] = m[k] ? p.viscosity * (VN[k] - un) / p.dy : 0.f;
+    FE2[k] = m[k] ? p.viscosity * (V[k + 1] - un) * p.rdx : 0.f;
+    FN2[k] = m[k] ? p.viscosity * (VN[k] - un) * p.rdy : 0.f;
     if (p.north_wall && j == p.ny - 2) FN2[k] = 0.f;
     o.a[0][k] = FE2[k]; o.a[1][k] = FN2[k];
   }
@@ -281,7 +282,7 @@ __device__ __forceinline__ void swe_k5_body(const B2SweParams& p, float* __restr
   float Vn[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float vn = Vo[k] + p.dt * ((FE[k + 1] - FE[k]) / p.dx + (FN[k] - FNS[k]) / p.dy);
+    const float vn = Vo[k] + p.dt * ((FE[k + 1] - FE[k]) * p.rdx + (FN[k] - FNS[k]) * p.rdy);
     Vn[k] = m[k] ? vn : Vo[k];
   }
   st4(v, off, make_float4(Vn[0], Vn[1], Vn[2], Vn[3]));

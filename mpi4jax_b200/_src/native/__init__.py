@@ -74,6 +74,8 @@ class B2SweParams(Structure):
         ("dt", c_float),
         ("gravity", c_float),
         ("viscosity", c_float),
+        ("rdx", c_float),
+        ("rdy", c_float),
         ("ab_a", c_float),
         ("ab_b", c_float),
         ("first_step", c_int),

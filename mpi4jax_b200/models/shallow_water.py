@@ -160,6 +160,8 @@ class ShallowWaterModel:
             p.ny, p.nx, p.pitch = self.ny_local, self.nx_local, self.pitch
             p.dx, p.dy, p.dt = self.cfg.dx, self.cfg.dy, self.cfg.dt
             p.gravity, p.viscosity = self.cfg.gravity, self.cfg.lateral_viscosity
+            p.rdx = float(np.float32(1.0) / np.float32(self.cfg.dx))
+            p.rdy = float(np.float32(1.0) / np.float32(self.cfg.dy))
             p.ab_a, p.ab_b = self.cfg.ab_a, self.cfg.ab_b
             p.first_step = 0
             p.south_wall, p.north_wall = int(self.at_south_wall), int(self.at_north_wall)
