@@ -30,11 +30,12 @@ from ._src import (  # noqa: F401
 )
 from . import MPI  # noqa: F401
 from ._src.jit import jit, linear_transpose  # noqa: F401
+from ._src.compile_ops import compiled  # noqa: F401  (torch.library / torch.compile frontend)
 
 effects_barrier = flush
 
 __all__ = [
     "allgather", "allreduce", "alltoall", "barrier", "bcast", "gather", "recv", "reduce",
     "scan", "scatter", "send", "sendrecv", "has_cuda_support", "has_sycl_support",
-    "MPI", "jit", "flush", "effects_barrier", "linear_transpose", "send_with_grad",
+    "MPI", "jit", "compiled", "flush", "effects_barrier", "linear_transpose", "send_with_grad",
 ]

@@ -1,0 +1,75 @@
+"""torch.library registration: the ops are traceable custom ops with an ORDERED effect, the
+torch counterpart of the reference's JAX primitives + ordered effect token
+(/root/reference/mpi4jax/_src/utils.py:45-53; acceptance test = test_send_recv_deadlock)."""
+
+import pytest
+import torch
+
+import mpi4jax_b200 as m
+from mpi4jax_b200 import MPI
+from mpi4jax_b200 import compiled as mc
+from mpi4jax_b200._src import compile_ops
+
+comm = MPI.COMM_WORLD
+rank, size = comm.Get_rank(), comm.Get_size()
+
+
+def test_ops_are_registered_and_effectful():
+    for name in compile_ops.ALL_OPS:
+        assert hasattr(torch.ops.mpi4jax_b200, name)
+    assert compile_ops.ORDERED_EFFECT, "ordered effect registration failed (torch internals moved?)"
+    from torch._higher_order_ops.effects import _EffectType, _get_effect
+
+    assert _get_effect("mpi4jax_b200::send") == _EffectType.ORDERED
+    assert _get_effect("mpi4jax_b200::barrier") == _EffectType.ORDERED
+
+
+def test_fake_kernels_give_reference_shapes():
+    """abstract-eval rules of the reference: allgather S -> (nproc, *S), ..."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    with FakeTensorMode():
+        x = torch.empty(3, 2)
+        assert mc.allreduce(x, MPI.SUM, comm=comm).shape == (3, 2)
+        assert mc.allgather(x, comm=comm).shape == (size, 3, 2)
+        assert mc.alltoall(torch.empty(size, 4), comm=comm).shape == (size, 4)
+        assert mc.recv(x, source=0, comm=comm).shape == (3, 2)
+        assert mc.sendrecv(torch.empty(5), torch.empty(7), 0, 0, comm=comm).shape == (7,)
+        assert mc.send(x, 0, comm=comm) is None
+
+
+def test_compiled_allreduce_and_grad(device):
+    f = torch.compile(lambda x: (mc.allreduce(x * 2, MPI.SUM, comm=comm) + 1).sum(),
+                      backend="aot_eager", fullgraph=True)
+    x = torch.ones(4, device=device, requires_grad=True)
+    y = f(x)
+    assert y.item() == (2 * size + 1) * 4
+    y.backward()
+    assert torch.equal(x.grad, torch.full((4,), 2.0, device=device))
+
+
+def test_compiled_program_order_is_kept(device):
+    """send / recv / barrier have no data dependence on each other: only the ordered effect
+    keeps them in program order (and keeps the result-less send alive)."""
+
+    def exchange(arr):
+        other = (rank + 1) % size
+        if size == 1:
+            mc.send(arr, rank, tag=3, comm=comm)
+            mc.barrier(comm=comm)
+            return mc.recv(arr, source=rank, tag=3, comm=comm)
+        if rank % 2 == 0:
+            mc.send(arr, other, comm=comm)
+            return mc.recv(arr, (rank - 1) % size, comm=comm)
+        got = mc.recv(arr, (rank - 1) % size, comm=comm)
+        mc.send(arr, other, comm=comm)
+        return got
+
+    if size > 1 and size % 2:
+        pytest.skip("ring with an odd number of ranks needs sendrecv")
+    f = torch.compile(exchange, backend="aot_eager", fullgraph=True)
+    arr = torch.ones(10, device=device) * rank
+    for _ in range(2):
+        out = f(arr)
+        assert torch.equal(out, torch.ones(10, device=device) * ((rank - 1) % size))
+    m.flush()
