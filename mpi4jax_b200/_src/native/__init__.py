@@ -217,6 +217,7 @@ def set_logging(enable: bool) -> None:
 
 
 def get_logging() -> bool:
+    """Whether the per-call debug log is on (also set by ``MPI4JAX_B200_DEBUG=1`` at import)."""
     return _logging
 
 

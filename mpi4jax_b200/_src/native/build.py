@@ -33,7 +33,10 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 
 
 def _nvcc() -> str:
-    for cand in (os.environ.get("MPI4JAX_B200_NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+    roots = [os.environ.get(k) for k in ("CUDA_HOME", "CUDA_PATH", "CUDA_ROOT")]
+    cands = [os.environ.get("MPI4JAX_B200_NVCC"), shutil.which("nvcc"),
+             *[os.path.join(r, "bin", "nvcc") for r in roots if r], "/usr/local/cuda/bin/nvcc"]
+    for cand in cands:
         if cand and Path(cand).exists():
             return cand
     raise RuntimeError("nvcc not found; set MPI4JAX_B200_NVCC")

@@ -14,7 +14,24 @@ import re
 import warnings
 
 MIN_TORCH = "2.4.0"
-LATEST_TESTED_TORCH = "2.11.0"
+
+
+def _read_latest_tested() -> str:
+    """Pinned in ``_latest_torch_version.txt`` (bumped by dependabot, like the reference's
+    ``_latest_jax_version.txt``)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    try:
+        with open(os.path.join(here, "_latest_torch_version.txt")) as f:
+            for line in f:
+                line = line.strip()
+                if line.startswith("torch=="):
+                    return line.split("==", 1)[1]
+    except OSError:  # pragma: no cover
+        pass
+    return "2.11.0"
+
+
+LATEST_TESTED_TORCH = _read_latest_tested()
 
 
 def versiontuple(verstr: str) -> tuple:

@@ -21,7 +21,16 @@ import torch
 from . import comm as _comm
 from .native import codes
 
-NOTSET = object()
+class _NotSet:
+    """Sentinel type of ``NOTSET`` (prints nicely in signatures and generated docs)."""
+
+    __slots__ = ()
+
+    def __repr__(self) -> str:
+        return "NOTSET"
+
+
+NOTSET = _NotSet()
 
 _default_comm: Optional[_comm.Comm] = None
 
