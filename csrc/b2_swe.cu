@@ -181,6 +181,19 @@ struct B2SweState {
   float *h0, *h1, *u, *v, *dh, *du, *dv, *fe, *fn, *q, *ke, *fe2, *fn2;
 };
 
+// Layout record for the import-time ABI check (mpi4jax_b200/_src/native/__init__.py): the Python
+// side mirrors these structs with ctypes, so a stale library with a different layout must be
+// rejected before the first call (the reference checks the MPI handle ABI the same way,
+// xla_bridge/__init__.py:23-89).
+int b2_abi_info(int* out, int n) {
+  const int v[] = {B2_ABI_VERSION,
+                   (int)sizeof(B2StatusRecord), (int)sizeof(B2HaloDesc), (int)sizeof(B2SweParams),
+                   (int)sizeof(B2SweState), (int)sizeof(B2ErrorRecord), B2_MAX_RANKS, B2_P2P_NSLOT};
+  const int have = (int)(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < n && i < have; ++i) out[i] = v[i];
+  return have;
+}
+
 int b2_swe_multistep(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const B2HaloDesc* topo,
                      int nsteps, int first_step, cudaStream_t s) {
   B2SweParams p = *p0;

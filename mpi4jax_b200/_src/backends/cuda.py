@@ -17,6 +17,7 @@ host, so ops can be recorded into CUDA graphs (``mpi4jax_b200.jit``).
 from __future__ import annotations
 
 import ctypes
+import functools
 import os
 import socket
 import sys
@@ -34,6 +35,15 @@ from ..decorators import env_flag, env_float, env_int, setup_cuda_mpi
 from ..native import codes
 
 _MIN_STAGE = 64 << 20
+_POISON = env_flag("MPI4JAX_B200_POISON", False)
+
+
+class _RawDeviceBytes:
+    """``__cuda_array_interface__`` view of raw device memory (for the poison debug mode)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 2}
 
 
 def _lib():
@@ -265,6 +275,14 @@ class NativeComm:
         new = _Segment(self.comm, self.device, size, self.mode, want_mc=self.want_mc)
         lib.b2_comm_set_stage(self.handle, new.seg, new.mc)
         self._stage_half = int(lib.b2_comm_stage_half(self.handle))
+        if _POISON:
+            # debug mode: staging never written by a peer reads back as NaN / 0xFF.. instead of
+            # stale-but-plausible data; the barrier keeps peers from writing early
+            ptr = int(lib.b2_seg_ptr(new.seg, self.comm.rank))
+            torch.as_tensor(_RawDeviceBytes(ptr, new.bytes), device=f"cuda:{self.device}").fill_(0xFF)
+            torch.cuda.synchronize()
+            if self.comm.size > 1:
+                dist.barrier(group=self.comm._group)
         old, self.stage = self.stage, new
         if old is not None:
             old.destroy()
@@ -499,6 +517,27 @@ class NativeComm:
         d.at_east_wall = int(at_east_wall)
         d.at_north_wall = int(at_north_wall)
         self._check(_lib().b2_halo_exchange(self.handle, ctypes.byref(d), self._stream()), "Halo")
+
+
+def _nvtx_wrap(name: str, fn):
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        torch.cuda.nvtx.range_push(f"mpi4jax_b200.{name}")
+        try:
+            return fn(self, *args, **kwargs)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    return wrapped
+
+
+#: ``MPI4JAX_B200_NVTX=1``: one NVTX range per op (visible in Nsight Systems timelines); the
+#: methods are left untouched otherwise, so the fast path pays nothing
+NVTX_OPS = ("barrier", "allreduce", "reduce", "scan", "allgather", "alltoall", "bcast", "gather", "scatter",
+            "send", "recv", "sendrecv", "gemm_allreduce", "halo_exchange")
+if env_flag("MPI4JAX_B200_NVTX", False):
+    for _name in NVTX_OPS:
+        setattr(NativeComm, _name, _nvtx_wrap(_name, getattr(NativeComm, _name)))
 
 
 class _NullEvent:

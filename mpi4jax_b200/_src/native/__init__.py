@@ -163,6 +163,7 @@ _SIGNATURES = {
         [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_size_t, c_int, c_int,
          POINTER(B2StatusRecord), c_void_p],
     ),
+    "b2_abi_info": (c_int, [POINTER(c_int), c_int]),
     "b2_gemm_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2_halo_exchange": (c_int, [c_void_p, POINTER(B2HaloDesc), c_void_p]),
     "b2_swe_fluxes": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 7 + [c_void_p]),
@@ -182,6 +183,32 @@ _SIGNATURES = {
 }
 
 
+#: must equal B2_ABI_VERSION in csrc/b2_common.h
+ABI_VERSION = 3
+_ABI_FIELDS = ("abi_version", "sizeof_status_record", "sizeof_halo_desc", "sizeof_swe_params",
+               "sizeof_swe_state", "sizeof_error_record", "max_ranks", "p2p_nslot")
+
+
+def _abi_expected() -> dict:
+    return {"abi_version": ABI_VERSION, "sizeof_status_record": ctypes.sizeof(B2StatusRecord),
+            "sizeof_halo_desc": ctypes.sizeof(B2HaloDesc), "sizeof_swe_params": ctypes.sizeof(B2SweParams),
+            "sizeof_swe_state": ctypes.sizeof(B2SweState)}
+
+
+def _abi_native(handle) -> dict:
+    buf = (c_int * len(_ABI_FIELDS))()
+    n = handle.b2_abi_info(buf, len(_ABI_FIELDS))
+    return {k: int(buf[i]) for i, k in enumerate(_ABI_FIELDS[:n])}
+
+
+def _abi_mismatch(handle) -> str:
+    """'' if the ctypes mirrors match the structs compiled into the library, else a description
+    (counterpart of the reference's import-time MPI ABI check, xla_bridge/__init__.py:23-89)."""
+    have = _abi_native(handle)
+    bad = [f"{k}: library {have.get(k)} != python {v}" for k, v in _abi_expected().items() if have.get(k) != v]
+    return "; ".join(bad)
+
+
 def _load() -> None:
     global lib, HAS_CUDA_EXT, CUDA_EXT_ERROR
     if not _LIB_PATH.exists():
@@ -197,6 +224,13 @@ def _load() -> None:
     except (OSError, AttributeError) as exc:  # pragma: no cover - build problems
         CUDA_EXT_ERROR = f"{type(exc).__name__}: {exc}"
         return
+    problem = _abi_mismatch(handle)
+    if problem and not env_flag("MPI4JAX_B200_SKIP_ABI_CHECK", False):
+        raise RuntimeError(
+            f"mpi4jax_b200: {_LIB_PATH} does not match this Python package ({problem}). The library is "
+            "stale: rebuild it with `python -m mpi4jax_b200._src.native.build` (or set "
+            "MPI4JAX_B200_SKIP_ABI_CHECK=1 to load it anyway, at your own risk)."
+        )
     lib = handle
     HAS_CUDA_EXT = True
 
@@ -237,6 +271,8 @@ NATIVE_ABI_INFO = {
     "arch": "sm_100a",
     "sizeof_status_record": ctypes.sizeof(B2StatusRecord),
     "sizeof_halo_desc": ctypes.sizeof(B2HaloDesc),
+    "python": _abi_expected(),
+    "native": _abi_native(lib) if HAS_CUDA_EXT else None,
 }
 
 # reference: MPI4JAX_DEBUG is read at import (xla_bridge/__init__.py:128-129)

@@ -18,12 +18,13 @@ rank = comm.Get_rank()
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_in_subprocess(code, test_file, timeout=120, device="cpu"):
+def run_in_subprocess(code, test_file, timeout=120, device="cpu", extra_env=None):
     """Runs the given code in a fresh single-rank interpreter (scrubbed environment so that
     the child does not inherit RANK/WORLD_SIZE)."""
     test_file.write_text(code)
     env = dict(HOME=os.getenv("HOME", ""), PATH=os.getenv("PATH", ""), PYTHONPATH=REPO,
                LD_LIBRARY_PATH=os.getenv("LD_LIBRARY_PATH", ""), MPI4JAX_B200_DEVICE=device)
+    env.update(extra_env or {})
     return subprocess.run([sys.executable, str(test_file)], capture_output=True, timeout=timeout,
                           text=True, env=env)
 
@@ -130,3 +131,30 @@ def test_status_object():
     st._set(3, 7, 40, itemsize=4)
     assert (st.Get_source(), st.Get_tag(), st.Get_count(), st.Get_count(MPI.BYTE)) == (3, 7, 10, 40)
     assert st.source == 3 and st.tag == 7
+
+
+@pytest.mark.skipif(rank > 0, reason="Runs only on rank 0")
+def test_nvtx_and_poison_debug_modes(tmp_path, device):
+    """MPI4JAX_B200_NVTX wraps every native op in an NVTX range, MPI4JAX_B200_POISON fills fresh
+    staging memory with 0xFF; both must leave results unchanged."""
+    script = dedent("""
+        import torch
+        import mpi4jax_b200 as m
+        from mpi4jax_b200 import MPI
+        from mpi4jax_b200._src.backends import cuda as backend
+
+        assert hasattr(backend.NativeComm.allreduce, "__wrapped__")      # NVTX wrapper installed
+        assert backend._POISON
+        comm = MPI.COMM_WORLD
+        x = torch.arange(1000, dtype=torch.float32, device=comm.device)
+        y = m.allreduce(x, MPI.SUM, comm=comm)
+        z = m.allgather(x, comm=comm)
+        big = m.allreduce(torch.ones(1 << 22, device=comm.device), MPI.SUM, comm=comm)
+        m.flush()
+        assert torch.equal(y, x) and torch.equal(z[0], x) and bool((big == 1).all())
+        print("ok")
+    """)
+    proc = run_in_subprocess(script, tmp_path / "debug_modes.py", device=device.type,
+                             extra_env={"MPI4JAX_B200_NVTX": "1", "MPI4JAX_B200_POISON": "1"})
+    assert proc.returncode == 0, proc.stderr
+    assert "ok" in proc.stdout

@@ -7,6 +7,7 @@ import os
 import pytest
 import torch
 
+import mpi4jax_b200 as m
 from mpi4jax_b200 import MPI
 from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel, solve_shallow_water
 
@@ -37,6 +38,46 @@ def test_shallow_water_mass_conservation(device):
     model.multistep(50)
     m1 = model.total_mass().item()
     assert abs(m1 - m0) / abs(m0) < 1e-5
+
+
+def test_shallow_water_checkpoint_resume_is_bitwise(device):
+    """save at step 7, restore into a fresh model, continue: identical to the uninterrupted run."""
+    import os
+    import tempfile
+
+    cfg = _cfg()
+    # every rank must use the same directory: rank 0 picks it
+    root = tempfile.mkdtemp(prefix="b2ckpt_") if comm.Get_rank() == 0 else None
+    root = _share_path(root)
+    ref = ShallowWaterModel(cfg, comm=comm, device=device)
+    ref.multistep(7)
+    ref.save_checkpoint(root)
+    ref.multistep(6)
+    resumed = ShallowWaterModel(cfg, comm=comm, device=device)
+    assert resumed.load_checkpoint(root) == 7
+    resumed.multistep(6)
+    for a, b in zip(ref.state, resumed.state):
+        assert torch.equal(a, b)
+    assert resumed.steps_done == ref.steps_done == 13
+    other = ShallowWaterModel(ShallowWaterConfig(nx=cfg.nx * 2, ny=cfg.ny), comm=comm, device=device)
+    with pytest.raises(ValueError, match="does not match this model"):
+        other.load_checkpoint(root)
+    m.barrier(comm=comm)
+    m.flush()
+    if comm.Get_rank() == 0:
+        for f in os.listdir(root):
+            os.remove(os.path.join(root, f))
+        os.rmdir(root)
+
+
+def _share_path(path):
+    """rank 0's temp directory name -> all ranks (uint8 bcast through the public op)."""
+    buf = torch.zeros(256, dtype=torch.uint8)
+    if comm.Get_rank() == 0:
+        raw = path.encode()
+        buf[: len(raw)] = torch.tensor(list(raw), dtype=torch.uint8)
+    buf = m.bcast(buf.to(comm.device), 0, comm=comm).cpu()
+    return bytes(buf[buf != 0].tolist()).decode()
 
 
 @pytest.mark.gpu
