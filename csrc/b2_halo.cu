@@ -31,6 +31,7 @@
 
 #include "b2_device.cuh"
 #include "b2_halo_ll.cuh"
+#include "b2_launch.cuh"
 #include "b2_runtime.h"
 
 extern "C" void b2_set_error(const char* fmt, ...);
@@ -58,6 +59,7 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
 // receive buffer parity is count & 1.  Both ends of a channel count the same messages, so
 // exchanges with different neighbour sets can be mixed freely.
 __global__ void __launch_bounds__(HALO_THREADS) b2_k_halo(const B2DevComm c, const B2HaloDesc d) {
+  b2_pdl_enter();
   __shared__ unsigned s_rx[NSIDES], s_tx[NSIDES];
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
   const int ny = d.ny, nx = d.nx, F = d.nfields;
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(HALO_THREADS) b2_k_halo(const B2DevComm c, con
 
 __global__ void __launch_bounds__(HALO_THREADS) b2_k_halo_ll(const B2DevComm c, const B2HaloDesc d,
                                                              const int fs) {
+  b2_pdl_enter();
   __shared__ unsigned s_rx[FS_NSIDES], s_tx[FS_NSIDES];
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
   const int ny = d.ny, nx = d.nx, F = d.nfields;
@@ -392,10 +395,10 @@ extern "C" int b2_halo_exchange(B2Comm* c, const B2HaloDesc* d, cudaStream_t str
     int ctas = (d->nfields * mx + HALO_THREADS - 1) / HALO_THREADS;
     if (ctas < HALO_LL_CTAS) ctas = HALO_LL_CTAS;
     if (ctas > 96) ctas = 96;
-    b2_k_halo_ll<<<ctas, HALO_THREADS, 0, stream>>>(c->dev, *d, fs);
+    b2_launch(b2_k_halo_ll, ctas, HALO_THREADS, 0, stream, c->dev, *d, fs);
   }
   else
-    b2_k_halo<<<HALO_CTAS, HALO_THREADS, 0, stream>>>(c->dev, *d);
+    b2_launch(b2_k_halo, HALO_CTAS, HALO_THREADS, 0, stream, c->dev, *d);
   b2_count_launch(c);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {

@@ -33,11 +33,13 @@ extern "C" void b2_set_error(const char* fmt, ...);
 extern "C" void b2_count_launch(B2Comm* c);
 
 #include "b2_swe_body.cuh"
+#include "b2_launch.cuh"
 
 __global__ void __launch_bounds__(SWE_THREADS)
 swe_k1_fluxes(B2SweParams p, const float* __restrict__ h, const float* __restrict__ u,
               const float* __restrict__ v, float* __restrict__ fe, float* __restrict__ fn,
               float* __restrict__ q, float* __restrict__ ke) {
+  b2_pdl_enter();
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
@@ -51,6 +53,7 @@ swe_k2_tendencies(B2SweParams p, const float* __restrict__ h, float* __restrict_
                   float* __restrict__ du, float* __restrict__ dv, const float* __restrict__ fe,
                   const float* __restrict__ fn, const float* __restrict__ q,
                   const float* __restrict__ ke) {
+  b2_pdl_enter();
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
@@ -61,6 +64,7 @@ swe_k2_tendencies(B2SweParams p, const float* __restrict__ h, float* __restrict_
 __global__ void __launch_bounds__(SWE_THREADS)
 swe_k3_friction_flux_u(B2SweParams p, const float* __restrict__ u, float* __restrict__ fe,
                        float* __restrict__ fn, int local_halo, int has_south) {
+  b2_pdl_enter();
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
@@ -71,6 +75,7 @@ __global__ void __launch_bounds__(SWE_THREADS)
 swe_k4_friction_u_flux_v(B2SweParams p, float* __restrict__ u, const float* __restrict__ v,
                          const float* __restrict__ fe, const float* __restrict__ fn,
                          float* __restrict__ fe2, float* __restrict__ fn2) {
+  b2_pdl_enter();
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
@@ -79,18 +84,21 @@ swe_k4_friction_u_flux_v(B2SweParams p, float* __restrict__ u, const float* __re
 }
 
 __global__ void __launch_bounds__(SWE_THREADS)
-swe_k34_friction_u(B2SweParams p, float* __restrict__ u, const float* __restrict__ v,
-                   float* __restrict__ fe2, float* __restrict__ fn2, int has_south) {
+swe_k34_friction_u(B2SweParams p, const float* __restrict__ u, float* __restrict__ u_new,
+                   const float* __restrict__ v, float* __restrict__ fe2, float* __restrict__ fn2,
+                   int has_south) {
+  b2_pdl_enter();
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
   SweOut4 o;
-  swe_k34_body(p, u, v, fe2, fn2, j, i0, m, has_south != 0, o);
+  swe_k34_body(p, u, u_new, v, fe2, fn2, j, i0, m, has_south != 0, o);
 }
 
 __global__ void __launch_bounds__(SWE_THREADS)
 swe_k5_friction_v(B2SweParams p, float* __restrict__ v, const float* __restrict__ fe2,
                   const float* __restrict__ fn2) {
+  b2_pdl_enter();
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
@@ -126,7 +134,7 @@ extern "C" {
 int b2_swe_fluxes(B2Comm* c, const B2SweParams* p, const float* h, const float* u, const float* v,
                   float* fe, float* fn, float* q, float* ke, cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
-  swe_k1_fluxes<<<swe_blocks(p), SWE_THREADS, 0, s>>>(*p, h, u, v, fe, fn, q, ke);
+  b2_launch(swe_k1_fluxes, swe_blocks(p), SWE_THREADS, 0, s, *p, h, u, v, fe, fn, q, ke);
   return swe_done(c, "swe_fluxes");
 }
 
@@ -134,7 +142,7 @@ int b2_swe_tendencies(B2Comm* c, const B2SweParams* p, const float* h, float* h_
                       float* v, float* dh, float* du, float* dv, const float* fe, const float* fn,
                       const float* q, const float* ke, cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
-  swe_k2_tendencies<<<swe_blocks(p), SWE_THREADS, 0, s>>>(*p, h, h_new, u, v, dh, du, dv, fe, fn, q, ke);
+  b2_launch(swe_k2_tendencies, swe_blocks(p), SWE_THREADS, 0, s, *p, h, h_new, u, v, dh, du, dv, fe, fn, q, ke);
   return swe_done(c, "swe_tendencies");
 }
 
@@ -144,7 +152,7 @@ int b2_swe_tendencies(B2Comm* c, const B2SweParams* p, const float* h, float* h_
 int b2_swe_friction_flux_u(B2Comm* c, const B2SweParams* p, const float* u, float* fe, float* fn,
                            int local_halo, int has_south, cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
-  swe_k3_friction_flux_u<<<swe_blocks(p), SWE_THREADS, 0, s>>>(*p, u, fe, fn, local_halo, has_south);
+  b2_launch(swe_k3_friction_flux_u, swe_blocks(p), SWE_THREADS, 0, s, *p, u, fe, fn, local_halo, has_south);
   return swe_done(c, "swe_friction_flux_u");
 }
 
@@ -152,22 +160,27 @@ int b2_swe_friction_u_flux_v(B2Comm* c, const B2SweParams* p, float* u, const fl
                              const float* fe, const float* fn, float* fe2, float* fn2,
                              cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
-  swe_k4_friction_u_flux_v<<<swe_blocks(p), SWE_THREADS, 0, s>>>(*p, u, v, fe, fn, fe2, fn2);
+  b2_launch(swe_k4_friction_u_flux_v, swe_blocks(p), SWE_THREADS, 0, s, *p, u, v, fe, fn, fe2, fn2);
   return swe_done(c, "swe_friction_u_flux_v");
 }
 
 // friction-u flux + apply + friction-v flux in one kernel (no fe/fn round trip through HBM)
-int b2_swe_friction_u_fused(B2Comm* c, const B2SweParams* p, float* u, const float* v, float* fe2,
-                            float* fn2, int has_south, cudaStream_t s) {
+// (u -> u_new: out of place, u_new must not alias u)
+int b2_swe_friction_u_fused(B2Comm* c, const B2SweParams* p, const float* u, float* u_new,
+                            const float* v, float* fe2, float* fn2, int has_south, cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
-  swe_k34_friction_u<<<swe_blocks(p), SWE_THREADS, 0, s>>>(*p, u, v, fe2, fn2, has_south);
+  if (u == u_new) {
+    b2_set_error("swe_friction_u_fused: u_new must not alias u (the update reads u's neighbours)");
+    return B2_ERR_BAD_ARG;
+  }
+  b2_launch(swe_k34_friction_u, swe_blocks(p), SWE_THREADS, 0, s, *p, u, u_new, v, fe2, fn2, has_south);
   return swe_done(c, "swe_friction_u_fused");
 }
 
 int b2_swe_friction_v(B2Comm* c, const B2SweParams* p, float* v, const float* fe2, const float* fn2,
                       cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
-  swe_k5_friction_v<<<swe_blocks(p), SWE_THREADS, 0, s>>>(*p, v, fe2, fn2);
+  b2_launch(swe_k5_friction_v, swe_blocks(p), SWE_THREADS, 0, s, *p, v, fe2, fn2);
   return swe_done(c, "swe_friction_v");
 }
 
@@ -179,6 +192,7 @@ int b2_swe_friction_v(B2Comm* c, const B2SweParams* p, float* v, const float* fe
 // ends with one device copy).
 struct B2SweState {
   float *h0, *h1, *u, *v, *dh, *du, *dv, *fe, *fn, *q, *ke, *fe2, *fn2;
+  float* u1;   // ping-pong partner of u for the friction update (unused by the fused path)
 };
 
 // Layout record for the import-time ABI check (mpi4jax_b200/_src/native/__init__.py): the Python
@@ -199,6 +213,8 @@ int b2_swe_multistep(B2Comm* c, const B2SweParams* p0, const B2SweState* st, con
   B2SweParams p = *p0;
   float* h = st->h0;
   float* hn = st->h1;
+  float* u = st->u;
+  float* un = st->u1;
   B2HaloDesc d = *topo;
   d.ny = p.ny;
   d.nx = p.nx;
@@ -206,24 +222,25 @@ int b2_swe_multistep(B2Comm* c, const B2SweParams* p0, const B2SweState* st, con
   int rc = 0;
   for (int it = 0; it < nsteps && rc == 0; ++it) {
     p.first_step = (first_step && it == 0) ? 1 : 0;
-    if ((rc = b2_swe_fluxes(c, &p, h, st->u, st->v, st->fe, st->fn, st->q, st->ke, s))) break;
+    if ((rc = b2_swe_fluxes(c, &p, h, u, st->v, st->fe, st->fn, st->q, st->ke, s))) break;
     d.nfields = 4;
     d.field[0] = st->fe; d.kind[0] = 1;
     d.field[1] = st->fn; d.kind[1] = 2;
     d.field[2] = st->q;  d.kind[2] = 0;
     d.field[3] = st->ke; d.kind[3] = 0;
     if ((rc = b2_halo_exchange(c, &d, s))) break;
-    if ((rc = b2_swe_tendencies(c, &p, h, hn, st->u, st->v, st->dh, st->du, st->dv, st->fe, st->fn,
+    if ((rc = b2_swe_tendencies(c, &p, h, hn, u, st->v, st->dh, st->du, st->dv, st->fe, st->fn,
                                 st->q, st->ke, s))) break;
     d.nfields = 3;
     d.field[0] = hn;    d.kind[0] = 0;
-    d.field[1] = st->u; d.kind[1] = 1;
+    d.field[1] = u;     d.kind[1] = 1;
     d.field[2] = st->v; d.kind[2] = 2;
     if ((rc = b2_halo_exchange(c, &d, s))) break;
     if (p.viscosity > 0.f) {
       // friction-u fluxes are evaluated inline from u (incl. their halo, from u's fresh halo):
       // no K3 launch, no (fe, fn) exchange, no HBM round trip of the fluxes
-      if ((rc = b2_swe_friction_u_fused(c, &p, st->u, st->v, st->fe2, st->fn2, topo->south >= 0, s))) break;
+      if ((rc = b2_swe_friction_u_fused(c, &p, u, un, st->v, st->fe2, st->fn2, topo->south >= 0, s))) break;
+      { float* t = u; u = un; un = t; }
       d.nfields = 2;
       d.field[0] = st->fe2; d.kind[0] = 1;
       d.field[1] = st->fn2; d.kind[1] = 2;
@@ -231,6 +248,14 @@ int b2_swe_multistep(B2Comm* c, const B2SweParams* p0, const B2SweState* st, con
       if ((rc = b2_swe_friction_v(c, &p, st->v, st->fe2, st->fn2, s))) break;
     }
     float* t = h; h = hn; hn = t;
+  }
+  if (rc == 0 && u != st->u) {
+    cudaError_t e = cudaMemcpyAsync(st->u, u, (size_t)p.ny * p.pitch * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) {
+      b2_set_error("swe_multistep: copy failed: %s", cudaGetErrorString(e));
+      rc = 1000 + (int)e;
+    }
   }
   if (rc == 0 && h != st->h0) {
     cudaError_t e = cudaMemcpyAsync(st->h0, h, (size_t)p.ny * p.pitch * sizeof(float),

@@ -232,7 +232,13 @@ __device__ __forceinline__ void swe_k4_body(const B2SweParams& p, float* __restr
 // fn's south halo row = 0 on south-wall ranks (never received), u's halo supplying the west /
 // south halo fluxes elsewhere -- the same expressions on the same operands as the separate
 // K3 -> exchange -> K4 sequence, hence the same bits.
-__device__ __forceinline__ void swe_k34_body(const B2SweParams& p, float* __restrict__ u,
+//
+// u is read with its 5-point neighbourhood, so the update must NOT be in place (a neighbour's
+// thread may already have stored its new value): u -> u_new ping-pong, like h in K2.  The halo
+// rows / columns / pad lanes of u_new are copies of u's, i.e. what the in-place update of the
+// reference leaves there (u's halo as exchanged before the friction step).
+__device__ __forceinline__ void swe_k34_body(const B2SweParams& p, const float* __restrict__ u,
+                                             float* __restrict__ u_new,
                                              const float* __restrict__ v, float* __restrict__ fe2,
                                              float* __restrict__ fn2, int j, int i0, const bool m[4],
                                              bool has_south, SweOut4& o) {
@@ -263,9 +269,11 @@ __device__ __forceinline__ void swe_k34_body(const B2SweParams& p, float* __rest
     if (p.north_wall && j == p.ny - 2) FN2[k] = 0.f;
     o.a[0][k] = FE2[k]; o.a[1][k] = FN2[k];
   }
-  st4(u, off, make_float4(Un[0], Un[1], Un[2], Un[3]));
+  st4(u_new, off, make_float4(Un[0], Un[1], Un[2], Un[3]));
   st4(fe2, off, make_float4(FE2[0], FE2[1], FE2[2], FE2[3]));
   st4(fn2, off, make_float4(FN2[0], FN2[1], FN2[2], FN2[3]));
+  if (j == 1) st4(u_new, (size_t)i0, us4);                                   // south halo row
+  if (j == p.ny - 2) st4(u_new, (size_t)(p.ny - 1) * P + i0, un4);         // north halo row
 }
 
 __device__ __forceinline__ void swe_k5_body(const B2SweParams& p, float* __restrict__ v,

@@ -87,7 +87,7 @@ class B2SweParams(Structure):
 
 class B2SweState(Structure):
     _fields_ = [(name, c_void_p) for name in
-                ("h0", "h1", "u", "v", "dh", "du", "dv", "fe", "fn", "q", "ke", "fe2", "fn2")]
+                ("h0", "h1", "u", "v", "dh", "du", "dv", "fe", "fn", "q", "ke", "fe2", "fn2", "u1")]
 
 
 class B2StatusRecord(Structure):
@@ -164,13 +164,15 @@ _SIGNATURES = {
          POINTER(B2StatusRecord), c_void_p],
     ),
     "b2_abi_info": (c_int, [POINTER(c_int), c_int]),
+    "b2_pdl_enabled": (c_int, []),
+    "b2_set_pdl": (None, [c_int]),
     "b2_gemm_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2_halo_exchange": (c_int, [c_void_p, POINTER(B2HaloDesc), c_void_p]),
     "b2_swe_fluxes": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 7 + [c_void_p]),
     "b2_swe_tendencies": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 11 + [c_void_p]),
     "b2_swe_friction_flux_u": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
     "b2_swe_friction_u_flux_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 6 + [c_void_p]),
-    "b2_swe_friction_u_fused": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 4 + [c_int, c_void_p]),
+    "b2_swe_friction_u_fused": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 5 + [c_int, c_void_p]),
     "b2_swe_friction_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_void_p]),
     "b2_swe_multistep_fused": (
         c_int,
@@ -184,7 +186,7 @@ _SIGNATURES = {
 
 
 #: must equal B2_ABI_VERSION in csrc/b2_common.h
-ABI_VERSION = 3
+ABI_VERSION = 4
 _ABI_FIELDS = ("abi_version", "sizeof_status_record", "sizeof_halo_desc", "sizeof_swe_params",
                "sizeof_swe_state", "sizeof_error_record", "max_ranks", "p2p_nslot")
 
@@ -225,10 +227,13 @@ def _load() -> None:
         CUDA_EXT_ERROR = f"{type(exc).__name__}: {exc}"
         return
     problem = _abi_mismatch(handle)
+    if problem and any("native.build" in a or a.endswith("build.py") for a in getattr(sys, "orig_argv", [])):
+        CUDA_EXT_ERROR = f"stale library ({problem}); rebuilding"     # `python -m ...native.build` itself
+        return
     if problem and not env_flag("MPI4JAX_B200_SKIP_ABI_CHECK", False):
         raise RuntimeError(
             f"mpi4jax_b200: {_LIB_PATH} does not match this Python package ({problem}). The library is "
-            "stale: rebuild it with `python -m mpi4jax_b200._src.native.build` (or set "
+            "stale: rebuild it with `python setup.py build_ext --inplace` (or set "
             "MPI4JAX_B200_SKIP_ABI_CHECK=1 to load it anyway, at your own risk)."
         )
     lib = handle

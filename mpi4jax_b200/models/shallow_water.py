@@ -151,6 +151,7 @@ class ShallowWaterModel:
         self.h, self.u, self.v = z(), z(), z()
         self.dh, self.du, self.dv = z(), z(), z()
         self._h1 = z()
+        self._u1 = z()      # ping-pong partner of u for the friction update
         self.fe, self.fn, self.q, self.ke, self.fe2, self.fn2 = z(), z(), z(), z(), z(), z()
         y_global = (np.arange(-1, self.ny_global - 1) * self.cfg.dy)
         cor = self.cfg.coriolis_f + y_global[self.local_slice[0]] * self.cfg.coriolis_beta
@@ -169,6 +170,7 @@ class ShallowWaterModel:
             p.coriolis = self.coriolis.data_ptr()
             st = self._state = native.B2SweState()
             st.h0, st.h1 = self.h.data_ptr(), self._h1.data_ptr()
+            st.u1 = self._u1.data_ptr()
             for name in ("u", "v", "dh", "du", "dv", "fe", "fn", "q", "ke", "fe2", "fn2"):
                 setattr(st, name, getattr(self, name).data_ptr())
             t = self._topo = native.B2HaloDesc()
