@@ -32,17 +32,20 @@ from .comm import ANY_SOURCE, ANY_TAG, SUM, Comm, as_op
 from .native import codes
 from .utils import get_default_comm
 
-_COMMS: dict = {}
-
-
 def _register(comm: Optional[Comm]) -> int:
+    """Communicator -> integer graph attribute.  No registration side effect here: Dynamo defers
+    Python side effects of a traced frame until after the graph has run, so the lookup table must
+    exist beforehand -- it is the registry every ``Comm`` enters at construction."""
     comm = comm or get_default_comm()
-    _COMMS[comm._id] = comm
     return comm._id
 
 
 def _c(comm_id: int) -> Comm:
-    return _COMMS[comm_id]
+    for comm in list(_comm_mod._comm_registry):
+        if comm._id == comm_id:
+            return comm
+    raise RuntimeError(f"mpi4jax_b200: communicator #{comm_id} no longer exists (it was freed or garbage "
+                       "collected after the function using it was compiled)")
 
 
 # ---------------------------------------------------------------- op definitions

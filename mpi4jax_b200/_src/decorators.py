@@ -11,7 +11,7 @@ peer-mapped HBM), so the flags that remain are:
 ``MPI4JAX_B200_HEAP``              ``vmm`` (default, enables NVLS) or ``ipc`` (cudaIpc fallback)
 ``MPI4JAX_B200_NVLS``              falsy -> do not create multicast objects
 ``MPI4JAX_B200_TIMEOUT``           device watchdog in seconds (default 60)
-``MPI4JAX_B200_P2P_SLOT_BYTES``    bytes per p2p ring slot (default 16 MiB, ring capped at 512 MiB)
+``MPI4JAX_B200_P2P_SLOT_BYTES``    bytes per p2p ring slot (default 16 MiB, ring capped at 256 MiB)
 ``MPI4JAX_B200_ABORT_ON_ERROR``    falsy -> raise ``MPIError`` instead of aborting the process
 ``MPI4JAX_USE_CUDA_MPI``           accepted for compatibility; only emits a note when falsy
 =================================  ==========================================================
