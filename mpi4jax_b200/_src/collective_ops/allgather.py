@@ -31,6 +31,11 @@ class _Allgather(torch.autograd.Function):
         total = _dispatch.allreduce(ctx.comm, g.contiguous(), SUM.code)
         return total[ctx.comm.rank], None
 
+    @staticmethod
+    def vmap(info, in_dims, x, comm):
+        # (B, *S) on every rank -> one message -> (P, B, *S): the batch axis ends up at position 1
+        return _Allgather.apply(x.movedim(in_dims[0], 0).contiguous(), comm), 1
+
 
 @enforce_types(comm=(type(None), Comm))
 def allgather(x, *, comm=None, token=NOTSET):

@@ -29,6 +29,11 @@ class _Alltoall(torch.autograd.Function):
     def backward(ctx, g):
         return _Alltoall.apply(g.contiguous(), ctx.comm), None
 
+    @staticmethod
+    def vmap(info, in_dims, x, comm):
+        # keep the (nproc, ...) axis in front: (B, P, *S) -> (P, B, *S), exchanged as one message
+        return _Alltoall.apply(x.movedim(in_dims[0], 1).contiguous(), comm), 1
+
 
 @enforce_types(comm=(type(None), Comm))
 def alltoall(x, *, comm=None, token=NOTSET):

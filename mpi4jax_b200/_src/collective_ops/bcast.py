@@ -36,6 +36,10 @@ class _Bcast(torch.autograd.Function):
             return total, None, None
         return torch.zeros_like(g), None, None
 
+    @staticmethod
+    def vmap(info, in_dims, x, root, comm):
+        return _Bcast.apply(x, root, comm), in_dims[0]
+
 
 @enforce_types(root=(np.integer,), comm=(type(None), Comm))
 def bcast(x, root, *, comm=None, token=NOTSET):

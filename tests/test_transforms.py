@@ -54,3 +54,35 @@ def test_ops_in_python_loop_jit(device):
     x = torch.zeros(8, device=device)
     for _ in range(3):
         assert torch.equal(fj(x), torch.full((8,), 5.0, device=device))
+
+
+def test_vmap_allgather_alltoall_bcast(device):
+    """vmap rules beyond the reference's (allreduce, barrier, sendrecv): the batch travels as one
+    message; results equal a Python loop over the batch."""
+    from torch.func import vmap
+
+    comm = MPI.COMM_WORLD
+    rank, size = comm.Get_rank(), comm.Get_size()
+    xb = torch.arange(3 * 4, dtype=torch.float32, device=device).reshape(3, 4) + 100 * rank
+
+    got = vmap(lambda x: m.allgather(x, comm=comm))(xb)
+    want = torch.stack([m.allgather(x, comm=comm) for x in xb])
+    assert got.shape == (3, size, 4) and torch.equal(got, want)
+
+    got = vmap(lambda x: m.allgather(x, comm=comm), in_dims=1, out_dims=1)(xb)       # batch over columns
+    want = torch.stack([m.allgather(xb[:, j], comm=comm) for j in range(4)], dim=1)
+    assert got.shape == (size, 4, 3) and torch.equal(got, want)
+
+    ab = torch.arange(5 * size * 2, dtype=torch.float32, device=device).reshape(5, size, 2) + 1000 * rank
+    got = vmap(lambda x: m.alltoall(x, comm=comm))(ab)
+    want = torch.stack([m.alltoall(x, comm=comm) for x in ab])
+    assert got.shape == (5, size, 2) and torch.equal(got, want)
+
+    got = vmap(lambda x: m.bcast(x, 0, comm=comm))(xb)
+    want = torch.stack([m.bcast(x, 0, comm=comm) for x in xb])
+    assert torch.equal(got, want)
+    if rank != 0:
+        assert torch.equal(got, torch.arange(12, dtype=torch.float32, device=device).reshape(3, 4))
+    # and through grad-of-vmap: d/dx sum(allgather(x)) = nproc
+    g = torch.func.grad(lambda x: vmap(lambda r: m.allgather(r, comm=comm))(x).sum())(xb)
+    assert torch.equal(g, torch.full_like(xb, float(size)))
