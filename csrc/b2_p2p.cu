@@ -25,8 +25,13 @@
 // CUDA-graph capturable and never synchronise the host.  MPI semantics kept:
 // tags (validated against the pair FIFO), ANY_TAG, ANY_SOURCE (device-side
 // election over the P inbox heads), Status(source, tag, count), zero-byte
-// messages, self-sends.  Restriction (documented in docs/sharp-bits.md):
-// messages of one (source, dest) pair are matched in the order they were sent.
+// messages, self-sends.  Tag matching: a receive with a tag takes the EARLIEST
+// pending message of that source carrying the tag (MPI's non-overtaking rule);
+// a message that fits one slot may thereby be received ahead of earlier
+// messages with other tags (per-source bitmap of slots consumed out of order).
+// Messages larger than a slot stream through the ring and can only be matched
+// at the head of the pair's queue -- like MPI's rendezvous protocol, where the
+// blocked sender would not have reached the later send either.
 #include <cstdio>
 #include <cstring>
 
@@ -46,6 +51,7 @@ extern "C" void b2_debug_end(B2DebugScope* s, int code);
 #define CTL_ELECT 2        // any-source election word: (gen << 8) | source
 #define CTL_GEN 3          // election generation
 #define CTL_SLOT_DONE 8    // [NSLOT] per-slot receiver-lane completion counters
+#define CTL_OOO 16         // [B2_MAX_RANKS] per-source bitmap: bit i = fragment head+i consumed out of order
 
 struct B2P2PArgs {
   const void* sendbuf;
@@ -110,6 +116,46 @@ __device__ void p2p_send_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
                  (unsigned)a.send_lanes);
 }
 
+// Sequence number of the first fragment of the message a receive (src, tag) consumes.  Executed by
+// thread 0 of EVERY receiving lane on the lane-0 headers (every message has one): the pair state
+// (head, bitmap) only changes when a receive kernel finishes, headers arrive in sequence order and
+// the scan stops at the first fragment that has not arrived, so all lanes pick the same message.
+__device__ unsigned p2p_match(const B2DevComm& c, const B2P2PArgs& a, int src) {
+  const unsigned head = b2_ld_volatile(c.p2p_recv_seq + src);
+  if (a.recv_tag < 0) return head;                       // ANY_TAG: always the head of the queue
+  const unsigned ooo = b2_ld_volatile(c.p2p_ctl + CTL_OOO + src);
+  const size_t slot_bytes = c.lay.p2p_slot_bytes;
+  const unsigned* hdr_base = (const unsigned*)(c.heap[c.rank] + c.lay.p2p_hdr_off);
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
+  while (true) {
+    unsigned i = 0;
+    while (i < B2_P2P_NSLOT) {
+      if ((ooo >> i) & 1u) { ++i; continue; }            // already consumed out of order
+      const unsigned sq = head + i;
+      const unsigned* h = hdr_base + (((size_t)src * B2_P2P_NSLOT + sq % B2_P2P_NSLOT) * B2_P2P_MAX_LANES) * 4;
+      if (b2_ld_acquire_sys(h) != sq + 1u) break;        // not here yet (nor anything behind it)
+      const int tag = (int)b2_ld_volatile(h + 1);
+      const unsigned long long nb =
+          (unsigned long long)b2_ld_volatile(h + 2) | ((unsigned long long)b2_ld_volatile(h + 3) << 32);
+      const unsigned long long nf = nb == 0 ? 1 : (nb + slot_bytes - 1) / slot_bytes;
+      if (tag == a.recv_tag) {
+        if (i != 0 && nf != 1)       // a streamed message cannot overtake (see the file header)
+          b2_fatal(c, B2_ERR_TAG_MISMATCH, a.opcode, src, (unsigned)a.recv_tag, (unsigned)tag, 5);
+        return sq;
+      }
+      if (nf >= B2_P2P_NSLOT - i) break;                  // its fragments fill the rest of the window
+      i += (unsigned)nf;
+    }
+    if ((++spins & 0x3ffu) == 0) {
+      unsigned long long now = b2_gtime();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > c.timeout_ns)
+        b2_fatal(c, B2_ERR_TIMEOUT, a.opcode, src, (unsigned)a.recv_tag, head, 6);
+    }
+  }
+}
+
 __device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) {
   __shared__ int s_src;
   __shared__ unsigned s_seq0;
@@ -158,7 +204,7 @@ __device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
       }
     }
     s_src = src;
-    s_seq0 = b2_ld_volatile(c.p2p_recv_seq + src);
+    s_seq0 = p2p_match(c, a, src);
   }
   __syncthreads();
   const int src = s_src;
@@ -217,7 +263,18 @@ __device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
     const unsigned old = atomicAdd(c.p2p_ctl + CTL_RECV_FIN, 1u);
     if (old == (unsigned)a.recv_lanes - 1u) {
       b2_st_volatile(c.p2p_ctl + CTL_RECV_FIN, 0u);
-      b2_st_volatile(c.p2p_recv_seq + src, seq0 + (unsigned)nfrag);
+      const unsigned head = b2_ld_volatile(c.p2p_recv_seq + src);
+      unsigned ooo = b2_ld_volatile(c.p2p_ctl + CTL_OOO + src);
+      if (seq0 == head) {
+        // in order: advance past this message and past anything behind it that was already taken
+        unsigned nh = head + (unsigned)nfrag;
+        ooo = nfrag >= B2_P2P_NSLOT ? 0u : (ooo >> (unsigned)nfrag);
+        while (ooo & 1u) { ooo >>= 1; ++nh; }
+        b2_st_volatile(c.p2p_recv_seq + src, nh);
+      } else {
+        ooo |= 1u << (seq0 - head);                     // single-slot message taken ahead of the head
+      }
+      b2_st_volatile(c.p2p_ctl + CTL_OOO + src, ooo);
       b2_st_volatile(c.p2p_ctl + CTL_GEN, b2_ld_volatile(c.p2p_ctl + CTL_GEN) + 1u);
       __threadfence();
     }

@@ -142,3 +142,67 @@ def test_send_recv_grad(device):
     elif rank == 1:
         y = m.recv(torch.empty(3, device=device, requires_grad=True), source=0)
         (y * 3).sum().backward()
+
+
+@pytest.mark.parametrize("nelem", [5, 40_000, 300_000], ids=["tiny", "1lane", "multilane"])
+@pytest.mark.parametrize("order", [(2, 0, 1), (1, 2, 0), (2, 1, 0), (0, 2, 1)])
+def test_tags_matched_out_of_order_self(device, nelem, order):
+    """MPI tag matching: a tagged receive takes the earliest pending message with that tag, even
+    if messages with other tags were sent before it (the reference gets this from MPI itself)."""
+    msgs = [torch.arange(nelem, dtype=torch.float32, device=device) + 1000 * k for k in range(3)]
+    for k, x in enumerate(msgs):
+        m.send(x, rank, tag=10 + k)
+    for k in order:
+        status = MPI.Status()
+        got = m.recv(torch.empty_like(msgs[k]), source=rank, tag=10 + k, status=status)
+        assert torch.equal(got, msgs[k])
+        assert status.Get_tag() == 10 + k and status.Get_source() == rank
+    # the queue is clean again: plain FIFO traffic with ANY_TAG still works afterwards
+    for k, x in enumerate(msgs):
+        m.send(x, rank, tag=20 + k)
+    for k, x in enumerate(msgs):
+        assert torch.equal(m.recv(torch.empty_like(x), source=rank), x)
+
+
+def test_same_tag_is_not_overtaken_self(device):
+    """Non-overtaking: two pending messages with the same tag are received in send order, also
+    when they sit behind a message with another tag."""
+    a, b, c_ = (torch.full((9,), float(v), device=device) for v in (1, 2, 3))
+    m.send(a, rank, tag=1)
+    m.send(b, rank, tag=7)
+    m.send(c_, rank, tag=7)
+    assert torch.equal(m.recv(torch.empty_like(a), source=rank, tag=7), b)
+    assert torch.equal(m.recv(torch.empty_like(a), source=rank, tag=7), c_)
+    assert torch.equal(m.recv(torch.empty_like(a), source=rank, tag=1), a)
+
+
+@need2
+def test_tags_matched_out_of_order_between_ranks(device):
+    """rank r sends tags 0..3 to its right neighbour, which receives them in a different order,
+    repeatedly (ring slots wrap around several times) and inside a jit-captured function."""
+    dest, src = (rank + 1) % size, (rank - 1) % size
+    perm = (3, 0, 2, 1)
+
+    def round_trip(base):
+        outs = []
+        if rank % 2 == 0:
+            for k in range(4):
+                m.send(base + k, dest, tag=k)
+        for k in perm:
+            outs.append(m.recv(base, source=src, tag=k))
+        if rank % 2 == 1:
+            for k in range(4):
+                m.send(base + k, dest, tag=k)
+        return torch.stack(outs)
+
+    if size % 2:
+        pytest.skip("needs an even number of ranks")
+    base = torch.arange(70_000, dtype=torch.float32, device=device) + 100 * rank
+    want_base = torch.arange(70_000, dtype=torch.float32, device=device) + 100 * src
+    want = torch.stack([want_base + k for k in perm])
+    for _ in range(5):
+        assert torch.equal(round_trip(base), want)
+    f = m.jit(round_trip)
+    for _ in range(4):
+        assert torch.equal(f(base), want)
+    m.flush()
