@@ -24,6 +24,49 @@ def _log(comm: Comm, opname: str, details: str):
     return None
 
 
+_is_wrapped = torch._C._functorch.is_functorch_wrapped_tensor
+
+
+def _plain(x: torch.Tensor) -> torch.Tensor:
+    """Backends need real storage (the CUDA path takes raw pointers).  A torch.func wrapper here
+    means an op's autograd rule called the backend directly instead of going through a
+    ``torch.autograd.Function`` (which peels the transform levels) -- caught on every backend so the
+    CPU suite sees it too."""
+    if _is_wrapped(x):
+        raise RuntimeError("mpi4jax_b200 internal error: a torch.func-wrapped tensor reached the "
+                           "communication backend; use run_opaque() / a differentiable op in the rule")
+    return x
+
+
+class _Opaque(torch.autograd.Function):
+    """Runs ``fn(x)`` with the torch.func transform levels peeled off ``x``."""
+
+    @staticmethod
+    def forward(fn, x):
+        out = fn(x)
+        return x.new_empty(0) if out is None else out
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("higher-order derivatives through this communication rule are not defined")
+
+    @staticmethod
+    def vmap(info, in_dims, fn, x):
+        return _Opaque.apply(fn, x), in_dims[1]     # rank-wise elementwise rules: the batch rides along
+
+
+def run_opaque(fn, x: torch.Tensor):
+    """Call a non-differentiable backend function from inside an autograd rule (where ``x`` may be a
+    GradTrackingTensor / BatchedTensor of an active torch.func transform)."""
+    if _is_wrapped(x) or torch._C._functorch.peek_interpreter_stack() is not None:
+        return _Opaque.apply(fn, x)
+    return fn(x)
+
+
 def _is_cuda(*tensors) -> bool:
     return any(t is not None and t.is_cuda for t in tensors)
 
@@ -39,6 +82,7 @@ def barrier(comm: Comm) -> None:
 
 
 def allreduce(comm: Comm, x: torch.Tensor, op_code: int, algo: int = codes.ALGO_AUTO) -> torch.Tensor:
+    _plain(x)
     if x.is_cuda:
         return comm._native_comm().allreduce(x, op_code, algo)
     done = _log(comm, "Allreduce", f"with {x.numel()} items")
@@ -49,6 +93,7 @@ def allreduce(comm: Comm, x: torch.Tensor, op_code: int, algo: int = codes.ALGO_
 
 
 def reduce(comm: Comm, x: torch.Tensor, op_code: int, root: int) -> Optional[torch.Tensor]:
+    _plain(x)
     if x.is_cuda:
         return comm._native_comm().reduce(x, op_code, root)
     done = _log(comm, "Reduce", f"with {x.numel()} items to root {root}")
@@ -59,6 +104,7 @@ def reduce(comm: Comm, x: torch.Tensor, op_code: int, root: int) -> Optional[tor
 
 
 def scan(comm: Comm, x: torch.Tensor, op_code: int) -> torch.Tensor:
+    _plain(x)
     if x.is_cuda:
         return comm._native_comm().scan(x, op_code)
     done = _log(comm, "Scan", f"with {x.numel()} items")
@@ -69,6 +115,7 @@ def scan(comm: Comm, x: torch.Tensor, op_code: int) -> torch.Tensor:
 
 
 def allgather(comm: Comm, x: torch.Tensor) -> torch.Tensor:
+    _plain(x)
     if x.is_cuda:
         return comm._native_comm().allgather(x)
     done = _log(comm, "Allgather", f"sending {x.numel() * x.element_size()} bytes")
@@ -79,6 +126,7 @@ def allgather(comm: Comm, x: torch.Tensor) -> torch.Tensor:
 
 
 def alltoall(comm: Comm, x: torch.Tensor) -> torch.Tensor:
+    _plain(x)
     if x.is_cuda:
         return comm._native_comm().alltoall(x)
     done = _log(comm, "Alltoall", f"with {x.numel()} items")
@@ -89,6 +137,7 @@ def alltoall(comm: Comm, x: torch.Tensor) -> torch.Tensor:
 
 
 def bcast(comm: Comm, x: torch.Tensor, root: int) -> torch.Tensor:
+    _plain(x)
     if x.is_cuda:
         return comm._native_comm().bcast(x, root)
     done = _log(comm, "Bcast", f"{x.numel()} items from root {root}")
@@ -99,6 +148,7 @@ def bcast(comm: Comm, x: torch.Tensor, root: int) -> torch.Tensor:
 
 
 def gather(comm: Comm, x: torch.Tensor, root: int) -> Optional[torch.Tensor]:
+    _plain(x)
     if x.is_cuda:
         return comm._native_comm().gather(x, root)
     done = _log(comm, "Gather", f"{x.numel()} items to root {root}")
@@ -109,6 +159,7 @@ def gather(comm: Comm, x: torch.Tensor, root: int) -> Optional[torch.Tensor]:
 
 
 def scatter(comm: Comm, x: torch.Tensor, root: int, out_shape, dtype) -> torch.Tensor:
+    _plain(x)
     if x.is_cuda:
         return comm._native_comm().scatter(x, root, out_shape, dtype)
     done = _log(comm, "Scatter", f"from root {root}")
@@ -119,6 +170,7 @@ def scatter(comm: Comm, x: torch.Tensor, root: int, out_shape, dtype) -> torch.T
 
 
 def send(comm: Comm, x: torch.Tensor, dest: int, tag: int) -> None:
+    _plain(x)
     if x.is_cuda:
         comm._native_comm().send(x, dest, tag)
         return

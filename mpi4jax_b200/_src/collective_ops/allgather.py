@@ -28,7 +28,9 @@ class _Allgather(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        total = _dispatch.allreduce(ctx.comm, g.contiguous(), SUM.code)
+        from .allreduce import allreduce      # the differentiable op: works under torch.func too
+
+        total = allreduce(g.contiguous(), SUM, comm=ctx.comm)
         return total[ctx.comm.rank], None
 
     @staticmethod

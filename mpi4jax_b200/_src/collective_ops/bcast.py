@@ -31,8 +31,9 @@ class _Bcast(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        total = _dispatch.reduce(ctx.comm, g.contiguous(), SUM.code, ctx.root)
-        if ctx.comm.rank == ctx.root:
+        comm, root = ctx.comm, ctx.root
+        total = _dispatch.run_opaque(lambda t: _dispatch.reduce(comm, t, SUM.code, root), g.contiguous())
+        if comm.rank == root:
             return total, None, None
         return torch.zeros_like(g), None, None
 

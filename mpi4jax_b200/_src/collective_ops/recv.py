@@ -35,7 +35,8 @@ class _Recv(torch.autograd.Function):
     def backward(ctx, g):
         if ctx.source == ANY_SOURCE:
             raise RuntimeError("recv with source=ANY_SOURCE cannot be differentiated")
-        _dispatch.send(ctx.comm, g.contiguous(), ctx.source, max(ctx.tag, 0))
+        comm, source, tag = ctx.comm, ctx.source, max(ctx.tag, 0)
+        _dispatch.run_opaque(lambda t: _dispatch.send(comm, t, source, tag), g.contiguous())
         return None, None, None, None, None
 
 

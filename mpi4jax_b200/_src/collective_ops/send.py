@@ -31,11 +31,13 @@ class _SendWithGrad(torch.autograd.Function):
     @staticmethod
     def setup_context(ctx, inputs, output):
         x, ctx.dest, ctx.tag, ctx.comm = inputs
-        ctx.template = torch.empty_like(x)
+        ctx.meta = (tuple(x.shape), x.dtype, x.device)      # not a tensor: x may be a torch.func wrapper
 
     @staticmethod
     def backward(ctx, _g):
-        return _dispatch.recv(ctx.comm, ctx.template, ctx.dest, ctx.tag, None), None, None, None
+        shape, dtype, device = ctx.meta
+        template = torch.empty(shape, dtype=dtype, device=device)
+        return _dispatch.recv(ctx.comm, template, ctx.dest, ctx.tag, None), None, None, None
 
 
 @enforce_types(dest=(np.integer,), tag=(np.integer,), comm=(type(None), Comm))

@@ -144,6 +144,18 @@ def test_send_recv_grad(device):
         (y * 3).sum().backward()
 
 
+@need2
+def test_send_recv_func_grad(device):
+    """The same loop under torch.func.grad: the rules must peel the transform levels before they
+    hand cotangents to the backend (raw pointers on the GPU path)."""
+    if rank == 0:
+        g = torch.func.grad(lambda x: m.send_with_grad(x * 2, 1))(torch.ones(3, device=device))
+        assert torch.equal(g, torch.ones(3, device=device) * 2 * 3)
+    elif rank == 1:
+        g = torch.func.grad(lambda t: (m.recv(t, source=0) * 3).sum())(torch.empty(3, device=device))
+        assert g is not None
+
+
 @pytest.mark.parametrize("nelem", [5, 40_000, 300_000], ids=["tiny", "1lane", "multilane"])
 @pytest.mark.parametrize("order", [(2, 0, 1), (1, 2, 0), (2, 1, 0), (0, 2, 1)])
 def test_tags_matched_out_of_order_self(device, nelem, order):

@@ -86,3 +86,19 @@ def test_vmap_allgather_alltoall_bcast(device):
     # and through grad-of-vmap: d/dx sum(allgather(x)) = nproc
     g = torch.func.grad(lambda x: vmap(lambda r: m.allgather(r, comm=comm))(x).sum())(xb)
     assert torch.equal(g, torch.full_like(xb, float(size)))
+
+
+def test_func_grad_through_bcast(device):
+    """bcast VJP (= reduce of the cotangents to the root) under torch.func.grad and vmap-of-grad."""
+    comm = MPI.COMM_WORLD
+    rank, size = comm.Get_rank(), comm.Get_size()
+    x = torch.arange(4, dtype=torch.float32, device=device) + 1
+
+    def loss(t):
+        return (m.bcast(t * 2, 0, comm=comm) ** 2).sum()
+
+    g = torch.func.grad(loss)(x)
+    want = 8 * x * size if rank == 0 else torch.zeros_like(x)
+    assert torch.allclose(g, want)
+    gb = torch.func.vmap(torch.func.grad(loss))(torch.stack([x, 2 * x]))
+    assert torch.allclose(gb, torch.stack([want, 2 * want]))
