@@ -73,3 +73,20 @@ def test_compiled_program_order_is_kept(device):
         out = f(arr)
         assert torch.equal(out, torch.ones(10, device=device) * ((rank - 1) % size))
     m.flush()
+
+
+def test_torch_export_keeps_all_ops(device):
+    """torch.export produces a graph that contains every op, including the result-less barrier."""
+
+    class Mod(torch.nn.Module):
+        def forward(self, x):
+            y = mc.allreduce(x * 2, MPI.SUM, comm=comm)
+            mc.barrier(comm=comm)
+            return mc.allgather(y, comm=comm)
+
+    ep = torch.export.export(Mod(), (torch.ones(3, device=device),))
+    targets = [str(n.target) for n in ep.graph.nodes if n.op == "call_function"]
+    for name in ("allreduce", "barrier", "allgather"):
+        assert any(f"mpi4jax_b200.{name}" in t for t in targets), targets
+    out = ep.module()(torch.ones(3, device=device))
+    assert torch.equal(out, torch.full((size, 3), 2.0 * size, device=device))
