@@ -293,10 +293,20 @@ class Comm:
         """The native (GPU) side of the communicator; created collectively on first use."""
         self._check_alive()
         if self._native is None:
-            from .backends.cuda import NativeComm
+            from .backends import transport
 
-            self._native = NativeComm(self)
+            self._native = transport.create(self)      # NVLink kernels, or host staging off-node
         return self._native
+
+    @property
+    def transport(self) -> str:
+        """``"native"`` (NVLink kernels), ``"host"`` (host-staged fallback) or ``"cpu"``; decided
+        collectively on first use."""
+        if self.device.type != "cuda":
+            return "cpu"
+        from .backends.host_staged import HostStagedComm
+
+        return "host" if isinstance(self._native_comm(), HostStagedComm) else "native"
 
     def _cpu(self):
         if self._cpu_state is None:

@@ -106,9 +106,10 @@ def setup_cuda_mpi() -> None:
     """One-time handling of the reference's ``MPI4JAX_USE_CUDA_MPI`` switch.
 
     The reference copies every GPU buffer through pageable host memory unless this
-    is truthy (decorators.py:38-64).  Here device buffers always travel GPU->GPU
-    over NVLink, so the variable has no effect; a falsy value earns a warning so
-    that ported job scripts do not silently assume host staging.
+    is truthy (decorators.py:38-64).  Here device buffers travel GPU->GPU over NVLink by
+    default; a falsy value selects the host-staged transport (``backends/host_staged.py``,
+    see ``backends/transport.py``) and earns a warning, because on one node that is never
+    what you want.
     """
     global _cuda_mpi_note_done
     if _cuda_mpi_note_done:
@@ -117,6 +118,7 @@ def setup_cuda_mpi() -> None:
     raw = os.environ.get("MPI4JAX_USE_CUDA_MPI")
     if raw is not None and _is_falsy(raw):
         warnings.warn(
-            "MPI4JAX_USE_CUDA_MPI=0 requests host-staged transfers, which mpi4jax_b200 "
-            "does not implement: GPU buffers always move directly over NVLink."
+            "MPI4JAX_USE_CUDA_MPI=0 requests host-staged transfers: CUDA tensors will be copied "
+            "through host memory instead of moving directly over NVLink (unset it, or set "
+            "MPI4JAX_B200_TRANSPORT=native, for the fast path)."
         )

@@ -97,7 +97,7 @@ def jit(fn: Callable = None, *, donate_outputs: bool = False, static_inputs: boo
             not leaves and torch.cuda.is_available() and _default_device_is_cuda()
         )
         needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in leaves)
-        if (not on_gpu) or needs_grad or torch.cuda.is_current_stream_capturing():
+        if (not on_gpu) or needs_grad or torch.cuda.is_current_stream_capturing() or _host_staged():
             return fn(*args, **kwargs)
         key = (_spec_key(spec), tuple((t.shape, t.dtype, t.device) for t in leaves))
         n = calls.get(key, 0)
@@ -119,6 +119,13 @@ def jit(fn: Callable = None, *, donate_outputs: bool = False, static_inputs: boo
     wrapped.__wrapped_fn__ = fn
     wrapped._cache = cache
     return wrapped
+
+
+def _host_staged() -> bool:
+    """Host-staged communicators block the host inside every op: nothing to capture."""
+    from .backends import host_staged
+
+    return host_staged.ACTIVE
 
 
 def _default_device_is_cuda() -> bool:

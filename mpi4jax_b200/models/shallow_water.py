@@ -81,7 +81,9 @@ class ShallowWaterModel:
         self.comm = comm = comm or get_default_comm()
         self.device = torch.device(device) if device is not None else comm.device
         if backend == "auto":
-            backend = "native" if self.device.type == "cuda" else "ops"
+            # the fused kernels need the NVLink transport; a host-staged communicator (ranks on
+            # several nodes) runs the same discrete system through the 12 primitives
+            backend = "native" if (self.device.type == "cuda" and comm.transport == "native") else "ops"
         if backend == "native" and self.device.type != "cuda":
             raise ValueError("backend='native' needs a CUDA device")
         self.backend = backend
