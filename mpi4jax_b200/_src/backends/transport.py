@@ -27,6 +27,15 @@ def requested() -> str:
     return want
 
 
+def _node_name() -> str:
+    """Hostname = NVLink domain.  ``MPI4JAX_B200_FAKE_NODE_SIZE=k`` (testing only) pretends that every
+    k consecutive world ranks form their own node, so the multi-node paths can run on one machine."""
+    fake = os.environ.get("MPI4JAX_B200_FAKE_NODE_SIZE")
+    if fake:
+        return f"fake-node-{int(os.environ.get('RANK', '0')) // max(1, int(fake))}"
+    return socket.gethostname()
+
+
 def decide(wants, hosts):
     """Pure decision function (unit-tested): every rank's request + hostname -> (transport, reason)."""
     if "host" in wants:
@@ -48,7 +57,7 @@ def create(comm):
     from .cuda import _all_gather_obj
 
     setup_cuda_mpi()
-    info = _all_gather_obj(comm, (requested(), socket.gethostname()))
+    info = _all_gather_obj(comm, (requested(), _node_name()))
     kind, reason = decide([w for w, _ in info], [h for _, h in info])
     if kind == "native":
         from .cuda import NativeComm

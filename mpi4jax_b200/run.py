@@ -3,8 +3,8 @@
 The reference is launched with ``mpirun -n N python script.py`` (README.rst:83-89) and its
 test-suite with ``mpirun -np 2 pytest .`` (docs/developers.rst:18-27).  This image has no
 MPI launcher, and ``torchrun`` insists on a resolvable hostname, so this tiny launcher
-starts N local ranks with RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR=127.0.0.1 /
-MASTER_PORT set, prefixes nothing, waits for all of them and propagates the first
+starts N local ranks with RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR (default 127.0.0.1) /
+MASTER_PORT set (``--nnodes / --node-rank / --master-addr / --master-port`` for several nodes), prefixes nothing, waits for all of them and propagates the first
 non-zero exit code (killing the remaining ranks -- exactly the processes it started).
 
 ``-m module`` runs ``python -m module`` in every rank (``-m pytest tests/distributed``).
@@ -28,15 +28,24 @@ def _free_port() -> int:
 
 
 def launch(nprocs: int, argv: list, *, cpu: bool = False, timeout: float | None = None,
-           env_extra: dict | None = None, capture: bool = False):
-    """Start ``nprocs`` ranks running ``python <argv...>``; returns (exit_code, outputs)."""
-    port = _free_port()
+           env_extra: dict | None = None, capture: bool = False, nnodes: int = 1, node_rank: int = 0,
+           master_addr: str = "127.0.0.1", master_port: int | None = None):
+    """Start ``nprocs`` local ranks running ``python <argv...>``; returns (exit_code, outputs).
+
+    Multi-node jobs run this launcher once per node with the same ``nnodes`` / ``master_addr`` /
+    ``master_port`` and their own ``node_rank``; global rank = ``node_rank * nprocs + local rank``.
+    Communicators that span nodes use the host-staged transport (``backends/transport.py``)."""
+    if nnodes > 1 and master_port is None:
+        raise ValueError("multi-node launches need an explicit --master-port (the same on every node)")
+    port = master_port if master_port is not None else _free_port()
     procs = []
-    for rank in range(nprocs):
+    for local in range(nprocs):
+        rank = node_rank * nprocs + local
         env = dict(os.environ)
         env.update(
-            RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(nprocs),
-            LOCAL_WORLD_SIZE=str(nprocs), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+            RANK=str(rank), LOCAL_RANK=str(local), WORLD_SIZE=str(nnodes * nprocs),
+            LOCAL_WORLD_SIZE=str(nprocs), MASTER_ADDR=master_addr, MASTER_PORT=str(port),
+            GROUP_RANK=str(node_rank),
         )
         if cpu:
             env["MPI4JAX_B200_DEVICE"] = "cpu"
@@ -95,6 +104,10 @@ def main(argv=None) -> int:
     ap.add_argument("-n", "--np", type=int, default=2, dest="nprocs", help="number of ranks")
     ap.add_argument("--cpu", action="store_true", help="force the CPU (gloo) backend")
     ap.add_argument("--timeout", type=float, default=None, help="kill the job after this many seconds")
+    ap.add_argument("--nnodes", type=int, default=1, help="number of nodes (run the launcher once per node)")
+    ap.add_argument("--node-rank", type=int, default=0, help="index of this node, 0 .. nnodes-1")
+    ap.add_argument("--master-addr", default="127.0.0.1", help="address of node 0 (rendezvous)")
+    ap.add_argument("--master-port", type=int, default=None, help="rendezvous port (required for nnodes > 1)")
     ap.add_argument("-m", dest="module", default=None, help="run a module (python -m ...) in every rank")
     ap.add_argument("rest", nargs=argparse.REMAINDER)
     ns = ap.parse_args(argv)
@@ -102,7 +115,8 @@ def main(argv=None) -> int:
     cmd = (["-m", ns.module] if ns.module else []) + rest
     if not cmd:
         ap.error("nothing to run")
-    code, _ = launch(ns.nprocs, cmd, cpu=ns.cpu, timeout=ns.timeout)
+    code, _ = launch(ns.nprocs, cmd, cpu=ns.cpu, timeout=ns.timeout, nnodes=ns.nnodes, node_rank=ns.node_rank,
+                     master_addr=ns.master_addr, master_port=ns.master_port)
     return code
 
 

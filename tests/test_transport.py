@@ -135,3 +135,89 @@ def test_host_transport_end_to_end(tmp_path, device):
                              extra_env={"MPI4JAX_B200_TRANSPORT": "host"})
     assert proc.returncode == 0, proc.stderr[-3000:]
     assert "ok" in proc.stdout
+
+
+_inside_job = size > 1 or "MPI4JAX_B200_NESTED" in __import__("os").environ
+
+_FALLBACK_JOB = """
+import warnings
+import torch
+import mpi4jax_b200 as m
+from mpi4jax_b200 import MPI
+
+comm = MPI.COMM_WORLD
+rank, size = comm.Get_rank(), comm.Get_size()
+with warnings.catch_warnings(record=True) as w:
+    warnings.simplefilter("always")
+    kind = comm.transport
+want = "host" if comm.device.type == "cuda" else "cpu"
+assert kind == want, (kind, want)
+if rank == 0 and want == "host":
+    assert any("ranks span 2 hosts" in str(x.message) for x in w), [str(x.message) for x in w]
+x = torch.arange(5, dtype=torch.float32, device=comm.device) + rank
+assert torch.equal(m.allreduce(x, MPI.SUM, comm=comm), 2 * torch.arange(5, device=comm.device) + 1.0)
+other = 1 - rank
+y = m.sendrecv(x, torch.empty_like(x), other, other, comm=comm)
+assert torch.equal(y, torch.arange(5, dtype=torch.float32, device=comm.device) + other)
+if rank == 0:
+    m.send(x, 1, tag=4)
+else:
+    assert torch.equal(m.recv(torch.empty_like(x), 0, tag=4), x - 1)
+sub = comm.Split(rank, 0)                 # one rank per fake node: single-host again -> native on GPU
+assert sub.transport == ("native" if comm.device.type == "cuda" else "cpu")
+assert torch.equal(m.allreduce(x, MPI.SUM, comm=sub), x)
+m.barrier(comm=comm)
+m.flush()
+print("fallback ok", rank, kind)
+"""
+
+
+def _run_fallback_job(tmp_path, cpu):
+    import os
+
+    from mpi4jax_b200.run import launch
+
+    script = tmp_path / "fallback_job.py"
+    script.write_text(_FALLBACK_JOB)
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code, outs = launch(2, [str(script)], cpu=cpu, timeout=240, capture=True,
+                        env_extra={"MPI4JAX_B200_FAKE_NODE_SIZE": "1", "MPI4JAX_B200_NESTED": "1",
+                                   "PYTHONPATH": repo})
+    assert code == 0, "\n".join(o[-3000:] for o in outs)
+    assert all("fallback ok" in o for o in outs)
+
+
+@pytest.mark.skipif(_inside_job, reason="already inside a multi-rank job")
+def test_multi_node_job_on_cpu(tmp_path):
+    """Two fake nodes with CPU tensors: nothing changes (gloo is the transport anyway)."""
+    _run_fallback_job(tmp_path, cpu=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_inside_job, reason="already inside a multi-rank job")
+def test_multi_node_job_falls_back_to_host_staging(tmp_path):
+    """Two GPU ranks that pretend to sit on different nodes: the world communicator picks the
+    host-staged transport (with a warning), a per-node sub-communicator stays native."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    _run_fallback_job(tmp_path, cpu=False)
+
+
+def test_launcher_multi_node_rank_layout(tmp_path):
+    """--nnodes/--node-rank: global rank = node_rank * nprocs + local rank (no rendezvous needed)."""
+    import json
+
+    from mpi4jax_b200.run import launch
+
+    script = tmp_path / "env.py"
+    script.write_text("import os, json; print(json.dumps({k: os.environ[k] for k in "
+                      "('RANK','LOCAL_RANK','WORLD_SIZE','LOCAL_WORLD_SIZE','MASTER_ADDR','MASTER_PORT')}))")
+    code, outs = launch(2, [str(script)], capture=True, nnodes=3, node_rank=2, master_addr="10.0.0.1",
+                        master_port=29999, timeout=60)
+    assert code == 0
+    envs = sorted((json.loads(o.strip().splitlines()[-1]) for o in outs), key=lambda e: int(e["RANK"]))
+    assert [e["RANK"] for e in envs] == ["4", "5"] and [e["LOCAL_RANK"] for e in envs] == ["0", "1"]
+    assert all(e["WORLD_SIZE"] == "6" and e["MASTER_ADDR"] == "10.0.0.1" and e["MASTER_PORT"] == "29999"
+               for e in envs)
+    with pytest.raises(ValueError, match="master-port"):
+        launch(1, [str(script)], nnodes=2)
