@@ -49,3 +49,25 @@ def Get_library_version():
     from ._src import native
 
     return f"mpi4jax_b200 NVLink transport ({native.NATIVE_ABI_INFO['version']})"
+
+
+def Get_processor_name() -> str:
+    import socket
+
+    return socket.gethostname()
+
+
+def Wtime() -> float:
+    import time
+
+    return time.perf_counter()
+
+
+def Is_initialized() -> bool:
+    import torch.distributed as dist
+
+    return dist.is_initialized()
+
+
+def Is_finalized() -> bool:
+    return False

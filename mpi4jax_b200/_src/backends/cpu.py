@@ -216,8 +216,8 @@ def _match(queue: deque, tag: int):
     return None
 
 
-def recv(comm: Comm, template: torch.Tensor, source: int, tag: int,
-         status: Optional[Status]) -> torch.Tensor:
+def recv_bytes(comm: Comm, source: int, tag: int):
+    """Blocking matched receive of one message: returns ``(source, tag, payload uint8 tensor)``."""
     st = comm._cpu()
     got = None
     src = source
@@ -254,6 +254,12 @@ def recv(comm: Comm, template: torch.Tensor, source: int, tag: int,
             else:
                 st.unexpected[q].append((int(hdr[0]), payload))
     t, payload = got
+    return src, t, payload
+
+
+def recv(comm: Comm, template: torch.Tensor, source: int, tag: int,
+         status: Optional[Status]) -> torch.Tensor:
+    src, t, payload = recv_bytes(comm, source, tag)
     want = template.numel() * template.element_size()
     if payload.numel() > want:
         raise RuntimeError(
@@ -266,6 +272,22 @@ def recv(comm: Comm, template: torch.Tensor, source: int, tag: int,
     if status is not None:
         status._set(src, t, payload.numel(), template.element_size())
     return out
+
+
+def send_object(comm: Comm, obj, dest: int, tag: int) -> None:
+    """Pickle-based message (mpi4py's lower-case ``comm.send``)."""
+    import pickle
+
+    send(comm, torch.frombuffer(bytearray(pickle.dumps(obj)), dtype=torch.uint8), dest, tag)
+
+
+def recv_object(comm: Comm, source: int, tag: int, status: Optional[Status]):
+    import pickle
+
+    src, t, payload = recv_bytes(comm, source, tag)
+    if status is not None:
+        status._set(src, t, payload.numel(), 1)
+    return pickle.loads(payload.numpy().tobytes())
 
 
 def sendrecv(comm: Comm, sendbuf: torch.Tensor, recv_template: torch.Tensor, source: int,

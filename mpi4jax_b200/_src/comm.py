@@ -51,6 +51,21 @@ class Op:
     def __repr__(self) -> str:
         return f"<mpi4jax_b200.MPI.{self.name}>"
 
+    def python_function(self):
+        """Binary Python function of the operator (used by the object collectives, like mpi4py's
+        ``comm.allreduce(obj, op)``)."""
+        import operator
+
+        return {
+            "SUM": operator.add, "PROD": operator.mul, "MIN": min, "MAX": max,
+            "LAND": lambda a, b: bool(a) and bool(b), "LOR": lambda a, b: bool(a) or bool(b),
+            "LXOR": lambda a, b: bool(a) != bool(b),
+            "BAND": operator.and_, "BOR": operator.or_, "BXOR": operator.xor,
+        }[self.name]
+
+    def __call__(self, a, b):
+        return self.python_function()(a, b)
+
     def __reduce__(self):
         return (_op_by_name, (self.name,))
 
@@ -268,6 +283,75 @@ class Comm:
         if self._native is not None:
             self._native.destroy()
             self._native = None
+
+    # -- mpi4py's lower-case (pickle-based, host-synchronous) object API ----------------------
+    # Scripts written for mpi4jax use mpi4py for their Python-side bookkeeping (rank-0 gathers of
+    # results, parameter broadcasts, ...); there is no mpi4py here, so the communicator offers the
+    # same calls over the gloo control plane.  Like in the reference (docs/sharp-bits.rst:74-135)
+    # they share the tag space of the tensor ops of this communicator: do not interleave the two
+    # on one communicator -- the default communicator of the tensor ops is a private clone.
+    def barrier(self) -> None:
+        self.Barrier()
+
+    def bcast(self, obj=None, root: int = 0):
+        self._check_alive()
+        if self.size == 1:
+            return obj
+        box = [obj]
+        dist.broadcast_object_list(box, src=self._global(root), group=self._group)
+        return box[0]
+
+    def allgather(self, obj) -> list:
+        self._check_alive()
+        out = [None] * self.size
+        if self.size == 1:
+            return [obj]
+        dist.all_gather_object(out, obj, group=self._group)
+        return out
+
+    def gather(self, obj, root: int = 0):
+        everything = self.allgather(obj)           # gloo's gather_object needs the same traffic
+        return everything if self.rank == root else None
+
+    def scatter(self, objs=None, root: int = 0):
+        if self.rank == root and (objs is None or len(objs) != self.size):
+            raise ValueError(f"scatter needs a sequence of {self.size} objects on the root")
+        return self.bcast(list(objs) if self.rank == root else None, root)[self.rank]
+
+    def allreduce(self, obj, op=None):
+        import functools
+
+        fn = (op or SUM).python_function()
+        return functools.reduce(fn, self.allgather(obj))
+
+    def reduce(self, obj, op=None, root: int = 0):
+        total = self.allreduce(obj, op)
+        return total if self.rank == root else None
+
+    def send(self, obj, dest: int, tag: int = 0) -> None:
+        from .backends import cpu as _cpu
+
+        self._check_alive()
+        _cpu.send_object(self, obj, int(dest), int(tag))
+
+    def recv(self, buf=None, source: int = ANY_SOURCE, tag: int = ANY_TAG, status: Optional[Status] = None):
+        from .backends import cpu as _cpu
+
+        self._check_alive()
+        return _cpu.recv_object(self, int(source), int(tag), status)
+
+    def sendrecv(self, sendobj, dest: int, sendtag: int = 0, recvbuf=None, source: int = ANY_SOURCE,
+                 recvtag: int = ANY_TAG, status: Optional[Status] = None):
+        self.send(sendobj, dest, sendtag)          # eager: cannot deadlock against the receive
+        return self.recv(None, source, recvtag, status)
+
+    def Abort(self, errorcode: int = 1) -> None:
+        """Kill the job (the launcher stops the remaining ranks when one exits non-zero)."""
+        import sys
+
+        sys.stderr.write(f"r{self.rank} | MPI_Abort called with error code {errorcode} - aborting\n")
+        sys.stderr.flush()
+        os._exit(errorcode if 0 < errorcode < 256 else 1)
 
     def py2f(self) -> int:
         return self._id
