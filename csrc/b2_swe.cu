@@ -190,11 +190,6 @@ int b2_swe_friction_v(B2Comm* c, const B2SweParams* p, float* v, const float* fe
 // capture turns into a single replayable graph.  `h0`/`h1` ping-pong (their wall rows are
 // initialised identically and never written); the state is returned in h0 (an odd step count
 // ends with one device copy).
-struct B2SweState {
-  float *h0, *h1, *u, *v, *dh, *du, *dv, *fe, *fn, *q, *ke, *fe2, *fn2;
-  float* u1;   // ping-pong partner of u for the friction update (unused by the fused path)
-};
-
 // Layout record for the import-time ABI check (mpi4jax_b200/_src/native/__init__.py): the Python
 // side mirrors these structs with ctypes, so a stale library with a different layout must be
 // rejected before the first call (the reference checks the MPI handle ABI the same way,

@@ -17,6 +17,13 @@ struct B2SweParams {
   const float* coriolis;      // [ny]
 };
 
+// Device pointers of a model's fields (mirrored by ctypes in _src/native/__init__.py; the layout
+// is part of the ABI checked at import).  h0/h1 and u/u1 are ping-pong pairs.
+struct B2SweState {
+  float *h0, *h1, *u, *v, *dh, *du, *dv, *fe, *fn, *q, *ke, *fe2, *fn2;
+  float* u1;   // partner of u for the friction update of the stand-alone path (b2_swe.cu)
+};
+
 #define SWE_THREADS 256
 
 // An aligned group of four cells plus its west / east neighbours.

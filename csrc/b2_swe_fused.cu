@@ -42,11 +42,6 @@ extern "C" void b2_count_launch(B2Comm* c);
 
 #define SWE_UNPACKERS 16
 
-struct B2SweState {
-  float *h0, *h1, *u, *v, *dh, *du, *dv, *fe, *fn, *q, *ke, *fe2, *fn2;
-  float* u1;   // used by the stand-alone path only (csrc/b2_swe.cu)
-};
-
 struct FusedArgs {
   B2SweParams p;
   float *h, *hn, *u, *v, *dh, *du, *dv, *fe, *fn, *q, *ke, *fe2, *fn2;
