@@ -50,7 +50,8 @@ def reference_arm() -> int:
         why = "baseline/_ref/mpi4jax imports, but no MPI launcher / jax runtime exists to run it"
     except Exception:
         pass
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:          # one line per job, also under torchrun
+        print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
 
 
