@@ -73,6 +73,30 @@ __device__ __forceinline__ int hc_row(const B2SweParams& p, int j) {
 
 struct SweOut4 { float a[4][4]; };   // [field][lane]
 
+// ---- the four diagnostic quantities of the flux kernel, with every rounding spelled out --------
+// (explicit round-to-nearest intrinsics are never contracted by ptxas).  Spelling them out makes
+// the result independent of the kernel the expression is inlined into, which is what allows a
+// kernel that RECOMPUTES these quantities at its stencil neighbours to be bit-identical to one
+// that reads them from memory.  The operation order is the one nvcc chose for the plain
+// expressions of swe_k1_body (read off its SASS: which products are rounded before the FMA).
+__device__ __forceinline__ float swe_fe(float h_c, float h_e, float u_c) {          // mass flux east
+  return __fmul_rn(__fmul_rn(__fadd_rn(h_c, h_e), 0.5f), u_c);
+}
+__device__ __forceinline__ float swe_fn(float h_c, float h_n, float v_c) {          // mass flux north
+  return __fmul_rn(__fmul_rn(__fadd_rn(h_c, h_n), 0.5f), v_c);
+}
+__device__ __forceinline__ float swe_q(const B2SweParams& p, float cor, float v_e, float v_c, float u_n,
+                                       float u_c, float h_c, float h_e, float h_n, float h_ne) {
+  const float rel = __fmaf_rn(__fadd_rn(v_e, -v_c), p.rdx, -__fmul_rn(__fadd_rn(u_n, -u_c), p.rdy));
+  const float den = __fmul_rn(__fadd_rn(h_ne, __fadd_rn(h_n, __fadd_rn(h_c, h_e))), 0.25f);
+  return __fmul_rn(__fadd_rn(cor, rel), 1.0f / den);                                 // potential vorticity
+}
+__device__ __forceinline__ float swe_ke(float u_c, float u_w, float v_c, float v_s) {   // kinetic energy
+  const float uu = __fmaf_rn(u_c, u_c, __fmul_rn(u_w, u_w));
+  const float vv = __fmaf_rn(v_c, v_c, __fmul_rn(v_s, v_s));
+  return __fmul_rn(__fmaf_rn(vv, 0.5f, __fmul_rn(uu, 0.5f)), 0.5f);
+}
+
 __device__ __forceinline__ void swe_k1_body(const B2SweParams& p, const float* __restrict__ h,
                                             const float* __restrict__ u, const float* __restrict__ v,
                                             float* __restrict__ fe, float* __restrict__ fn,
