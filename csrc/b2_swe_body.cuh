@@ -22,6 +22,7 @@ struct B2SweParams {
 struct B2SweState {
   float *h0, *h1, *u, *v, *dh, *du, *dv, *fe, *fn, *q, *ke, *fe2, *fn2;
   float* u1;   // partner of u for the friction update of the stand-alone path (b2_swe.cu)
+  float* v1;   // partner of v, used by the fused flux+tendency path only (b2_swe_k12.cu)
 };
 
 #define SWE_THREADS 256

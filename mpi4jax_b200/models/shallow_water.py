@@ -76,7 +76,7 @@ class ShallowWaterConfig:
 class ShallowWaterModel:
     def __init__(self, config: Optional[ShallowWaterConfig] = None, comm: Optional[Comm] = None,
                  device: Optional[torch.device] = None, backend: str = "auto",
-                 fused: Optional[bool] = None):
+                 fused: Optional[bool] = None, k12: Optional[bool] = None):
         self.cfg = cfg = config or ShallowWaterConfig()
         self.comm = comm = comm or get_default_comm()
         self.device = torch.device(device) if device is not None else comm.device
@@ -87,6 +87,10 @@ class ShallowWaterModel:
         if backend == "native" and self.device.type != "cuda":
             raise ValueError("backend='native' needs a CUDA device")
         self.backend = backend
+        # k12=True: flux and tendency kernels fused, 21 instead of 32 array passes per step
+        # (csrc/b2_swe_k12.cu).  EXPERIMENTAL: written and host-emulated (tests/
+        # test_swe_host_emulation.py) but not yet measured on hardware; opt-in only.
+        self.k12 = env_flag("MPI4JAX_B200_SWE_K12", False) if k12 is None else bool(k12)
         # fused=True: halo exchange fused into the stencil kernels (csrc/b2_swe_fused.cu);
         # default is the stand-alone exchange kernel, which currently measures faster (profiles/)
         self.fused = env_flag("MPI4JAX_B200_SWE_FUSED", False) if fused is None else bool(fused)
@@ -154,6 +158,7 @@ class ShallowWaterModel:
         self.dh, self.du, self.dv = z(), z(), z()
         self._h1 = z()
         self._u1 = z()      # ping-pong partner of u for the friction update
+        self._v1 = z()      # ping-pong partner of v (fused flux+tendency path only)
         self.fe, self.fn, self.q, self.ke, self.fe2, self.fn2 = z(), z(), z(), z(), z(), z()
         y_global = (np.arange(-1, self.ny_global - 1) * self.cfg.dy)
         cor = self.cfg.coriolis_f + y_global[self.local_slice[0]] * self.cfg.coriolis_beta
@@ -173,6 +178,7 @@ class ShallowWaterModel:
             st = self._state = native.B2SweState()
             st.h0, st.h1 = self.h.data_ptr(), self._h1.data_ptr()
             st.u1 = self._u1.data_ptr()
+            st.v1 = self._v1.data_ptr()
             for name in ("u", "v", "dh", "du", "dv", "fe", "fn", "q", "ke", "fe2", "fn2"):
                 setattr(st, name, getattr(self, name).data_ptr())
             t = self._topo = native.B2HaloDesc()
@@ -216,8 +222,14 @@ class ShallowWaterModel:
         for t in (self.dh, self.du, self.dv, self.fe, self.fn, self.q, self.ke, self.fe2, self.fn2):
             t.zero_()
         self.enforce_boundaries([self.h, self.u, self.v], ["h", "u", "v"])
-        self._h1.copy_(self.h)      # ping-pong partner: identical wall rows / halos
+        self._sync_partners()
         self.steps_done = 0
+
+    def _sync_partners(self) -> None:
+        """Ping-pong partners start as copies: identical wall rows / halos that no kernel writes."""
+        self._h1.copy_(self.h)
+        self._u1.copy_(self.u)
+        self._v1.copy_(self.v)
 
     def load_state(self, state: ModelState) -> None:
         """Overwrite the prognostic fields (e.g. from pinned host memory, non-blocking)."""
@@ -278,7 +290,8 @@ class ShallowWaterModel:
             first_step = self.steps_done == 0
         if self.backend == "native":
             nc = self.comm._native_comm()
-            fn = native.lib.b2_swe_multistep_fused if self.fused else native.lib.b2_swe_multistep
+            fn = (native.lib.b2_swe_multistep_fused if self.fused else
+                  native.lib.b2_swe_multistep_k12 if self.k12 else native.lib.b2_swe_multistep)
             rc = fn(
                 nc.handle, ctypes.byref(self._params), ctypes.byref(self._state),
                 ctypes.byref(self._topo), int(nsteps), int(bool(first_step)),
@@ -402,7 +415,7 @@ class ShallowWaterModel:
         if bad:
             raise ValueError(f"checkpoint {path} does not match this model (checkpoint, model): {bad}")
         self.load_state(ModelState(**payload["state"]))
-        self._h1.copy_(self.h)
+        self._sync_partners()
         self.steps_done = int(payload["steps_done"])
         return self.steps_done
 
