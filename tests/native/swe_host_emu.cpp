@@ -107,6 +107,39 @@ void emu_k5_pp(const B2SweParams* p, const float* v, float* v_new, const float* 
     }
 }
 
+// merged friction kernel: u -> u_new, friction-v fluxes (swe_k34_friction_u)
+void emu_k34(const B2SweParams* p, const float* u, float* u_new, const float* v, float* fe2, float* fn2,
+             int has_south) {
+  for (int j = 1; j <= p->ny - 2; ++j)
+    for (int i0 = 0; i0 < p->pitch; i0 += 4) {
+      bool m[4];
+      masks(*p, i0, m);
+      if (!(m[0] || m[1] || m[2] || m[3])) continue;
+      SweOut4 o;
+      swe_k34_body(*p, u, u_new, v, fe2, fn2, j, i0, m, has_south != 0, o);
+    }
+}
+
+// the two-kernel formulation it replaced: K3 (fluxes of u, local halo) then K4 (apply + v fluxes)
+void emu_k3_k4(const B2SweParams* p, float* u, const float* v, float* fe, float* fn, float* fe2, float* fn2,
+               int has_south) {
+  for (int j = 1; j <= p->ny - 2; ++j)
+    for (int i0 = 0; i0 < p->pitch; i0 += 4) {
+      bool m[4];
+      masks(*p, i0, m);
+      if (!(m[0] || m[1] || m[2] || m[3])) continue;
+      swe_k3_body(*p, u, fe, fn, j, i0, m, true, has_south != 0);
+    }
+  for (int j = 1; j <= p->ny - 2; ++j)
+    for (int i0 = 0; i0 < p->pitch; i0 += 4) {
+      bool m[4];
+      masks(*p, i0, m);
+      if (!(m[0] || m[1] || m[2] || m[3])) continue;
+      SweOut4 o;
+      swe_k4_body(*p, u, v, fe, fn, fe2, fn2, j, i0, m, o);
+    }
+}
+
 int emu_k12_supported(const B2SweParams* p) { return swe_k12_supported(*p) ? 1 : 0; }
 
 // which (row, group) tasks does a frame of width w enumerate?  marks[j * ngroups + g] += 1

@@ -169,3 +169,157 @@ def test_friction_v_ping_pong_equals_in_place(emu):
     emu.emu_k5_pp(ctypes.byref(p), _ptr(fld["v"]), _ptr(v_new), _ptr(fe2), _ptr(fn2))
     ncol = ((nx - 2) // 4 + 1) * 4           # the pure pad group is never touched
     assert np.array_equal(v_new[:, :ncol], v_ref[:, :ncol])
+
+
+def test_merged_friction_kernel_equals_k3_k4(emu):
+    """swe_k34_body (friction-u fluxes inline, out of place) vs K3 -> K4 (fluxes through memory,
+    in place): same numbers -- the claim behind removing one kernel and one exchange per step."""
+    for walls, has_south in (((1, 0), 0), ((0, 1), 1), ((0, 0), 1), ((1, 1), 0)):
+        ny, nx = 21, 30
+        p, fld, cor, rng = _setup(ny, nx, False, *walls, seed=7)
+        ncol = ((nx - 2) // 4 + 1) * 4
+        z = lambda: np.zeros((ny, p.pitch), np.float32)   # noqa: E731
+        u_ref, fe, fn, fe2_ref, fn2_ref = fld["u"].copy(), z(), z(), z(), z()
+        emu.emu_k3_k4(ctypes.byref(p), _ptr(u_ref), _ptr(fld["v"]), _ptr(fe), _ptr(fn), _ptr(fe2_ref),
+                      _ptr(fn2_ref), has_south)
+        u_new, fe2, fn2 = np.full_like(u_ref, np.nan), z(), z()
+        emu.emu_k34(ctypes.byref(p), _ptr(fld["u"]), _ptr(u_new), _ptr(fld["v"]), _ptr(fe2), _ptr(fn2), has_south)
+        assert np.array_equal(u_new[:, :ncol], u_ref[:, :ncol]), (walls, has_south)
+        assert np.array_equal(fe2[1:-1, :ncol], fe2_ref[1:-1, :ncol])
+        assert np.array_equal(fn2[1:-1, :ncol], fn2_ref[1:-1, :ncol])
+
+
+# ---- whole steps: the launch sequence of b2_swe_multistep(_k12), emulated on a process grid -------
+def _blocks(model, PY, PX):
+    """Cut the model's global initial condition into (PY x PX) blocks with one halo cell, as
+    ShallowWaterModel does per rank; returns per-rank dicts of pitch-padded float32 arrays."""
+    h0, u0, v0 = model.initial_conditions_global()
+    NY, NX = h0.shape
+    nyi, nxi = (NY - 2) // PY, (NX - 2) // PX
+    pitch = (nxi + 2 + 3) // 4 * 4
+    ranks = []
+    for py in range(PY):
+        for px in range(PX):
+            blk = {}
+            for name, g in (("h", h0), ("u", u0), ("v", v0)):
+                a = np.zeros((nyi + 2, pitch), np.float32)
+                a[:, :nxi + 2] = g[py * nyi: py * nyi + nyi + 2, px * nxi: px * nxi + nxi + 2]
+                blk[name] = a
+            for name in ("h1", "u1", "v1", "dh", "du", "dv", "fe", "fn", "q", "ke", "fe2", "fn2"):
+                blk[name] = np.zeros((nyi + 2, pitch), np.float32)
+            y_global = np.arange(-1, NY - 1) * model.cfg.dy
+            cor = (model.cfg.coriolis_f + y_global[py * nyi: py * nyi + nyi + 2] * model.cfg.coriolis_beta)
+            blk["cor"] = cor.astype(np.float32)
+            ranks.append(blk)
+    return ranks, nyi + 2, nxi + 2, pitch
+
+
+def _params(model, blk, ny, nx, pitch, py, PY, first):
+    cfg = model.cfg
+    return Params(ny=ny, nx=nx, pitch=pitch, dx=cfg.dx, dy=cfg.dy, dt=cfg.dt, gravity=cfg.gravity,
+                  viscosity=cfg.lateral_viscosity, rdx=np.float32(1) / np.float32(cfg.dx),
+                  rdy=np.float32(1) / np.float32(cfg.dy), ab_a=cfg.ab_a, ab_b=cfg.ab_b, first_step=int(first),
+                  south_wall=int(py == 0), north_wall=int(py == PY - 1), coriolis=blk["cor"].ctypes.data)
+
+
+def _exchange(ranks, names, kinds, nx, PY, PX):
+    from ._halo_sim import new_exchange
+
+    for name, kind in zip(names, kinds):
+        new_exchange([r[name][:, :nx] for r in ranks], PY, PX, kind)
+
+
+def _emulate(emu, model, PY, PX, nsteps, k12):
+    from ._halo_sim import new_exchange
+
+    ranks, ny, nx, pitch = _blocks(model, PY, PX)
+    # reset(): halos of the initial state, ping-pong partners start as copies
+    for name, kind in (("h", "h"), ("u", "u"), ("v", "v")):
+        new_exchange([r[name][:, :nx] for r in ranks], PY, PX, kind)
+    for r in ranks:
+        r["h1"][:], r["u1"][:], r["v1"][:] = r["h"], r["u"], r["v"]
+    hk, hnk = "h", "h1"
+    for it in range(nsteps):
+        ps = [_params(model, r, ny, nx, pitch, i // PX, PY, it == 0) for i, r in enumerate(ranks)]
+        B = ctypes.byref
+        if k12:
+            for r, p in zip(ranks, ps):
+                emu.emu_k12_bulk(B(p), _ptr(r[hk]), _ptr(r[hnk]), _ptr(r["u"]), _ptr(r["u1"]), _ptr(r["v"]),
+                                 _ptr(r["v1"]), _ptr(r["dh"]), _ptr(r["du"]), _ptr(r["dv"]))
+                emu.emu_k1_frame(B(p), _ptr(r[hk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["fe"]), _ptr(r["fn"]),
+                                 _ptr(r["q"]), _ptr(r["ke"]))
+            _exchange(ranks, ("fe", "fn", "q", "ke"), ("u", "v", "h", "h"), nx, PY, PX)
+            for r, p in zip(ranks, ps):
+                emu.emu_k2_ring(B(p), _ptr(r[hk]), _ptr(r[hnk]), _ptr(r["u"]), _ptr(r["u1"]), _ptr(r["v"]),
+                                _ptr(r["v1"]), _ptr(r["dh"]), _ptr(r["du"]), _ptr(r["dv"]), _ptr(r["fe"]),
+                                _ptr(r["fn"]), _ptr(r["q"]), _ptr(r["ke"]))
+            _exchange(ranks, (hnk, "u1", "v1"), ("h", "u", "v"), nx, PY, PX)
+            for i, (r, p) in enumerate(zip(ranks, ps)):
+                emu.emu_k34(B(p), _ptr(r["u1"]), _ptr(r["u"]), _ptr(r["v1"]), _ptr(r["fe2"]), _ptr(r["fn2"]),
+                            int(i // PX > 0))
+            _exchange(ranks, ("fe2", "fn2"), ("u", "v"), nx, PY, PX)
+            for r, p in zip(ranks, ps):
+                emu.emu_k5_pp(B(p), _ptr(r["v1"]), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]))
+        else:
+            for r, p in zip(ranks, ps):
+                emu.emu_k1_all(B(p), _ptr(r[hk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["fe"]), _ptr(r["fn"]),
+                               _ptr(r["q"]), _ptr(r["ke"]))
+            _exchange(ranks, ("fe", "fn", "q", "ke"), ("u", "v", "h", "h"), nx, PY, PX)
+            for r, p in zip(ranks, ps):
+                emu.emu_k2_all(B(p), _ptr(r[hk]), _ptr(r[hnk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["dh"]),
+                               _ptr(r["du"]), _ptr(r["dv"]), _ptr(r["fe"]), _ptr(r["fn"]), _ptr(r["q"]),
+                               _ptr(r["ke"]))
+            _exchange(ranks, (hnk, "u", "v"), ("h", "u", "v"), nx, PY, PX)
+            for i, (r, p) in enumerate(zip(ranks, ps)):
+                emu.emu_k34(B(p), _ptr(r["u"]), _ptr(r["u1"]), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]),
+                            int(i // PX > 0))
+                r["u"], r["u1"] = r["u1"], r["u"]
+            _exchange(ranks, ("fe2", "fn2"), ("u", "v"), nx, PY, PX)
+            for r, p in zip(ranks, ps):
+                emu.emu_k5(B(p), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]))
+        hk, hnk = hnk, hk
+    return [dict(h=r[hk][:, :nx], u=r["u"][:, :nx], v=r["v"][:, :nx], dh=r["dh"][:, :nx], du=r["du"][:, :nx],
+                 dv=r["dv"][:, :nx]) for r in ranks]
+
+
+def _close(a, b, tol):
+    return np.abs(a - b).max() <= tol * (np.abs(b).max() + 1e-30)
+
+
+def test_emulated_native_step_matches_the_ops_backend(emu):
+    """The kernel launch sequence of b2_swe_multistep (bodies + single-phase halo exchange),
+    executed on the host, vs the model written with the public ops -- the GPU suite's
+    native-vs-ops comparison, on a box without a GPU."""
+    import torch
+
+    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
+
+    cfg = ShallowWaterConfig(nx=48, ny=24)
+    model = ShallowWaterModel(cfg, device="cpu", backend="ops")
+    nsteps = 6
+    emu_state = _emulate(emu, model, 1, 1, nsteps, k12=False)[0]
+    model.multistep(nsteps)
+    for name, t in model.state._asdict().items():
+        got, want = emu_state[name], t.numpy()
+        assert np.isfinite(got).all()
+        tol = 2e-4 if name in ("h", "u", "v") else 2e-3
+        assert _close(got[1:-1, 1:-1], want[1:-1, 1:-1], tol), name
+    assert isinstance(model.h, torch.Tensor)
+
+
+@pytest.mark.parametrize("grid", [(1, 1), (1, 2), (2, 2), (3, 2)])
+def test_emulated_k12_pipeline_matches_standalone_pipeline(emu, grid):
+    """Whole steps on a process grid: the fused flux+tendency pipeline (incl. its frame exchange
+    and the u / v ping-pong) against the stand-alone pipeline, same decomposition."""
+    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
+
+    PY, PX = grid
+    cfg = ShallowWaterConfig(nx=48 * PX, ny=24 * PY)
+    model = ShallowWaterModel(cfg, device="cpu", backend="ops")
+    a = _emulate(emu, model, PY, PX, 5, k12=False)
+    b = _emulate(emu, model, PY, PX, 5, k12=True)
+    for ra, rb in zip(a, b):
+        for name in ra:
+            assert np.isfinite(rb[name]).all(), name
+            tol = 5e-6 if name in ("h", "u", "v") else 1e-3
+            assert _close(rb[name][1:-1, 1:-1], ra[name][1:-1, 1:-1], tol), (grid, name)
