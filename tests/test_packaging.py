@@ -47,3 +47,17 @@ def test_setup_py_skip_native_build(tmp_path):
                           "--build-temp", str(tmp_path)], cwd=REPO, env=env, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     assert "skipping the native build" in res.stderr
+
+
+def test_info_cli():
+    res = subprocess.run([sys.executable, "-m", "mpi4jax_b200.info", "--json"], cwd=REPO, capture_output=True,
+                         text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    import json
+
+    info = json.loads(res.stdout)
+    assert info["version"] == m.__version__ and info["native_loaded"] is True
+    assert info["native_abi"]["abi_version"] >= 5 and info["requested_transport"] in ("auto", "native", "host")
+    res = subprocess.run([sys.executable, "-m", "mpi4jax_b200.info"], cwd=REPO, capture_output=True, text=True,
+                         timeout=120)
+    assert res.returncode == 0 and "native core" in res.stdout
