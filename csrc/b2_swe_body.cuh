@@ -74,6 +74,14 @@ __device__ __forceinline__ int hc_row(const B2SweParams& p, int j) {
 
 struct SweOut4 { float a[4][4]; };   // [field][lane]
 
+// B2_SWE_EXPLICIT_ROUNDING=1 makes swe_k1_body use the explicit-rounding helpers below instead of
+// plain expressions (whose FMA contraction ptxas picks, differently per lane).  With it, a kernel
+// that recomputes the flux quantities (b2_swe_k12.cu) agrees with the two-kernel path to the bit.
+// Default 0: the validated binaries were built from the plain expressions; flip after a GPU run.
+#ifndef B2_SWE_EXPLICIT_ROUNDING
+#define B2_SWE_EXPLICIT_ROUNDING 0
+#endif
+
 // ---- the four diagnostic quantities of the flux kernel, with every rounding spelled out --------
 // (explicit round-to-nearest intrinsics are never contracted by ptxas).  Spelling them out makes
 // the result independent of the kernel the expression is inlined into, which is what allows a
@@ -118,11 +126,18 @@ __device__ __forceinline__ void swe_k1_body(const B2SweParams& p, const float* _
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float uk = U[k + 1], vk = V[k];
+#if B2_SWE_EXPLICIT_ROUNDING
+    FE[k] = swe_fe(H[k], H[k + 1], uk);
+    FN[k] = swe_fn(H[k], HN[k], vk);
+    Q[k] = swe_q(p, cor, V[k + 1], vk, UN[k], uk, H[k], H[k + 1], HN[k], HN[k + 1]);
+    KE[k] = swe_ke(uk, U[k], vk, VS[k]);
+#else
     FE[k] = 0.5f * (H[k] + H[k + 1]) * uk;
     FN[k] = 0.5f * (H[k] + HN[k]) * vk;
     const float rel = (V[k + 1] - vk) * p.rdx - (UN[k] - uk) * p.rdy;
     Q[k] = (cor + rel) * (1.0f / (0.25f * (H[k] + H[k + 1] + HN[k] + HN[k + 1])));
     KE[k] = 0.5f * (0.5f * (uk * uk + U[k] * U[k]) + 0.5f * (vk * vk + VS[k] * VS[k]));
+#endif
     if (!m[k]) FE[k] = FN[k] = Q[k] = KE[k] = 0.f;   // halo / pad lanes: refreshed by the exchange
     if (p.north_wall && j == p.ny - 2) FN[k] = 0.f;    // "v" wall rule (shallow_water.py:261-262)
     o.a[0][k] = FE[k]; o.a[1][k] = FN[k]; o.a[2][k] = Q[k]; o.a[3][k] = KE[k];

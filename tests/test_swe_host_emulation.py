@@ -29,18 +29,29 @@ class Params(ctypes.Structure):       # B2SweParams (csrc/b2_swe_body.cuh)
                 ("coriolis", ctypes.c_void_p)]
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    out = tmp_path_factory.mktemp("emu") / "libswe_emu.so"
-    cmd = ["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(REPO, "csrc"),
-           "-I", CUDA_INC, os.path.join(REPO, "tests", "native", "swe_host_emu.cpp"), "-o", str(out)]
+def _build(tmp_path_factory, name, *defines):
+    out = tmp_path_factory.mktemp(name) / f"lib{name}.so"
+    cmd = ["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", *defines, "-I",
+           os.path.join(REPO, "csrc"), "-I", CUDA_INC, os.path.join(REPO, "tests", "native", "swe_host_emu.cpp"),
+           "-o", str(out)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
-    lib = ctypes.CDLL(str(out))
+    return ctypes.CDLL(str(out))
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    lib = _build(tmp_path_factory, "swe_emu")
     from mpi4jax_b200._src import native
 
     assert ctypes.sizeof(Params) == ctypes.sizeof(native.B2SweParams)
     return lib
+
+
+@pytest.fixture(scope="module")
+def emu_explicit(tmp_path_factory):
+    """The same bodies with B2_SWE_EXPLICIT_ROUNDING=1 (flux kernel built from the helpers)."""
+    return _build(tmp_path_factory, "swe_emu_explicit", "-DB2_SWE_EXPLICIT_ROUNDING=1")
 
 
 def _ptr(a):
@@ -323,3 +334,23 @@ def test_emulated_k12_pipeline_matches_standalone_pipeline(emu, grid):
             assert np.isfinite(rb[name]).all(), name
             tol = 5e-6 if name in ("h", "u", "v") else 1e-3
             assert _close(rb[name][1:-1, 1:-1], ra[name][1:-1, 1:-1], tol), (grid, name)
+
+
+@pytest.mark.parametrize("grid", [(1, 1), (2, 2)])
+def test_explicit_rounding_build_makes_both_pipelines_bit_identical(emu, emu_explicit, grid):
+    """With B2_SWE_EXPLICIT_ROUNDING=1 the flux kernel and the fused kernel share every rounding:
+    the two pipelines agree to the bit (here: host arithmetic; the device build inherits the property
+    because explicit intrinsics are not contractable), and the switch moves the stand-alone results
+    only at rounding level."""
+    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
+
+    PY, PX = grid
+    model = ShallowWaterModel(ShallowWaterConfig(nx=48 * PX, ny=24 * PY), device="cpu", backend="ops")
+    a = _emulate(emu_explicit, model, PY, PX, 6, k12=False)
+    b = _emulate(emu_explicit, model, PY, PX, 6, k12=True)
+    plain = _emulate(emu, model, PY, PX, 6, k12=False)
+    for ra, rb, rp in zip(a, b, plain):
+        for name in ra:
+            assert np.array_equal(ra[name][1:-1, 1:-1], rb[name][1:-1, 1:-1]), (grid, name)
+            tol = 5e-5 if name in ("h", "u", "v") else 1e-3      # per-rank normalisation: v is tiny off the jet
+            assert _close(ra[name][1:-1, 1:-1], rp[name][1:-1, 1:-1], tol), (grid, name)
