@@ -149,6 +149,41 @@ __device__ __forceinline__ void swe_k1_body(const B2SweParams& p, const float* _
   st4(ke, off, make_float4(KE[0], KE[1], KE[2], KE[3]));
 }
 
+struct SweK2In {
+  float fe_c, fe_w, fen_c, fen_w;      // fe[j][i], fe[j][i-1], fe[j+1][i], fe[j+1][i-1]
+  float fn_c, fn_e, fns_c, fns_e;      // fn[j][i], fn[j][i+1], fn[j-1][i], fn[j-1][i+1]
+  float q_c, q_w, qs_c;                // q[j][i], q[j][i-1], q[j-1][i]
+  float ke_c, ke_e, ken_c;             // ke[j][i], ke[j][i+1], ke[j+1][i]
+  float h_c, h_e, h_n;                 // h[j][i], h[j][i+1], h[j+1][i]
+  float u_o, v_o, dh_o, du_o, dv_o;    // own cell, old values
+};
+struct SweK2Out {
+  float h, u, v, dh, du, dv;
+};
+
+// The per-cell arithmetic of swe_k2_body (same expressions, same order).
+__device__ __forceinline__ SweK2Out swe_k2_cell(const B2SweParams& p, const SweK2In& x) {
+  const float dh_new = -(x.fe_c - x.fe_w) * p.rdx - (x.fn_c - x.fns_c) * p.rdy;
+  float du_new = -p.gravity * (x.h_e - x.h_c) * p.rdx +
+                 0.5f * (x.q_c * 0.5f * (x.fn_c + x.fn_e) + x.qs_c * 0.5f * (x.fns_c + x.fns_e));
+  float dv_new = -p.gravity * (x.h_n - x.h_c) * p.rdy -
+                 0.5f * (x.q_c * 0.5f * (x.fe_c + x.fen_c) + x.q_w * 0.5f * (x.fe_w + x.fen_w));
+  du_new += -(x.ke_e - x.ke_c) * p.rdx;
+  dv_new += -(x.ken_c - x.ke_c) * p.rdy;
+  SweK2Out o;
+  if (p.first_step) {
+    o.u = x.u_o + p.dt * du_new;
+    o.v = x.v_o + p.dt * dv_new;
+    o.h = x.h_c + p.dt * dh_new;
+  } else {
+    o.u = x.u_o + p.dt * (p.ab_a * du_new + p.ab_b * x.du_o);
+    o.v = x.v_o + p.dt * (p.ab_a * dv_new + p.ab_b * x.dv_o);
+    o.h = x.h_c + p.dt * (p.ab_a * dh_new + p.ab_b * x.dh_o);
+  }
+  o.dh = dh_new; o.du = du_new; o.dv = dv_new;
+  return o;
+}
+
 __device__ __forceinline__ void swe_k2_body(const B2SweParams& p, const float* __restrict__ h,
                                             float* __restrict__ h_new, float* __restrict__ u,
                                             float* __restrict__ v, float* __restrict__ dh,
@@ -175,6 +210,24 @@ __device__ __forceinline__ void swe_k2_body(const B2SweParams& p, const float* _
   const float DHo[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, DUo[4] = {du4.x, du4.y, du4.z, du4.w},
               DVo[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
   float Un[4], Vn[4], Hn[4], DH[4], DU[4], DV[4];
+#if B2_SWE_EXPLICIT_ROUNDING
+  // the shared per-cell function (also used by the fused flux+tendency kernel)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    SweK2In in;
+    in.fe_c = FE[k + 1]; in.fe_w = FE[k]; in.fen_c = FEN[k + 1]; in.fen_w = FEN[k];
+    in.fn_c = FN[k]; in.fn_e = FN[k + 1]; in.fns_c = FNS[k]; in.fns_e = FNS[k + 1];
+    in.q_c = Q[k + 1]; in.q_w = Q[k]; in.qs_c = QS[k];
+    in.ke_c = KE[k]; in.ke_e = KE[k + 1]; in.ken_c = KEN[k];
+    in.h_c = H[k]; in.h_e = H[k + 1]; in.h_n = HN[k];
+    in.u_o = Uo[k]; in.v_o = Vo[k]; in.dh_o = DHo[k]; in.du_o = DUo[k]; in.dv_o = DVo[k];
+    const SweK2Out r = swe_k2_cell(p, in);
+    Un[k] = r.u; Vn[k] = r.v; Hn[k] = r.h; DH[k] = r.dh; DU[k] = r.du; DV[k] = r.dv;
+    if (!m[k]) { Un[k] = Uo[k]; Vn[k] = Vo[k]; Hn[k] = H[k]; DH[k] = DU[k] = DV[k] = 0.f; }
+    if (p.north_wall && j == p.ny - 2) Vn[k] = 0.f;
+    o.a[0][k] = Hn[k]; o.a[1][k] = Un[k]; o.a[2][k] = Vn[k];
+  }
+#else
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float fe_c = FE[k + 1], fe_w = FE[k], fn_c = FN[k], q_c = Q[k + 1];
@@ -199,6 +252,7 @@ __device__ __forceinline__ void swe_k2_body(const B2SweParams& p, const float* _
     if (p.north_wall && j == p.ny - 2) Vn[k] = 0.f;    // "v" wall rule, applied after the update
     o.a[0][k] = Hn[k]; o.a[1][k] = Un[k]; o.a[2][k] = Vn[k];
   }
+#endif
   st4(u, off, make_float4(Un[0], Un[1], Un[2], Un[3]));
   st4(v, off, make_float4(Vn[0], Vn[1], Vn[2], Vn[3]));
   st4(h_new, off, make_float4(Hn[0], Hn[1], Hn[2], Hn[3]));

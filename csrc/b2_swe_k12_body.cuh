@@ -24,41 +24,6 @@
 
 #include "b2_swe_body.cuh"
 
-struct SweK2In {
-  float fe_c, fe_w, fen_c, fen_w;      // fe[j][i], fe[j][i-1], fe[j+1][i], fe[j+1][i-1]
-  float fn_c, fn_e, fns_c, fns_e;      // fn[j][i], fn[j][i+1], fn[j-1][i], fn[j-1][i+1]
-  float q_c, q_w, qs_c;                // q[j][i], q[j][i-1], q[j-1][i]
-  float ke_c, ke_e, ken_c;             // ke[j][i], ke[j][i+1], ke[j+1][i]
-  float h_c, h_e, h_n;                 // h[j][i], h[j][i+1], h[j+1][i]
-  float u_o, v_o, dh_o, du_o, dv_o;    // own cell, old values
-};
-struct SweK2Out {
-  float h, u, v, dh, du, dv;
-};
-
-// The per-cell arithmetic of swe_k2_body (same expressions, same order).
-__device__ __forceinline__ SweK2Out swe_k2_cell(const B2SweParams& p, const SweK2In& x) {
-  const float dh_new = -(x.fe_c - x.fe_w) * p.rdx - (x.fn_c - x.fns_c) * p.rdy;
-  float du_new = -p.gravity * (x.h_e - x.h_c) * p.rdx +
-                 0.5f * (x.q_c * 0.5f * (x.fn_c + x.fn_e) + x.qs_c * 0.5f * (x.fns_c + x.fns_e));
-  float dv_new = -p.gravity * (x.h_n - x.h_c) * p.rdy -
-                 0.5f * (x.q_c * 0.5f * (x.fe_c + x.fen_c) + x.q_w * 0.5f * (x.fe_w + x.fen_w));
-  du_new += -(x.ke_e - x.ke_c) * p.rdx;
-  dv_new += -(x.ken_c - x.ke_c) * p.rdy;
-  SweK2Out o;
-  if (p.first_step) {
-    o.u = x.u_o + p.dt * du_new;
-    o.v = x.v_o + p.dt * dv_new;
-    o.h = x.h_c + p.dt * dh_new;
-  } else {
-    o.u = x.u_o + p.dt * (p.ab_a * du_new + p.ab_b * x.du_o);
-    o.v = x.v_o + p.dt * (p.ab_a * dv_new + p.ab_b * x.dv_o);
-    o.h = x.h_c + p.dt * (p.ab_a * dh_new + p.ab_b * x.dh_o);
-  }
-  o.dh = dh_new; o.du = du_new; o.dv = dv_new;
-  return o;
-}
-
 __device__ __forceinline__ bool swe_is_bulk(const B2SweParams& p, int j, int i) {
   return j >= 2 && j <= p.ny - 3 && i >= 2 && i <= p.nx - 3;
 }
