@@ -4,8 +4,8 @@ The reference is launched with ``mpirun -n N python script.py`` (README.rst:83-8
 test-suite with ``mpirun -np 2 pytest .`` (docs/developers.rst:18-27).  This image has no
 MPI launcher, and ``torchrun`` insists on a resolvable hostname, so this tiny launcher
 starts N local ranks with RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR (default 127.0.0.1) /
-MASTER_PORT set (``--nnodes / --node-rank / --master-addr / --master-port`` for several nodes), prefixes nothing, waits for all of them and propagates the first
-non-zero exit code (killing the remaining ranks -- exactly the processes it started).
+MASTER_PORT set (``--nnodes / --node-rank / --master-addr / --master-port`` for several nodes),
+prefixes nothing, waits for all of them and propagates the first non-zero exit code (killing the remaining ranks -- exactly the processes it started).
 
 ``-m module`` runs ``python -m module`` in every rank (``-m pytest tests/distributed``).
 """
