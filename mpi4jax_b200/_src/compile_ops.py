@@ -82,6 +82,19 @@ def _(x, comm_id, size):
     return x.new_empty((size, *x.shape))
 
 
+def _allgather_setup(ctx, inputs, output):
+    _, ctx.comm_id, _ = inputs
+
+
+def _allgather_backward(ctx, g):
+    # adjoint of allgather = reduce-scatter of the cotangent (here: allreduce + own slice)
+    total = torch.ops.mpi4jax_b200.allreduce(g.contiguous(), SUM.code, ctx.comm_id)
+    return total[_c(ctx.comm_id).Get_rank()], None, None
+
+
+_allgather.register_autograd(_allgather_backward, setup_context=_allgather_setup)
+
+
 @custom_op("mpi4jax_b200::alltoall", mutates_args=())
 def _alltoall(x: torch.Tensor, comm_id: int) -> torch.Tensor:
     return _dispatch.alltoall(_c(comm_id), x.contiguous())
@@ -90,6 +103,17 @@ def _alltoall(x: torch.Tensor, comm_id: int) -> torch.Tensor:
 @_alltoall.register_fake
 def _(x, comm_id):
     return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+def _alltoall_setup(ctx, inputs, output):
+    _, ctx.comm_id = inputs
+
+
+def _alltoall_backward(ctx, g):
+    return torch.ops.mpi4jax_b200.alltoall(g.contiguous(), ctx.comm_id), None      # self-adjoint up to the swap
+
+
+_alltoall.register_autograd(_alltoall_backward, setup_context=_alltoall_setup)
 
 
 @custom_op("mpi4jax_b200::bcast", mutates_args=())
@@ -101,6 +125,21 @@ def _bcast(x: torch.Tensor, root: int, comm_id: int) -> torch.Tensor:
 @_bcast.register_fake
 def _(x, root, comm_id):
     return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+def _bcast_setup(ctx, inputs, output):
+    _, ctx.root, ctx.comm_id = inputs
+
+
+def _bcast_backward(ctx, g):
+    # adjoint of bcast = sum of the cotangents on the root, nothing elsewhere
+    total = torch.ops.mpi4jax_b200.reduce(g.contiguous(), SUM.code, ctx.root, ctx.comm_id)
+    if _c(ctx.comm_id).Get_rank() == ctx.root:
+        return total, None, None
+    return torch.zeros_like(g), None, None
+
+
+_bcast.register_autograd(_bcast_backward, setup_context=_bcast_setup)
 
 
 @custom_op("mpi4jax_b200::scan", mutates_args=())
@@ -198,6 +237,24 @@ def _(sendbuf, recvbuf, source, dest, sendtag, recvtag, comm_id):
     return torch.empty_like(recvbuf, memory_format=torch.contiguous_format)
 
 
+def _sendrecv_setup(ctx, inputs, output):
+    sendbuf, _, ctx.source, ctx.dest, ctx.sendtag, ctx.recvtag, ctx.comm_id = inputs
+    ctx.send_meta = (tuple(sendbuf.shape), sendbuf.dtype, sendbuf.device)
+
+
+def _sendrecv_backward(ctx, g):
+    # transpose: the cotangent of what was received travels back to where it came from
+    # (the reference swaps source and dest the same way, sendrecv.py:277-292)
+    shape, dtype, device = ctx.send_meta
+    template = torch.empty(shape, dtype=dtype, device=device)
+    back = torch.ops.mpi4jax_b200.sendrecv(g.contiguous(), template, ctx.dest, ctx.source,
+                                           max(ctx.recvtag, 0), ctx.sendtag, ctx.comm_id)
+    return back, None, None, None, None, None, None
+
+
+_sendrecv.register_autograd(_sendrecv_backward, setup_context=_sendrecv_setup)
+
+
 ALL_OPS = ("allreduce", "allgather", "alltoall", "bcast", "scan", "reduce", "gather_root", "gather_leaf",
            "scatter", "barrier", "send", "recv", "sendrecv")
 ORDERED_EFFECT = False
@@ -221,8 +278,8 @@ class compiled:
 
     @staticmethod
     def allgather(x, *, comm=None):
-        cid = _register(comm)
-        return torch.ops.mpi4jax_b200.allgather(x, cid, _c(cid).Get_size())
+        comm = comm or get_default_comm()     # plain attribute reads only: this code is traced by Dynamo
+        return torch.ops.mpi4jax_b200.allgather(x, comm._id, comm.Get_size())
 
     @staticmethod
     def alltoall(x, *, comm=None):
@@ -242,16 +299,15 @@ class compiled:
 
     @staticmethod
     def gather(x, root, *, comm=None):
-        cid = _register(comm)
-        c = _c(cid)
-        if c.Get_rank() == root:
-            return torch.ops.mpi4jax_b200.gather_root(x, int(root), cid, c.Get_size())
-        return torch.ops.mpi4jax_b200.gather_leaf(x, int(root), cid)
+        comm = comm or get_default_comm()
+        if comm.Get_rank() == root:
+            return torch.ops.mpi4jax_b200.gather_root(x, int(root), comm._id, comm.Get_size())
+        return torch.ops.mpi4jax_b200.gather_leaf(x, int(root), comm._id)
 
     @staticmethod
     def scatter(x, root, *, comm=None):
-        cid = _register(comm)
-        return torch.ops.mpi4jax_b200.scatter(x, int(root), cid, _c(cid).Get_rank() == root)
+        comm = comm or get_default_comm()
+        return torch.ops.mpi4jax_b200.scatter(x, int(root), comm._id, comm.Get_rank() == root)
 
     @staticmethod
     def barrier(*, comm=None):

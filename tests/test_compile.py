@@ -2,6 +2,8 @@
 torch counterpart of the reference's JAX primitives + ordered effect token
 (/root/reference/mpi4jax/_src/utils.py:45-53; acceptance test = test_send_recv_deadlock)."""
 
+import os
+
 import pytest
 import torch
 
@@ -90,3 +92,47 @@ def test_torch_export_keeps_all_ops(device):
         assert any(f"mpi4jax_b200.{name}" in t for t in targets), targets
     out = ep.module()(torch.ones(3, device=device))
     assert torch.equal(out, torch.full((size, 3), 2.0 * size, device=device))
+
+
+def test_compiled_gradients_match_eager_rules(device):
+    """allgather / alltoall / bcast / sendrecv are differentiable in the traced frontend too, with
+    the same adjoints as the eager ops."""
+    if device.type == "cuda" and not os.environ.get("MPI4JAX_B200_TEST_EXPERIMENTAL"):
+        pytest.skip("added after the round's last GPU run: CUDA variant waits for MPI4JAX_B200_TEST_EXPERIMENTAL=1")
+    x = torch.arange(size * 3, dtype=torch.float32, device=device).reshape(size, 3) + rank
+
+    def via(ns, t):
+        a = ns.allgather(t[0], comm=comm)                       # (size, 3)
+        b = ns.alltoall(t * 2, comm=comm)                       # (size, 3)
+        c = ns.bcast(t[0] * 3, 0, comm=comm)                    # (3,)
+        d = ns.sendrecv(t[0] * 5, t[0], (rank - 1) % size, (rank + 1) % size, comm=comm)
+        w = torch.arange(1, 4, dtype=torch.float32, device=t.device)
+        return (a * w).sum() + (b * b).sum() + (c * w).sum() + (d * w).sum()
+
+    xe = x.clone().requires_grad_(True)
+    via(m, xe).backward()
+    xc = x.clone().requires_grad_(True)
+    f = torch.compile(lambda t: via(mc, t), backend="aot_eager", fullgraph=True)
+    f(xc).backward()
+    assert torch.allclose(xc.grad, xe.grad)
+    m.flush()
+
+
+def test_compiled_gather_scatter_allgather_shapes_under_compile(device):
+    """Rank-dependent static arguments (root / is_root, communicator size) are resolved while
+    tracing; no registry lookups inside the traced frame."""
+    if device.type == "cuda" and not os.environ.get("MPI4JAX_B200_TEST_EXPERIMENTAL"):
+        pytest.skip("added after the round's last GPU run: CUDA variant waits for MPI4JAX_B200_TEST_EXPERIMENTAL=1")
+
+    def f(t):
+        g = mc.gather(t, 0, comm=comm)
+        a = mc.allgather(t, comm=comm)
+        s = mc.scatter(a if rank == 0 else t, 0, comm=comm)
+        return g, a, s
+
+    t = torch.arange(4, dtype=torch.float32, device=device) + 10 * rank
+    g, a, s = torch.compile(f, backend="aot_eager", fullgraph=True)(t)
+    assert a.shape == (size, 4) and torch.equal(a[rank], t)
+    assert (g.shape == (size, 4)) if rank == 0 else torch.equal(g, t)
+    assert torch.equal(s, torch.arange(4, dtype=torch.float32, device=device) + 10 * rank)
+    m.flush()
