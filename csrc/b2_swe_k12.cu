@@ -72,6 +72,41 @@ swe_k5_pp(B2SweParams p, const float* __restrict__ v, float* __restrict__ v_new,
   swe_k5_pp_body(p, v, v_new, fe2, fn2, j, i0, m);
 }
 
+__global__ void __launch_bounds__(SWE_THREADS, 2)
+swe_k345_bulk(B2SweParams p, const float* __restrict__ u, float* __restrict__ u_new,
+              const float* __restrict__ v, float* __restrict__ v_new, int has_south) {
+  b2_pdl_enter();
+  int j, i0;
+  bool m[4];
+  if (!swe_map(p, j, i0, m)) return;
+  if (j < 2 || j > p.ny - 3) return;
+  swe_k345_body(p, u, u_new, v, v_new, j, i0, has_south != 0);
+}
+
+__global__ void __launch_bounds__(SWE_THREADS)
+swe_k34_frame(B2SweParams p, SweFrame f, const float* __restrict__ u, float* __restrict__ u_new,
+              const float* __restrict__ v, float* __restrict__ fe2, float* __restrict__ fn2,
+              int has_south) {
+  b2_pdl_enter();
+  int j, i0;
+  bool m[4];
+  if (!swe_frame_task(p, f, (long long)blockIdx.x * SWE_THREADS + threadIdx.x, j, i0, m)) return;
+  if (!(m[0] || m[1] || m[2] || m[3])) return;
+  SweOut4 o;
+  swe_k34_body(p, u, u_new, v, fe2, fn2, j, i0, m, has_south != 0, o);
+}
+
+__global__ void __launch_bounds__(SWE_THREADS)
+swe_k5_ring(B2SweParams p, SweFrame f, const float* __restrict__ v, float* __restrict__ v_new,
+            const float* __restrict__ fe2, const float* __restrict__ fn2) {
+  b2_pdl_enter();
+  int j, i0;
+  bool m[4];
+  if (!swe_frame_task(p, f, (long long)blockIdx.x * SWE_THREADS + threadIdx.x, j, i0, m)) return;
+  if (!(m[0] || m[1] || m[2] || m[3])) return;
+  swe_k5_ring_body(p, v, v_new, fe2, fn2, j, i0, m);
+}
+
 static int k12_done(B2Comm* c, const char* name) {
   b2_count_launch(c);
   cudaError_t err = cudaGetLastError();
@@ -86,8 +121,10 @@ static unsigned blocks_for(long long tasks) {
   return (unsigned)((tasks + SWE_THREADS - 1) / SWE_THREADS);
 }
 
-extern "C" int b2_swe_multistep_k12(B2Comm* c, const B2SweParams* p0, const B2SweState* st,
-                                    const B2HaloDesc* topo, int nsteps, int first_step, cudaStream_t s) {
+// fuse_friction != 0: the friction phase is fused as well (bulk kernel + K34 on the frame ->
+// exchange -> K5 on the ring): 16 instead of 21 array passes.
+static int multistep_k12(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const B2HaloDesc* topo,
+                         int nsteps, int first_step, int fuse_friction, cudaStream_t s) {
   // blocks too small for the bulk / frame split, or no friction step to bring u, v back to their
   // home buffers: the stand-alone path
   if (!swe_k12_supported(*p0) || !(p0->viscosity > 0.f) || !st->u1 || !st->v1)
@@ -131,13 +168,27 @@ extern "C" int b2_swe_multistep_k12(B2Comm* c, const B2SweParams* p0, const B2Sw
     d.field[1] = ub; d.kind[1] = 1;
     d.field[2] = vb; d.kind[2] = 2;
     if ((rc = b2_halo_exchange(c, &d, s))) break;
-    if ((rc = b2_swe_friction_u_fused(c, &p, ub, ua, vb, st->fe2, st->fn2, topo->south >= 0, s))) break;
+    const int has_south = topo->south >= 0;
+    if (fuse_friction) {
+      b2_launch(swe_k345_bulk, all_blocks, SWE_THREADS, 0, s, p, ub, ua, vb, va, has_south);
+      if ((rc = k12_done(c, "swe_k345_bulk"))) break;
+      b2_launch(swe_k34_frame, blocks_for(f2.total), SWE_THREADS, 0, s, p, f2, ub, ua, vb, st->fe2, st->fn2,
+                has_south);
+      if ((rc = k12_done(c, "swe_k34_frame"))) break;
+    } else {
+      if ((rc = b2_swe_friction_u_fused(c, &p, ub, ua, vb, st->fe2, st->fn2, has_south, s))) break;
+    }
     d.nfields = 2;
     d.field[0] = st->fe2; d.kind[0] = 1;
     d.field[1] = st->fn2; d.kind[1] = 2;
     if ((rc = b2_halo_exchange(c, &d, s))) break;
-    b2_launch(swe_k5_pp, all_blocks, SWE_THREADS, 0, s, p, vb, va, st->fe2, st->fn2);
-    if ((rc = k12_done(c, "swe_k5_pp"))) break;
+    if (fuse_friction) {
+      b2_launch(swe_k5_ring, blocks_for(f1.total), SWE_THREADS, 0, s, p, f1, vb, va, st->fe2, st->fn2);
+      if ((rc = k12_done(c, "swe_k5_ring"))) break;
+    } else {
+      b2_launch(swe_k5_pp, all_blocks, SWE_THREADS, 0, s, p, vb, va, st->fe2, st->fn2);
+      if ((rc = k12_done(c, "swe_k5_pp"))) break;
+    }
     float* t = h; h = hn; hn = t;
   }
   if (rc == 0 && h != st->h0) {
@@ -149,4 +200,14 @@ extern "C" int b2_swe_multistep_k12(B2Comm* c, const B2SweParams* p0, const B2Sw
     }
   }
   return rc;
+}
+
+extern "C" int b2_swe_multistep_k12(B2Comm* c, const B2SweParams* p0, const B2SweState* st,
+                                    const B2HaloDesc* topo, int nsteps, int first_step, cudaStream_t s) {
+  return multistep_k12(c, p0, st, topo, nsteps, first_step, 0, s);
+}
+
+extern "C" int b2_swe_multistep_k12f(B2Comm* c, const B2SweParams* p0, const B2SweState* st,
+                                     const B2HaloDesc* topo, int nsteps, int first_step, cudaStream_t s) {
+  return multistep_k12(c, p0, st, topo, nsteps, first_step, 1, s);
 }

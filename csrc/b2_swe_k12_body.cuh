@@ -219,6 +219,103 @@ __device__ __forceinline__ void swe_k5_pp_body(const B2SweParams& p, const float
   }
 }
 
+// ---- friction phase fused (u' -> u and v' -> v in one kernel), bulk cells only ----------------
+// The stand-alone friction phase is K34 (u' -> u, writes the friction-v fluxes fe2, fn2),
+// exchange(fe2, fn2), K5 (v' -> v): 9 array passes.  A bulk cell's K5 needs fe2 / fn2 only at its
+// own, its west and its south neighbour, all interior, so they can be recomputed from u_new at
+// those three cells (three evaluations of u's 5-point friction stencil instead of one): 4 passes.
+// The frame keeps K34 (on a frame of width 2, which also supplies fe2 / fn2 next to the ring)
+// -> exchange -> K5 on the ring.
+
+// the friction update of u at one cell: the expressions of swe_k34_body
+__device__ __forceinline__ float swe_friction_u(const B2SweParams& p, float u_c, float u_e, float u_w,
+                                                float u_n, float u_s, bool fn_c_zero, bool fn_s_zero) {
+  const float fe_c = p.viscosity * (u_e - u_c) * p.rdx;
+  const float fe_w = p.viscosity * (u_c - u_w) * p.rdx;
+  const float fn_c = fn_c_zero ? 0.f : p.viscosity * (u_n - u_c) * p.rdy;
+  const float fn_s = fn_s_zero ? 0.f : p.viscosity * (u_c - u_s) * p.rdy;
+  return u_c + p.dt * ((fe_c - fe_w) * p.rdx + (fn_c - fn_s) * p.rdy);
+}
+
+// one aligned group of row j (2 <= j <= ny-3); non-bulk lanes are written as copies of u', v'
+__device__ __forceinline__ void swe_k345_body(const B2SweParams& p, const float* __restrict__ u,
+                                              float* __restrict__ u_new, const float* __restrict__ v,
+                                              float* __restrict__ v_new, int j, int i0, bool has_south) {
+  const int P = p.pitch;
+  const size_t off = (size_t)j * P + i0;
+  // U*[d + 2] <-> column i0 + d, d = -2 .. 4
+  float Uc[7], Um[7], Up[7], Umm[7], Vc[7], Vp[7];
+  {
+    const Row6 r = ld_row<true, true>(u, j, i0, P);
+    Uc[0] = i0 >= 2 ? u[off - 2] : 0.f;
+    Uc[1] = r.w; Uc[2] = r.c0; Uc[3] = r.c1; Uc[4] = r.c2; Uc[5] = r.c3; Uc[6] = r.e;
+    const Row6 m1 = ld_row<true, true>(u, j - 1, i0, P);
+    Um[0] = 0.f; Um[1] = m1.w; Um[2] = m1.c0; Um[3] = m1.c1; Um[4] = m1.c2; Um[5] = m1.c3; Um[6] = m1.e;
+    const Row6 p1 = ld_row<true, false>(u, j + 1, i0, P);
+    Up[0] = 0.f; Up[1] = p1.w; Up[2] = p1.c0; Up[3] = p1.c1; Up[4] = p1.c2; Up[5] = p1.c3; Up[6] = 0.f;
+    const float4 m2 = ld4(u, off - 2 * (size_t)P);
+    Umm[0] = Umm[1] = 0.f; Umm[2] = m2.x; Umm[3] = m2.y; Umm[4] = m2.z; Umm[5] = m2.w; Umm[6] = 0.f;
+    const Row6 vc = ld_row<false, true>(v, j, i0, P);
+    Vc[0] = Vc[1] = 0.f; Vc[2] = vc.c0; Vc[3] = vc.c1; Vc[4] = vc.c2; Vc[5] = vc.c3; Vc[6] = vc.e;
+    const float4 vp = ld4(v, off + P);
+    Vp[0] = Vp[1] = 0.f; Vp[2] = vp.x; Vp[3] = vp.y; Vp[4] = vp.z; Vp[5] = vp.w; Vp[6] = 0.f;
+  }
+  const bool fnc0_j = p.north_wall && j == p.ny - 2, fnc0_m = p.north_wall && (j - 1) == p.ny - 2;
+  const bool fns0_j = (j == 1) && !has_south, fns0_m = (j - 1 == 1) && !has_south;
+  float UNj[5], UNm[4], FE2[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {                 // u_new[j][i0 + t - 1]
+    const int x = t + 1;
+    UNj[t] = swe_friction_u(p, Uc[x], Uc[x + 1], Uc[x - 1], Up[x], Um[x], fnc0_j, fns0_j);
+    FE2[t] = p.viscosity * (Vc[x + 1] - UNj[t]) * p.rdx;            // fe2[j][i0 + t - 1]
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {                 // u_new[j-1][i0 + t]
+    const int x = t + 2;
+    UNm[t] = swe_friction_u(p, Um[x], Um[x + 1], Um[x - 1], Uc[x], Umm[x], fnc0_m, fns0_m);
+  }
+  float Un[4], Vn[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float fn2_c = p.viscosity * (Vp[k + 2] - UNj[k + 1]) * p.rdy;       // fn2[j][i]
+    const float fn2_s = p.viscosity * (Vc[k + 2] - UNm[k]) * p.rdy;           // fn2[j-1][i]
+    const float vn = Vc[k + 2] + p.dt * ((FE2[k + 1] - FE2[k]) * p.rdx + (fn2_c - fn2_s) * p.rdy);
+    const bool bulk = swe_is_bulk(p, j, i0 + k);
+    Un[k] = bulk ? UNj[k + 1] : Uc[k + 2];
+    Vn[k] = bulk ? vn : Vc[k + 2];
+  }
+  st4(u_new, off, make_float4(Un[0], Un[1], Un[2], Un[3]));
+  st4(v_new, off, make_float4(Vn[0], Vn[1], Vn[2], Vn[3]));
+}
+
+// K5 on the ring cells of one group: ring lanes get the friction-v update from the exchanged
+// fe2 / fn2, halo / pad lanes copies of v', bulk lanes stay as swe_k345_body left them; rows 1 and
+// ny-2 carry v's halo rows over.
+__device__ __forceinline__ void swe_k5_ring_body(const B2SweParams& p, const float* __restrict__ v,
+                                                 float* __restrict__ v_new, const float* __restrict__ fe2,
+                                                 const float* __restrict__ fn2, int j, int i0,
+                                                 const bool m[4]) {
+  const int P = p.pitch;
+  const size_t off = (size_t)j * P + i0;
+  const Row6 fec = ld_row<true, false>(fe2, j, i0, P);
+  const float4 fnc = ld4(fn2, off), fns = ld4(fn2, off - P), v4 = ld4(v, off), vb4 = ld4(v_new, off);
+  const float FE[5] = {fec.w, fec.c0, fec.c1, fec.c2, fec.c3};
+  const float FN[4] = {fnc.x, fnc.y, fnc.z, fnc.w}, FNS[4] = {fns.x, fns.y, fns.z, fns.w};
+  const float Vo[4] = {v4.x, v4.y, v4.z, v4.w}, Vb[4] = {vb4.x, vb4.y, vb4.z, vb4.w};
+  float Vn[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float vn = Vo[k] + p.dt * ((FE[k + 1] - FE[k]) * p.rdx + (FN[k] - FNS[k]) * p.rdy);
+    Vn[k] = swe_is_ring(p, j, i0 + k) ? vn : (m[k] ? Vb[k] : Vo[k]);
+  }
+  st4(v_new, off, make_float4(Vn[0], Vn[1], Vn[2], Vn[3]));
+  if (j == 1) st4(v_new, (size_t)i0, ld4(v, (size_t)i0));
+  if (j == p.ny - 2) {
+    const size_t o2 = (size_t)(p.ny - 1) * P + i0;
+    st4(v_new, o2, ld4(v, o2));
+  }
+}
+
 // ---- frame enumeration --------------------------------------------------------------------
 // The frame of width w: rows [1, w] and [ny-1-w, ny-2] completely; of the rows in between, the
 // groups that contain the columns [1, w] (group 0 for w <= 2) or [nx-1-w, nx-2].

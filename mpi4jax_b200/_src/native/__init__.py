@@ -178,6 +178,10 @@ _SIGNATURES = {
         c_int,
         [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2HaloDesc), c_int, c_int, c_void_p],
     ),
+    "b2_swe_multistep_k12f": (
+        c_int,
+        [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2HaloDesc), c_int, c_int, c_void_p],
+    ),
     "b2_swe_multistep_k12": (
         c_int,
         [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2HaloDesc), c_int, c_int, c_void_p],
@@ -190,7 +194,7 @@ _SIGNATURES = {
 
 
 #: must equal B2_ABI_VERSION in csrc/b2_common.h
-ABI_VERSION = 5
+ABI_VERSION = 6
 _ABI_FIELDS = ("abi_version", "sizeof_status_record", "sizeof_halo_desc", "sizeof_swe_params",
                "sizeof_swe_state", "sizeof_error_record", "max_ranks", "p2p_nslot")
 

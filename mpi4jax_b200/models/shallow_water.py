@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from collections import namedtuple
 from dataclasses import dataclass
 from typing import Optional
@@ -90,7 +91,11 @@ class ShallowWaterModel:
         # k12=True: flux and tendency kernels fused, 21 instead of 32 array passes per step
         # (csrc/b2_swe_k12.cu).  EXPERIMENTAL: written and host-emulated (tests/
         # test_swe_host_emulation.py) but not yet measured on hardware; opt-in only.
-        self.k12 = env_flag("MPI4JAX_B200_SWE_K12", False) if k12 is None else bool(k12)
+        # k12=2 / "full" additionally fuses the friction phase (16 passes).
+        if k12 is None:
+            raw = os.environ.get("MPI4JAX_B200_SWE_K12", "0").strip().lower()
+            k12 = 2 if raw in ("2", "full") else 1 if raw in ("1", "true", "on") else 0
+        self.k12 = 2 if k12 in (2, "full") else int(bool(k12))
         # fused=True: halo exchange fused into the stencil kernels (csrc/b2_swe_fused.cu);
         # default is the stand-alone exchange kernel, which currently measures faster (profiles/)
         self.fused = env_flag("MPI4JAX_B200_SWE_FUSED", False) if fused is None else bool(fused)
@@ -291,6 +296,7 @@ class ShallowWaterModel:
         if self.backend == "native":
             nc = self.comm._native_comm()
             fn = (native.lib.b2_swe_multistep_fused if self.fused else
+                  native.lib.b2_swe_multistep_k12f if self.k12 == 2 else
                   native.lib.b2_swe_multistep_k12 if self.k12 else native.lib.b2_swe_multistep)
             rc = fn(
                 nc.handle, ctypes.byref(self._params), ctypes.byref(self._state),

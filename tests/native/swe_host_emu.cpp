@@ -140,6 +140,42 @@ void emu_k3_k4(const B2SweParams* p, float* u, const float* v, float* fe, float*
     }
 }
 
+// friction phase of the fused pipeline: bulk kernel, K34 on the frame (width 2), K5 on the ring
+void emu_k345_bulk(const B2SweParams* p, const float* u, float* u_new, const float* v, float* v_new,
+                   int has_south) {
+  for (int j = 2; j <= p->ny - 3; ++j)
+    for (int i0 = 0; i0 < p->pitch; i0 += 4) {
+      bool m[4];
+      masks(*p, i0, m);
+      if (!(m[0] || m[1] || m[2] || m[3])) continue;
+      swe_k345_body(*p, u, u_new, v, v_new, j, i0, has_south != 0);
+    }
+}
+
+void emu_k34_frame(const B2SweParams* p, const float* u, float* u_new, const float* v, float* fe2,
+                   float* fn2, int has_south) {
+  const SweFrame f = swe_frame(*p, 2);
+  for (long long t = 0; t < f.total; ++t) {
+    int j, i0;
+    bool m[4];
+    if (!swe_frame_task(*p, f, t, j, i0, m)) continue;
+    if (!(m[0] || m[1] || m[2] || m[3])) continue;
+    SweOut4 o;
+    swe_k34_body(*p, u, u_new, v, fe2, fn2, j, i0, m, has_south != 0, o);
+  }
+}
+
+void emu_k5_ring(const B2SweParams* p, const float* v, float* v_new, const float* fe2, const float* fn2) {
+  const SweFrame f = swe_frame(*p, 1);
+  for (long long t = 0; t < f.total; ++t) {
+    int j, i0;
+    bool m[4];
+    if (!swe_frame_task(*p, f, t, j, i0, m)) continue;
+    if (!(m[0] || m[1] || m[2] || m[3])) continue;
+    swe_k5_ring_body(*p, v, v_new, fe2, fn2, j, i0, m);
+  }
+}
+
 int emu_k12_supported(const B2SweParams* p) { return swe_k12_supported(*p) ? 1 : 0; }
 
 // which (row, group) tasks does a frame of width w enumerate?  marks[j * ngroups + g] += 1

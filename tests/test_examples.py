@@ -112,7 +112,8 @@ def test_native_step_is_bitwise_reproducible(pdl):
 @pytest.mark.skipif(not os.environ.get("MPI4JAX_B200_TEST_EXPERIMENTAL"),
                     reason="experimental kernel path, not yet validated on hardware: "
                            "set MPI4JAX_B200_TEST_EXPERIMENTAL=1 to run")
-def test_k12_path_matches_standalone_path():
+@pytest.mark.parametrize("k12", [1, 2], ids=["k12", "k12+friction"])
+def test_k12_path_matches_standalone_path(k12):
     """Fused flux+tendency kernels (csrc/b2_swe_k12.cu) vs the stand-alone kernels: same discrete
     system, agreement to rounding; the fused path itself is bitwise reproducible."""
     if not torch.cuda.is_available():
@@ -120,8 +121,8 @@ def test_k12_path_matches_standalone_path():
     size = comm.Get_size()
     cfg = ShallowWaterConfig.for_resolution(256 * max(1, size // 2), 192)
     runs = {}
-    for name, k12 in (("k12", True), ("k12_again", True), ("standalone", False)):
-        model = ShallowWaterModel(cfg, comm=comm, device=comm.device, backend="native", k12=k12)
+    for name, mode in (("k12", k12), ("k12_again", k12), ("standalone", 0)):
+        model = ShallowWaterModel(cfg, comm=comm, device=comm.device, backend="native", k12=mode)
         model.multistep(9)
         m.flush()
         runs[name] = [t.clone() for t in model.state]

@@ -265,12 +265,22 @@ def _emulate(emu, model, PY, PX, nsteps, k12):
                                 _ptr(r["v1"]), _ptr(r["dh"]), _ptr(r["du"]), _ptr(r["dv"]), _ptr(r["fe"]),
                                 _ptr(r["fn"]), _ptr(r["q"]), _ptr(r["ke"]))
             _exchange(ranks, (hnk, "u1", "v1"), ("h", "u", "v"), nx, PY, PX)
-            for i, (r, p) in enumerate(zip(ranks, ps)):
-                emu.emu_k34(B(p), _ptr(r["u1"]), _ptr(r["u"]), _ptr(r["v1"]), _ptr(r["fe2"]), _ptr(r["fn2"]),
-                            int(i // PX > 0))
-            _exchange(ranks, ("fe2", "fn2"), ("u", "v"), nx, PY, PX)
-            for r, p in zip(ranks, ps):
-                emu.emu_k5_pp(B(p), _ptr(r["v1"]), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]))
+            if k12 == 2:      # friction phase fused as well: bulk kernel + K34 frame -> exchange -> K5 ring
+                for i, (r, p) in enumerate(zip(ranks, ps)):
+                    hs = int(i // PX > 0)
+                    emu.emu_k345_bulk(B(p), _ptr(r["u1"]), _ptr(r["u"]), _ptr(r["v1"]), _ptr(r["v"]), hs)
+                    emu.emu_k34_frame(B(p), _ptr(r["u1"]), _ptr(r["u"]), _ptr(r["v1"]), _ptr(r["fe2"]),
+                                      _ptr(r["fn2"]), hs)
+                _exchange(ranks, ("fe2", "fn2"), ("u", "v"), nx, PY, PX)
+                for r, p in zip(ranks, ps):
+                    emu.emu_k5_ring(B(p), _ptr(r["v1"]), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]))
+            else:
+                for i, (r, p) in enumerate(zip(ranks, ps)):
+                    emu.emu_k34(B(p), _ptr(r["u1"]), _ptr(r["u"]), _ptr(r["v1"]), _ptr(r["fe2"]),
+                                _ptr(r["fn2"]), int(i // PX > 0))
+                _exchange(ranks, ("fe2", "fn2"), ("u", "v"), nx, PY, PX)
+                for r, p in zip(ranks, ps):
+                    emu.emu_k5_pp(B(p), _ptr(r["v1"]), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]))
         else:
             for r, p in zip(ranks, ps):
                 emu.emu_k1_all(B(p), _ptr(r[hk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["fe"]), _ptr(r["fn"]),
@@ -348,9 +358,28 @@ def test_explicit_rounding_build_makes_both_pipelines_bit_identical(emu, emu_exp
     model = ShallowWaterModel(ShallowWaterConfig(nx=48 * PX, ny=24 * PY), device="cpu", backend="ops")
     a = _emulate(emu_explicit, model, PY, PX, 6, k12=False)
     b = _emulate(emu_explicit, model, PY, PX, 6, k12=True)
+    c = _emulate(emu_explicit, model, PY, PX, 6, k12=2)
     plain = _emulate(emu, model, PY, PX, 6, k12=False)
-    for ra, rb, rp in zip(a, b, plain):
+    for ra, rb, rc, rp in zip(a, b, c, plain):
         for name in ra:
             assert np.array_equal(ra[name][1:-1, 1:-1], rb[name][1:-1, 1:-1]), (grid, name)
+            assert np.array_equal(ra[name][1:-1, 1:-1], rc[name][1:-1, 1:-1]), (grid, name, "fused friction")
             tol = 5e-5 if name in ("h", "u", "v") else 1e-3      # per-rank normalisation: v is tiny off the jet
             assert _close(ra[name][1:-1, 1:-1], rp[name][1:-1, 1:-1], tol), (grid, name)
+
+
+@pytest.mark.parametrize("grid", [(1, 1), (1, 2), (2, 2), (3, 2)])
+def test_emulated_fully_fused_pipeline_matches_standalone_pipeline(emu, grid):
+    """K12 plus the fused friction phase (bulk: u' -> u and v' -> v in one kernel; frame: K34 ->
+    exchange -> K5): 16 instead of 32 array passes per step, same numbers."""
+    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
+
+    PY, PX = grid
+    model = ShallowWaterModel(ShallowWaterConfig(nx=48 * PX, ny=24 * PY), device="cpu", backend="ops")
+    a = _emulate(emu, model, PY, PX, 6, k12=False)
+    b = _emulate(emu, model, PY, PX, 6, k12=2)
+    for ra, rb in zip(a, b):
+        for name in ra:
+            assert np.isfinite(rb[name]).all(), name
+            tol = 5e-5 if name in ("h", "u", "v") else 1e-3
+            assert _close(rb[name][1:-1, 1:-1], ra[name][1:-1, 1:-1], tol), (grid, name)
