@@ -325,6 +325,27 @@ __device__ __forceinline__ void swe_k4_body(const B2SweParams& p, float* __restr
   st4(fn2, off, make_float4(FN2[0], FN2[1], FN2[2], FN2[3]));
 }
 
+// ---- friction phase helpers, every rounding spelled out (no FMA anywhere: on a host build they
+// equal the plain expressions of swe_k34_body / swe_k5_body bit for bit) ---------------------------
+__device__ __forceinline__ float swe_visc_flux(float nu, float a, float b, float rd) {   // nu (a - b) / d
+  return __fmul_rn(__fmul_rn(nu, __fadd_rn(a, -b)), rd);
+}
+// x + dt ((fe_c - fe_w) / dx + (fn_c - fn_s) / dy)
+__device__ __forceinline__ float swe_apply_div(const B2SweParams& p, float x, float fe_c, float fe_w,
+                                               float fn_c, float fn_s) {
+  return __fadd_rn(x, __fmul_rn(p.dt, __fadd_rn(__fmul_rn(__fadd_rn(fe_c, -fe_w), p.rdx),
+                                                  __fmul_rn(__fadd_rn(fn_c, -fn_s), p.rdy))));
+}
+// the friction update of u at one cell (5-point stencil), with the reference's boundary rules
+__device__ __forceinline__ float swe_friction_u(const B2SweParams& p, float u_c, float u_e, float u_w,
+                                                float u_n, float u_s, bool fn_c_zero, bool fn_s_zero) {
+  const float fe_c = swe_visc_flux(p.viscosity, u_e, u_c, p.rdx);
+  const float fe_w = swe_visc_flux(p.viscosity, u_c, u_w, p.rdx);
+  const float fn_c = fn_c_zero ? 0.f : swe_visc_flux(p.viscosity, u_n, u_c, p.rdy);
+  const float fn_s = fn_s_zero ? 0.f : swe_visc_flux(p.viscosity, u_c, u_s, p.rdy);
+  return swe_apply_div(p, u_c, fe_c, fe_w, fn_c, fn_s);
+}
+
 // K3+K4 in one pass: the friction-u fluxes are re-evaluated from u's 5-point stencil instead of
 // being written to and re-read from HBM (saves one launch and 5 of 37 array passes per step).
 //   fe[c]    = nu (u[c+1] - u[c]) / dx      fe[c-1]  = nu (u[c] - u[c-1]) / dx
@@ -358,6 +379,12 @@ __device__ __forceinline__ void swe_k34_body(const B2SweParams& p, const float* 
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float uk = U[k + 1];
+#if B2_SWE_EXPLICIT_ROUNDING
+    const float un = swe_friction_u(p, uk, U[k + 2], U[k], UN[k], US[k], fn_c_zero, fn_s_zero);
+    Un[k] = m[k] ? un : uk;
+    FE2[k] = m[k] ? swe_visc_flux(p.viscosity, V[k + 1], un, p.rdx) : 0.f;
+    FN2[k] = m[k] ? swe_visc_flux(p.viscosity, VN[k], un, p.rdy) : 0.f;
+#else
     const float fe_c = p.viscosity * (U[k + 2] - uk) * p.rdx;
     const float fe_w = p.viscosity * (uk - U[k]) * p.rdx;
     const float fn_c = fn_c_zero ? 0.f : p.viscosity * (UN[k] - uk) * p.rdy;
@@ -367,6 +394,7 @@ __device__ __forceinline__ void swe_k34_body(const B2SweParams& p, const float* 
     // NOTE: `v - u` mirrors the reference (examples/shallow_water.py:387-392)
     FE2[k] = m[k] ? p.viscosity * (V[k + 1] - un) * p.rdx : 0.f;
     FN2[k] = m[k] ? p.viscosity * (VN[k] - un) * p.rdy : 0.f;
+#endif
     if (p.north_wall && j == p.ny - 2) FN2[k] = 0.f;
     o.a[0][k] = FE2[k]; o.a[1][k] = FN2[k];
   }
@@ -391,7 +419,11 @@ __device__ __forceinline__ void swe_k5_body(const B2SweParams& p, float* __restr
   float Vn[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+#if B2_SWE_EXPLICIT_ROUNDING
+    const float vn = swe_apply_div(p, Vo[k], FE[k + 1], FE[k], FN[k], FNS[k]);
+#else
     const float vn = Vo[k] + p.dt * ((FE[k + 1] - FE[k]) * p.rdx + (FN[k] - FNS[k]) * p.rdy);
+#endif
     Vn[k] = m[k] ? vn : Vo[k];
   }
   st4(v, off, make_float4(Vn[0], Vn[1], Vn[2], Vn[3]));

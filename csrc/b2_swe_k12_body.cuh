@@ -208,7 +208,7 @@ __device__ __forceinline__ void swe_k5_pp_body(const B2SweParams& p, const float
   float Vn[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float vn = Vo[k] + p.dt * ((FE[k + 1] - FE[k]) * p.rdx + (FN[k] - FNS[k]) * p.rdy);
+    const float vn = swe_apply_div(p, Vo[k], FE[k + 1], FE[k], FN[k], FNS[k]);
     Vn[k] = m[k] ? vn : Vo[k];
   }
   st4(v_new, off, make_float4(Vn[0], Vn[1], Vn[2], Vn[3]));
@@ -226,16 +226,6 @@ __device__ __forceinline__ void swe_k5_pp_body(const B2SweParams& p, const float
 // those three cells (three evaluations of u's 5-point friction stencil instead of one): 4 passes.
 // The frame keeps K34 (on a frame of width 2, which also supplies fe2 / fn2 next to the ring)
 // -> exchange -> K5 on the ring.
-
-// the friction update of u at one cell: the expressions of swe_k34_body
-__device__ __forceinline__ float swe_friction_u(const B2SweParams& p, float u_c, float u_e, float u_w,
-                                                float u_n, float u_s, bool fn_c_zero, bool fn_s_zero) {
-  const float fe_c = p.viscosity * (u_e - u_c) * p.rdx;
-  const float fe_w = p.viscosity * (u_c - u_w) * p.rdx;
-  const float fn_c = fn_c_zero ? 0.f : p.viscosity * (u_n - u_c) * p.rdy;
-  const float fn_s = fn_s_zero ? 0.f : p.viscosity * (u_c - u_s) * p.rdy;
-  return u_c + p.dt * ((fe_c - fe_w) * p.rdx + (fn_c - fn_s) * p.rdy);
-}
 
 // one aligned group of row j (2 <= j <= ny-3); non-bulk lanes are written as copies of u', v'
 __device__ __forceinline__ void swe_k345_body(const B2SweParams& p, const float* __restrict__ u,
@@ -267,7 +257,7 @@ __device__ __forceinline__ void swe_k345_body(const B2SweParams& p, const float*
   for (int t = 0; t < 5; ++t) {                 // u_new[j][i0 + t - 1]
     const int x = t + 1;
     UNj[t] = swe_friction_u(p, Uc[x], Uc[x + 1], Uc[x - 1], Up[x], Um[x], fnc0_j, fns0_j);
-    FE2[t] = p.viscosity * (Vc[x + 1] - UNj[t]) * p.rdx;            // fe2[j][i0 + t - 1]
+    FE2[t] = swe_visc_flux(p.viscosity, Vc[x + 1], UNj[t], p.rdx);  // fe2[j][i0 + t - 1]
   }
 #pragma unroll
   for (int t = 0; t < 4; ++t) {                 // u_new[j-1][i0 + t]
@@ -277,9 +267,9 @@ __device__ __forceinline__ void swe_k345_body(const B2SweParams& p, const float*
   float Un[4], Vn[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float fn2_c = p.viscosity * (Vp[k + 2] - UNj[k + 1]) * p.rdy;       // fn2[j][i]
-    const float fn2_s = p.viscosity * (Vc[k + 2] - UNm[k]) * p.rdy;           // fn2[j-1][i]
-    const float vn = Vc[k + 2] + p.dt * ((FE2[k + 1] - FE2[k]) * p.rdx + (fn2_c - fn2_s) * p.rdy);
+    const float fn2_c = swe_visc_flux(p.viscosity, Vp[k + 2], UNj[k + 1], p.rdy);   // fn2[j][i]
+    const float fn2_s = swe_visc_flux(p.viscosity, Vc[k + 2], UNm[k], p.rdy);       // fn2[j-1][i]
+    const float vn = swe_apply_div(p, Vc[k + 2], FE2[k + 1], FE2[k], fn2_c, fn2_s);
     const bool bulk = swe_is_bulk(p, j, i0 + k);
     Un[k] = bulk ? UNj[k + 1] : Uc[k + 2];
     Vn[k] = bulk ? vn : Vc[k + 2];
@@ -305,7 +295,7 @@ __device__ __forceinline__ void swe_k5_ring_body(const B2SweParams& p, const flo
   float Vn[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float vn = Vo[k] + p.dt * ((FE[k + 1] - FE[k]) * p.rdx + (FN[k] - FNS[k]) * p.rdy);
+    const float vn = swe_apply_div(p, Vo[k], FE[k + 1], FE[k], FN[k], FNS[k]);
     Vn[k] = swe_is_ring(p, j, i0 + k) ? vn : (m[k] ? Vb[k] : Vo[k]);
   }
   st4(v_new, off, make_float4(Vn[0], Vn[1], Vn[2], Vn[3]));
