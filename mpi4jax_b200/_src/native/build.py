@@ -30,6 +30,8 @@ LIB = OUT_DIR / "libb2mpi.so"
 
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
+# extra nvcc flags, e.g. MPI4JAX_B200_NVCC_FLAGS="-DB2_SWE_EXPLICIT_ROUNDING=1" (part of the cache key)
+COMMON += os.environ.get("MPI4JAX_B200_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:
