@@ -107,6 +107,33 @@ swe_k5_ring(B2SweParams p, SweFrame f, const float* __restrict__ v, float* __res
   swe_k5_ring_body(p, v, v_new, fe2, fn2, j, i0, m);
 }
 
+// Two independent roles in one launch (the step is latency-bound at 8 GPUs, every launch counts):
+// CTAs [0, bulk_blocks) run the bulk kernel, the rest the frame pass that precedes the exchange.
+__global__ void __launch_bounds__(SWE_THREADS, 2)
+swe_k12_bulk_k1_frame(B2SweParams p, SweFrame f, unsigned bulk_blocks, const float* __restrict__ h,
+                      float* __restrict__ h_new, const float* __restrict__ u, float* __restrict__ u_new,
+                      const float* __restrict__ v, float* __restrict__ v_new, float* __restrict__ dh,
+                      float* __restrict__ du, float* __restrict__ dv, float* __restrict__ fe,
+                      float* __restrict__ fn, float* __restrict__ q, float* __restrict__ ke) {
+  b2_pdl_enter();
+  int j, i0;
+  bool m[4];
+  if (blockIdx.x < bulk_blocks) {
+    if (!swe_map(p, j, i0, m)) return;
+    if (j < 2 || j > p.ny - 3) return;
+    swe_k12_body(p, h, h_new, u, u_new, v, v_new, dh, du, dv, j, i0, m);
+  } else {
+    const long long t = (long long)(blockIdx.x - bulk_blocks) * SWE_THREADS + threadIdx.x;
+    if (!swe_frame_task(p, f, t, j, i0, m)) return;
+    if (!(m[0] || m[1] || m[2] || m[3])) return;
+    SweOut4 o;
+    swe_k1_body(p, h, u, v, fe, fn, q, ke, j, i0, m, o);
+  }
+}
+
+// (The friction phase is NOT merged the same way: its bulk kernel and the K34 frame pass both
+// write u_new in the groups that contain ring and bulk lanes, so they must stay stream-ordered.)
+
 static int k12_done(B2Comm* c, const char* name) {
   b2_count_launch(c);
   cudaError_t err = cudaGetLastError();
@@ -149,11 +176,10 @@ static int multistep_k12(B2Comm* c, const B2SweParams* p0, const B2SweState* st,
   int rc = 0;
   for (int it = 0; it < nsteps && rc == 0; ++it) {
     p.first_step = (first_step && it == 0) ? 1 : 0;
-    b2_launch(swe_k12_bulk, all_blocks, SWE_THREADS, 0, s, p, h, hn, ua, ub, va, vb, st->dh, st->du, st->dv);
-    if ((rc = k12_done(c, "swe_k12_bulk"))) break;
-    b2_launch(swe_k1_frame, blocks_for(f2.total), SWE_THREADS, 0, s, p, f2, h, ua, va, st->fe, st->fn,
-              st->q, st->ke);
-    if ((rc = k12_done(c, "swe_k1_frame"))) break;
+    // bulk update and the frame's flux pass touch disjoint outputs: one launch, two CTA roles
+    b2_launch(swe_k12_bulk_k1_frame, all_blocks + blocks_for(f2.total), SWE_THREADS, 0, s, p, f2, all_blocks,
+              h, hn, ua, ub, va, vb, st->dh, st->du, st->dv, st->fe, st->fn, st->q, st->ke);
+    if ((rc = k12_done(c, "swe_k12_bulk_k1_frame"))) break;
     d.nfields = 4;
     d.field[0] = st->fe; d.kind[0] = 1;
     d.field[1] = st->fn; d.kind[1] = 2;
