@@ -156,6 +156,45 @@ __device__ unsigned p2p_match(const B2DevComm& c, const B2P2PArgs& a, int src) {
   }
 }
 
+// B2_P2P_ANYSOURCE_SCAN=1: an ANY_SOURCE receive with a tag looks as deep into every source's
+// window as a receive from a named source does (p2p_scan), instead of at the oldest pending message
+// of each source only.  Default 0 = the code that ran on hardware; the scanning variant is mirrored
+// by the model in tests/_p2p_sim.py (Inbox) and waits for its first GPU run.
+#ifndef B2_P2P_ANYSOURCE_SCAN
+#define B2_P2P_ANYSOURCE_SCAN 0
+#endif
+
+#if B2_P2P_ANYSOURCE_SCAN
+// Non-blocking single pass of the scan in p2p_match: does source `src` hold a message that a
+// receive with tag a.recv_tag may take right now?  (A streamed message that is not at the head is
+// "not available" here -- another source may match -- whereas p2p_match treats it as an error.)
+__device__ bool p2p_scan(const B2DevComm& c, const B2P2PArgs& a, int src) {
+  const unsigned head = b2_ld_volatile(c.p2p_recv_seq + src);
+  const unsigned* hdr_base = (const unsigned*)(c.heap[c.rank] + c.lay.p2p_hdr_off);
+  if (a.recv_tag < 0) {
+    const unsigned* h = hdr_base + (((size_t)src * B2_P2P_NSLOT + head % B2_P2P_NSLOT) * B2_P2P_MAX_LANES) * 4;
+    return b2_ld_acquire_sys(h) == head + 1u;
+  }
+  const unsigned ooo = b2_ld_volatile(c.p2p_ctl + CTL_OOO + src);
+  const size_t slot_bytes = c.lay.p2p_slot_bytes;
+  unsigned i = 0;
+  while (i < B2_P2P_NSLOT) {
+    if ((ooo >> i) & 1u) { ++i; continue; }
+    const unsigned sq = head + i;
+    const unsigned* h = hdr_base + (((size_t)src * B2_P2P_NSLOT + sq % B2_P2P_NSLOT) * B2_P2P_MAX_LANES) * 4;
+    if (b2_ld_acquire_sys(h) != sq + 1u) return false;
+    const int tag = (int)b2_ld_volatile(h + 1);
+    const unsigned long long nb =
+        (unsigned long long)b2_ld_volatile(h + 2) | ((unsigned long long)b2_ld_volatile(h + 3) << 32);
+    const unsigned long long nf = nb == 0 ? 1 : (nb + slot_bytes - 1) / slot_bytes;
+    if (tag == a.recv_tag) return i == 0 || nf == 1;
+    if (nf >= B2_P2P_NSLOT - i) return false;
+    i += (unsigned)nf;
+  }
+  return false;
+}
+#endif
+
 __device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) {
   __shared__ int s_src;
   __shared__ unsigned s_seq0;
@@ -172,6 +211,12 @@ __device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
         unsigned spins = 0;
         int probe = 0;
         while (src < 0) {
+#if B2_P2P_ANYSOURCE_SCAN
+          if (p2p_scan(c, a, probe)) {
+            src = probe;
+            break;
+          }
+#else
           const unsigned want = b2_ld_volatile(c.p2p_recv_seq + probe);
           const unsigned* h =
               hdr_base + (((size_t)probe * B2_P2P_NSLOT + want % B2_P2P_NSLOT) * B2_P2P_MAX_LANES) * 4;
@@ -180,6 +225,7 @@ __device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
             src = probe;
             break;
           }
+#endif
           probe = (probe + 1) % c.size;
           if ((++spins & 0xfffu) == 0) {
             unsigned long long now = b2_gtime();

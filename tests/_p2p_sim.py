@@ -107,3 +107,55 @@ class Pair:
             self.ooo |= 1 << (seq0 - self.head)
         self.log.append((seq0, self.hdr[seq0 % NSLOT][1], recv_bytes))
         return True
+
+
+    # ---- ANY_SOURCE support (B2_P2P_ANYSOURCE_SCAN) ----------------------------------------
+    def scan(self, recv_tag):
+        """Non-blocking variant of match() used by the ANY_SOURCE election: sequence number of the
+        message a receive with this tag would take from this source right now, or None.  A streamed
+        message that is not at the head is simply 'not available' here (another source may match)."""
+        head, ooo = self.head, self.ooo
+        if recv_tag < 0:
+            return head if self.hdr[head % NSLOT][0] == head + 1 else None
+        i = 0
+        while i < NSLOT:
+            if (ooo >> i) & 1:
+                i += 1
+                continue
+            sq = head + i
+            seq1, tag, nb = self.hdr[sq % NSLOT]
+            if seq1 != sq + 1:
+                return None
+            nf = self.nfrag(nb)
+            if tag == recv_tag:
+                return sq if (i == 0 or nf == 1) else None
+            if nf >= NSLOT - i:
+                return None
+            i += nf
+        return None
+
+
+class Inbox:
+    """All directed pairs that end at one receiver: ANY_SOURCE receives (device-side election)."""
+
+    def __init__(self, nsources, slot_bytes=4):
+        self.pairs = [Pair(slot_bytes) for _ in range(nsources)]
+        self.probe = 0
+
+    def try_recv_any(self, recv_tag):
+        """One ANY_SOURCE receive; returns (source, tag, nbytes) or None if nothing matches yet."""
+        n = len(self.pairs)
+        for _ in range(n):
+            src = self.probe
+            self.probe = (self.probe + 1) % n
+            pair = self.pairs[src]
+            pair.pump_sender()
+            sq = pair.scan(recv_tag)
+            if sq is None:
+                continue
+            _, tag, nb = pair.hdr[sq % NSLOT]
+            # the followers (and lane 0 itself) now run the blocking match on the elected source
+            assert pair.match(recv_tag) == sq
+            assert pair.try_recv(recv_tag, nb)
+            return src, tag, nb
+        return None
