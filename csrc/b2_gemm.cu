@@ -34,6 +34,7 @@
 
 #include "b2_device.cuh"
 #include "b2_runtime.h"
+#include "b2_gemm_raster.h"
 
 extern "C" void b2_set_error(const char* fmt, ...);
 extern "C" void b2_count_launch(B2Comm* c);
@@ -178,7 +179,8 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // ===== TMA producer =====
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      int m_blk, n_blk;
+      b2_gemm_tile_coords(tile, g.M / BM, num_n, m_blk, n_blk);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(bar(&empty_bar[stage]), phase ^ 1u);
         mbar_expect_tx(bar(&full_bar[stage]), A_STAGE_BYTES + B_STAGE_BYTES);
@@ -219,7 +221,8 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     int pend[GROUP], np = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      int m_blk, n_blk;
+      b2_gemm_tile_coords(tile, g.M / BM, num_n, m_blk, n_blk);
       mbar_wait(bar(&tmem_full_bar[as]), aph);
       asm volatile("tcgen05.fence::after_thread_sync;");
       const size_t row = (size_t)m_blk * BM + q * 32 + lane;
@@ -264,7 +267,9 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               if (i < nred) {
                 const int slot = i / slice_vec, w = i - slot * slice_vec;
                 const int tl = pend[slot], r = r0 + w / (BN / 8), v8 = w % (BN / 8);
-                offs[u] = ((size_t)(tl / num_n) * BM + r) * g.N + (size_t)(tl % num_n) * BN + v8 * 8;
+                int tm, tn;
+                b2_gemm_tile_coords(tl, g.M / BM, num_n, tm, tn);
+                offs[u] = ((size_t)tm * BM + r) * g.N + (size_t)tn * BN + v8 * 8;
                 v[u] = mc_ld_reduce_bf16(stage_mc + offs[u]);   // fp32 sum inside the NVSwitch
               }
             }
@@ -283,7 +288,9 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               if (i < ncp) {
                 const int slot = i / (BM * (BN / 8)), w = i - slot * (BM * (BN / 8));
                 const int tl = pend[slot], r = w / (BN / 8), v8 = w % (BN / 8);
-                offs[u] = ((size_t)(tl / num_n) * BM + r) * g.N + (size_t)(tl % num_n) * BN + v8 * 8;
+                int tm, tn;
+                b2_gemm_tile_coords(tl, g.M / BM, num_n, tm, tn);
+                offs[u] = ((size_t)tm * BM + r) * g.N + (size_t)tn * BN + v8 * 8;
                 v[u] = b2_ld_peer16(stage_local + offs[u]);
               }
             }
