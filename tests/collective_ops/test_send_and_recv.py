@@ -218,3 +218,22 @@ def test_tags_matched_out_of_order_between_ranks(device):
     for _ in range(4):
         assert torch.equal(f(base), want)
     m.flush()
+
+
+def test_any_source_with_tag_matches_behind_the_head(device):
+    """recv(ANY_SOURCE, tag=T) where T is not the oldest pending message of its source.  The CPU
+    backend always matches it; the GPU election does so when built with -DB2_P2P_ANYSOURCE_SCAN=1
+    (default build: only the oldest pending message of every source is considered)."""
+    import os
+
+    if device.type == "cuda" and not os.environ.get("MPI4JAX_B200_TEST_ANYSOURCE_SCAN"):
+        pytest.skip("needs a build with -DB2_P2P_ANYSOURCE_SCAN=1 (set MPI4JAX_B200_TEST_ANYSOURCE_SCAN=1)")
+    a = torch.full((6,), 1.0, device=device)
+    b = torch.full((6,), 2.0, device=device)
+    m.send(a, rank, tag=1)
+    m.send(b, rank, tag=2)
+    status = MPI.Status()
+    got = m.recv(torch.empty_like(a), source=MPI.ANY_SOURCE, tag=2, status=status)
+    assert torch.equal(got, b) and status.Get_source() == rank and status.Get_tag() == 2
+    got = m.recv(torch.empty_like(a), source=MPI.ANY_SOURCE, tag=1, status=status)
+    assert torch.equal(got, a) and status.Get_tag() == 1
