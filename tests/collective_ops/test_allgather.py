@@ -1,4 +1,5 @@
-"""Ports of /root/reference/tests/collective_ops/test_allgather.py."""
+"""allgather: every rank receives every rank's array, `S -> (nproc, *S)` (scenario parity with
+/root/reference/tests/collective_ops/test_allgather.py; plus dtypes, autograd and large messages)."""
 
 import torch
 

@@ -1,4 +1,4 @@
-"""Ports of /root/reference/tests/collective_ops/test_allreduce.py (same cases; jax
+"""Scenario parity with /root/reference/tests/collective_ops/test_allreduce.py (same cases; jax
 transforms replaced by their torch / mpi4jax_b200 equivalents)."""
 
 import pytest

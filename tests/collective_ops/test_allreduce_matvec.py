@@ -1,5 +1,5 @@
 """Linear-algebra property suite: column-sharded mat-vec with allreduce, nested transposes,
-jvp/vjp -- ports of /root/reference/tests/collective_ops/test_allreduce_matvec.py."""
+jvp/vjp -- scenario parity with /root/reference/tests/collective_ops/test_allreduce_matvec.py."""
 
 import pytest
 import torch

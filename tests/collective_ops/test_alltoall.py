@@ -1,4 +1,5 @@
-"""Ports of /root/reference/tests/collective_ops/test_alltoall.py."""
+"""alltoall: block q of rank r goes to block r of rank q (scenario parity with
+/root/reference/tests/collective_ops/test_alltoall.py incl. the non-contiguous regression mpi4jax#176)."""
 
 import pytest
 import torch

@@ -1,4 +1,5 @@
-"""Ports of /root/reference/tests/collective_ops/test_bcast.py."""
+"""bcast: everybody ends up with the root's array, the root gets its own input back (scenario parity
+with /root/reference/tests/collective_ops/test_bcast.py; plus other roots and the VJP)."""
 
 import torch
 

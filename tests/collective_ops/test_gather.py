@@ -1,49 +1,68 @@
-"""Ports of /root/reference/tests/collective_ops/test_gather.py."""
+"""gather: the root receives every rank's array stacked along a new leading axis, the other ranks
+get their input back (reference: /root/reference/mpi4jax/_src/collective_ops/gather.py:44-88,
+140-150)."""
 
+import pytest
 import torch
 
 import mpi4jax_b200 as m
 from mpi4jax_b200 import MPI
 
+from .._gating import new_on_gpu
+
 comm = MPI.COMM_WORLD
-rank = comm.Get_rank()
-size = comm.Get_size()
+rank, size = comm.Get_rank(), comm.Get_size()
+ROOTS = sorted({0, size - 1})
 
 
-def _check(res, arr, device):
-    if rank == 0:
-        assert res.shape == (size, *arr.shape)
-        for p in range(size):
-            assert torch.equal(res[p], torch.ones_like(arr) * p)
-    else:
-        assert torch.equal(res, arr)
+def _piece(r, shape, dtype, device):
+    n = 1
+    for s in shape:
+        n *= s
+    return (torch.arange(n, device=device).reshape(shape) + 100 * r).to(dtype)
 
 
-def test_gather(device):
-    arr = torch.ones((3, 2), device=device) * rank
-    _check(m.gather(arr, root=0), arr, device)
-
-
-def test_gather_jit(device):
-    arr = torch.ones((3, 2), device=device) * rank
-    f = m.jit(lambda x: m.gather(x, root=0))
-    for _ in range(3):
-        _check(f(arr), arr, device)
-
-
-def test_gather_scalar(device):
-    res = m.gather(rank, root=0)
-    if rank == 0:
-        assert torch.equal(res.cpu(), torch.arange(size))
-    else:
-        assert res.item() == rank
-
-
-def test_gather_nonzero_root(device):
-    root = size - 1
-    arr = torch.ones(4, device=device) * rank
-    res = m.gather(arr, root=root)
+@pytest.mark.parametrize("root", ROOTS)
+@pytest.mark.parametrize("shape, dtype", [((3, 2), torch.float32), ((4,), torch.float32), ((2, 3), torch.int32),
+                                          ((1,), torch.bool)], ids=lambda v: str(v).replace("torch.", ""))
+def test_root_collects_all_pieces_in_rank_order(device, root, shape, dtype):
+    if dtype != torch.float32:
+        new_on_gpu(device)
+    x = _piece(rank, shape, dtype, device)
+    keep = x.clone()
+    out = m.gather(x, root=root)
     if rank == root:
-        assert torch.equal(res[:, 0].cpu(), torch.arange(size, dtype=torch.float32))
+        assert out.shape == (size, *shape) and out.dtype == dtype
+        for r in range(size):
+            assert torch.equal(out[r], _piece(r, shape, dtype, device))
     else:
-        assert torch.equal(res, arr)
+        assert torch.equal(out, x)
+    assert torch.equal(x, keep)
+
+
+def test_python_scalar(device):
+    out = m.gather(rank, root=0)
+    if rank == 0:
+        assert out.cpu().tolist() == list(range(size))
+    else:
+        assert out.item() == rank
+
+
+def test_non_contiguous_input(device):
+    new_on_gpu(device)
+    x = _piece(rank, (4, 6), torch.float32, device).t()[::2]          # strided view, shape (3, 4)
+    out = m.gather(x, root=0)
+    if rank == 0:
+        for r in range(size):
+            assert torch.equal(out[r], _piece(r, (4, 6), torch.float32, device).t()[::2])
+
+
+def test_replay_under_jit(device):
+    x = _piece(rank, (3, 2), torch.float32, device)
+    collect = m.jit(lambda t: m.gather(t, root=0))
+    for _ in range(3):
+        out = collect(x)
+        if rank == 0:
+            assert torch.equal(out, torch.stack([_piece(r, (3, 2), torch.float32, device) for r in range(size)]))
+        else:
+            assert torch.equal(out, x)

@@ -1,4 +1,6 @@
-"""Ports of /root/reference/tests/collective_ops/test_scatter.py."""
+"""scatter: the root's ``(nproc, *S)`` input is dealt out, rank r receives block r
+(reference semantics: /root/reference/mpi4jax/_src/collective_ops/scatter.py:44-90, 145-153;
+non-root callers pass a template of the block's shape and dtype)."""
 
 import pytest
 import torch
@@ -6,31 +8,49 @@ import torch
 import mpi4jax_b200 as m
 from mpi4jax_b200 import MPI
 
+from .._gating import new_on_gpu
+
 comm = MPI.COMM_WORLD
-rank = comm.Get_rank()
-size = comm.Get_size()
+rank, size = comm.Get_rank(), comm.Get_size()
+
+ROOTS = sorted({0, size - 1})
+BLOCKS = [((3, 2), torch.float32), ((5,), torch.int64), ((2, 1, 4), torch.float64), ((), torch.float32)]
 
 
-def _input(device):
-    if rank == 0:
-        return torch.stack([torch.ones((3, 2)) * r for r in range(size)]).to(device)
-    return torch.ones((3, 2), device=device) * rank
+def _deck(shape, dtype, device):
+    """What the root scatters: block r is filled with 10 r + (0, 1, 2, ...)."""
+    n = 1
+    for s in shape:
+        n *= s
+    base = torch.arange(n, dtype=dtype, device=device).reshape(shape)
+    return torch.stack([base + 10 * r for r in range(size)])
 
 
-def test_scatter(device):
-    res = m.scatter(_input(device), root=0)
-    assert torch.equal(res, torch.ones((3, 2), device=device) * rank)
+@pytest.mark.parametrize("root", ROOTS)
+@pytest.mark.parametrize("shape, dtype", BLOCKS, ids=lambda v: str(v).replace("torch.", ""))
+def test_every_rank_gets_its_block(device, root, shape, dtype):
+    if (root, shape, dtype) != (0, (3, 2), torch.float32):
+        new_on_gpu(device)
+    deck = _deck(shape, dtype, device)
+    arg = deck if rank == root else torch.empty(shape, dtype=dtype, device=device)
+    before = arg.clone()
+    out = m.scatter(arg, root=root)
+    assert out.shape == torch.Size(shape) and out.dtype == dtype and out.device == arg.device
+    assert torch.equal(out, deck[rank])
+    assert torch.equal(arg, before)                       # inputs are never written to
 
 
-def test_scatter_jit(device):
-    x = _input(device)
-    f = m.jit(lambda v: m.scatter(v, root=0))
+def test_replay_under_jit(device):
+    deck = _deck((3, 2), torch.float32, device)
+    arg = deck if rank == 0 else torch.empty((3, 2), device=device)
+    dealt = m.jit(lambda t: m.scatter(t, root=0))
     for _ in range(3):
-        assert torch.equal(f(x), torch.ones((3, 2), device=device) * rank)
+        assert torch.equal(dealt(arg), deck[rank])
 
 
-def test_scatter_wrong_size(device):
-    if rank == 0:
-        with pytest.raises(ValueError) as excinfo:
-            m.scatter(torch.ones((size + 1, 3, 2), device=device), root=0)
-        assert "Scatter input must have shape (nproc, ...)" in str(excinfo.value)
+def test_leading_axis_must_equal_the_communicator_size(device):
+    if rank != 0:
+        return
+    for bad in (torch.ones((size + 1, 3, 2), device=device), torch.ones((size + 2,), device=device)):
+        with pytest.raises(ValueError, match=r"Scatter input must have shape \(nproc, \.\.\.\)"):
+            m.scatter(bad, root=0)

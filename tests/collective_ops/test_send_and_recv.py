@@ -1,4 +1,4 @@
-"""Ports of /root/reference/tests/collective_ops/test_send_and_recv.py (+ ANY_SOURCE/ANY_TAG,
+"""Scenario parity with /root/reference/tests/collective_ops/test_send_and_recv.py (+ ANY_SOURCE/ANY_TAG,
 self-send and large-message cases the reference does not cover)."""
 
 import pytest

@@ -1,4 +1,6 @@
-"""Ports of /root/reference/tests/collective_ops/test_sendrecv.py."""
+"""sendrecv: simultaneous send and receive, Status, vmap, reverse-mode AD through one and two
+exchanges, forward-mode rejection (scenario parity with
+/root/reference/tests/collective_ops/test_sendrecv.py)."""
 
 import pytest
 import torch

@@ -1,4 +1,4 @@
-"""Failure / lifecycle / observability (ports of /root/reference/tests/collective_ops/
+"""Failure / lifecycle / observability (scenario parity with /root/reference/tests/collective_ops/
 test_common.py: subprocess harness, abort-on-error, deadlock-on-exit, debug logging)."""
 
 import os

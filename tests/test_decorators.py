@@ -1,4 +1,5 @@
-"""Ports of /root/reference/tests/test_decorators.py (+ the other env flags)."""
+"""Environment-flag parsing and the extension guards (`_src/decorators.py`); covers the scenarios of
+/root/reference/tests/test_decorators.py plus the flags that only exist here."""
 
 import pytest
 

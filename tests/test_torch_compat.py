@@ -1,4 +1,5 @@
-"""Ports of /root/reference/tests/test_jax_compat.py for the torch version gate."""
+"""The host-framework version gate (`_src/torch_compat.py`): version parsing table, too-old error,
+too-new warning and its silencer -- the scenarios of /root/reference/tests/test_jax_compat.py for torch."""
 
 import importlib
 import warnings
