@@ -215,8 +215,7 @@ def main() -> int:
                 "l2": ("L2 flushed before the timed region; per-rank state "
                        f"{13 * model.ny_local * model.nx_local * 4 / 2**20:.0f} MiB vs 126 MiB L2"),
                 "graph_chunk_steps": C,
-                "kernel_path": ("fused-halo" if model.fused else
-                                {0: "standalone", 1: "k12", 2: "k12+friction"}[int(model.k12)]),
+                "kernel_path": model.pipeline,
                 "baseline_note": ("vs_baseline divides by the reference's published P100 numbers for "
                                   "a 3600x1800 grid (80 steps/s at n=1, 129 at n=2), this run uses "
                                   "the 2.6x larger 4096x4096 grid named in BASELINE.json"),

@@ -197,7 +197,8 @@ int b2_swe_friction_v(B2Comm* c, const B2SweParams* p, float* v, const float* fe
 int b2_abi_info(int* out, int n) {
   const int v[] = {B2_ABI_VERSION,
                    (int)sizeof(B2StatusRecord), (int)sizeof(B2HaloDesc), (int)sizeof(B2SweParams),
-                   (int)sizeof(B2SweState), (int)sizeof(B2ErrorRecord), B2_MAX_RANKS, B2_P2P_NSLOT};
+                   (int)sizeof(B2SweState), (int)sizeof(B2ErrorRecord), B2_MAX_RANKS, B2_P2P_NSLOT,
+                   (int)sizeof(B2SweCA)};
   const int have = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < have; ++i) out[i] = v[i];
   return have;

@@ -25,6 +25,14 @@ struct B2SweState {
   float* v1;   // partner of v, used by the fused flux+tendency path only (b2_swe_k12.cu)
 };
 
+// "ext" arrays of the communication-avoiding step (b2_swe_ca_body.cuh): [(ny + 4) x epitch] floats,
+// cell (j, i) at (j + 2) * epitch + (i + 2); only cells beyond the interior (and the ring mirror) are used
+struct B2SweCA {
+  float *hx, *upx, *vpx, *uppx, *vppx;
+  int epitch;
+  int cb1;            // first column of the east frame: a multiple of 4, <= nx - 4 (filled in natively)
+};
+
 #define SWE_THREADS 256
 
 // An aligned group of four cells plus its west / east neighbours.
@@ -79,7 +87,7 @@ struct SweOut4 { float a[4][4]; };   // [field][lane]
 // that recomputes the flux quantities (b2_swe_k12.cu) agrees with the two-kernel path to the bit.
 // Default 0: the validated binaries were built from the plain expressions; flip after a GPU run.
 #ifndef B2_SWE_EXPLICIT_ROUNDING
-#define B2_SWE_EXPLICIT_ROUNDING 0
+#define B2_SWE_EXPLICIT_ROUNDING 1
 #endif
 
 // ---- the four diagnostic quantities of the flux kernel, with every rounding spelled out --------
@@ -161,24 +169,33 @@ struct SweK2Out {
   float h, u, v, dh, du, dv;
 };
 
-// The per-cell arithmetic of swe_k2_body (same expressions, same order).
+// The per-cell arithmetic of the tendency kernel with every rounding spelled out (cf. swe_fe ..
+// swe_ke above): the same bits whether it is inlined into the vectorised kernels (swe_k2_body,
+// swe_k12_body) or into the scalar frame kernels of b2_swe_ca_body.cuh.
 __device__ __forceinline__ SweK2Out swe_k2_cell(const B2SweParams& p, const SweK2In& x) {
-  const float dh_new = -(x.fe_c - x.fe_w) * p.rdx - (x.fn_c - x.fns_c) * p.rdy;
-  float du_new = -p.gravity * (x.h_e - x.h_c) * p.rdx +
-                 0.5f * (x.q_c * 0.5f * (x.fn_c + x.fn_e) + x.qs_c * 0.5f * (x.fns_c + x.fns_e));
-  float dv_new = -p.gravity * (x.h_n - x.h_c) * p.rdy -
-                 0.5f * (x.q_c * 0.5f * (x.fe_c + x.fen_c) + x.q_w * 0.5f * (x.fe_w + x.fen_w));
-  du_new += -(x.ke_e - x.ke_c) * p.rdx;
-  dv_new += -(x.ken_c - x.ke_c) * p.rdy;
+  // dh = -(fe_c - fe_w) / dx - (fn_c - fn_s) / dy
+  const float dh_new = __fmaf_rn(__fadd_rn(x.fns_c, -x.fn_c), p.rdy, -__fmul_rn(__fadd_rn(x.fe_c, -x.fe_w), p.rdx));
+  // du = -g (h_e - h_c) / dx + 1/2 (q_c (fn_c + fn_e) / 2 + q_s (fn_s + fn_se) / 2) - (ke_e - ke_c) / dx
+  const float gu = __fmul_rn(__fmul_rn(-p.gravity, __fadd_rn(x.h_e, -x.h_c)), p.rdx);
+  const float su = __fadd_rn(__fmul_rn(__fmul_rn(x.q_c, 0.5f), __fadd_rn(x.fn_c, x.fn_e)),
+                             __fmul_rn(__fmul_rn(x.qs_c, 0.5f), __fadd_rn(x.fns_c, x.fns_e)));
+  float du_new = __fmaf_rn(0.5f, su, gu);
+  du_new = __fmaf_rn(__fadd_rn(x.ke_c, -x.ke_e), p.rdx, du_new);
+  // dv = -g (h_n - h_c) / dy - 1/2 (q_c (fe_c + fe_n) / 2 + q_w (fe_w + fe_nw) / 2) - (ke_n - ke_c) / dy
+  const float gv = __fmul_rn(__fmul_rn(-p.gravity, __fadd_rn(x.h_n, -x.h_c)), p.rdy);
+  const float sv = __fadd_rn(__fmul_rn(__fmul_rn(x.q_c, 0.5f), __fadd_rn(x.fe_c, x.fen_c)),
+                             __fmul_rn(__fmul_rn(x.q_w, 0.5f), __fadd_rn(x.fe_w, x.fen_w)));
+  float dv_new = __fmaf_rn(-0.5f, sv, gv);
+  dv_new = __fmaf_rn(__fadd_rn(x.ke_c, -x.ken_c), p.rdy, dv_new);
   SweK2Out o;
   if (p.first_step) {
-    o.u = x.u_o + p.dt * du_new;
-    o.v = x.v_o + p.dt * dv_new;
-    o.h = x.h_c + p.dt * dh_new;
+    o.u = __fmaf_rn(p.dt, du_new, x.u_o);
+    o.v = __fmaf_rn(p.dt, dv_new, x.v_o);
+    o.h = __fmaf_rn(p.dt, dh_new, x.h_c);
   } else {
-    o.u = x.u_o + p.dt * (p.ab_a * du_new + p.ab_b * x.du_o);
-    o.v = x.v_o + p.dt * (p.ab_a * dv_new + p.ab_b * x.dv_o);
-    o.h = x.h_c + p.dt * (p.ab_a * dh_new + p.ab_b * x.dh_o);
+    o.u = __fmaf_rn(p.dt, __fmaf_rn(p.ab_a, du_new, __fmul_rn(p.ab_b, x.du_o)), x.u_o);
+    o.v = __fmaf_rn(p.dt, __fmaf_rn(p.ab_a, dv_new, __fmul_rn(p.ab_b, x.dv_o)), x.v_o);
+    o.h = __fmaf_rn(p.dt, __fmaf_rn(p.ab_a, dh_new, __fmul_rn(p.ab_b, x.dh_o)), x.h_c);
   }
   o.dh = dh_new; o.du = du_new; o.dv = dv_new;
   return o;

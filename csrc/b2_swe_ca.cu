@@ -1,0 +1,323 @@
+// mpi4jax_b200 -- communication-avoiding shallow-water step: kernels and the two-stream schedule.
+// Design, storage and the "views" that keep the reference's discrete system: b2_swe_ca_body.cuh.
+//
+// One model step (the reference's shallow_water_step, examples/shallow_water.py:270-403):
+//
+//   stream s  (bulk) :  K12 bulk ------------------> friction bulk ------------+--> next step
+//                         \                            ^                        |
+//   stream s2 (frame):  A (tendencies, frame) -> X (deep halo exchange) -> D (friction, frame + ext)
+//
+// The bulk kernels read no halo and write no frame cell, so the NVLink round of X is hidden
+// behind them; cross edges: friction bulk needs A (u', v' next to the frame), D needs K12 bulk.
+// Under CUDA-graph capture (mpi4jax_b200.jit) the event fork / join becomes graph edges.
+// 16 array passes per step on the bulk (12 + 4) instead of 32, one exchange instead of three.
+#include <cstdio>
+#include <cstdlib>
+
+#include "b2_device.cuh"
+#include "b2_halo_ll.cuh"
+#include "b2_runtime.h"
+#include "b2_swe_ca_body.cuh"
+
+extern "C" void b2_set_error(const char* fmt, ...);
+extern "C" void b2_count_launch(B2Comm* c);
+extern "C" int b2_swe_multistep(B2Comm* c, const B2SweParams* p0, const B2SweState* st,
+                                const B2HaloDesc* topo, int nsteps, int first_step, cudaStream_t s);
+
+#define CA_THREADS 256
+
+// ---- frame kernels (one thread per cell; a few thousand cells) ------------------------------------
+__global__ void __launch_bounds__(CA_THREADS) swe_ca_tend_frame(const CACtx c, const CAFrame f) {
+  int j, i;
+  if (!ca_frame_cell(c.p, f, c.x.cb1, (long long)blockIdx.x * CA_THREADS + threadIdx.x, j, i)) return;
+  swe_ca_tend_cell(c, j, i);
+}
+
+// friction on the frame cells (u', v' -> ua_out, va_out) and u'' / v'' of the neighbours' cells
+__global__ void __launch_bounds__(CA_THREADS) swe_ca_fric_frame(const CACtx c, const CAFrame f,
+                                                                float* __restrict__ ua_out,
+                                                                float* __restrict__ va_out) {
+  const long long t = (long long)blockIdx.x * CA_THREADS + threadIdx.x;
+  int j, i;
+  if (t < f.total) {
+    ca_frame_cell(c.p, f, c.x.cb1, t, j, i);
+    swe_ca_fric_cell(c, ua_out, va_out, j, i);
+  } else if (ca_ext_cell(c.p, t - f.total, j, i)) {
+    swe_ca_fric_ext_cell(c, ua_out, va_out, j, i);
+  }
+}
+
+// after (re)initialising the state: no friction step has happened yet, so the "fresh" values of
+// the neighbours' cells are the exchanged ones, and the stale mirror of the ring is u, v itself
+__global__ void __launch_bounds__(CA_THREADS) swe_ca_init_ext(const B2SweParams p, const B2SweCA x,
+                                                              const float* __restrict__ u,
+                                                              const float* __restrict__ v) {
+  const long long t = (long long)blockIdx.x * CA_THREADS + threadIdx.x;
+  const long long next = ca_ext_total(p);
+  int j, i;
+  if (t < next) {
+    if (!ca_ext_cell(p, t, j, i)) return;
+    const size_t e = ca_e(x, j, i);
+    x.uppx[e] = x.upx[e];
+    x.vppx[e] = x.vpx[e];
+  } else {
+    const long long r = t - next;            // ring cells: rows 1, ny-2 and columns 1, nx-2
+    const int nrow = 2 * (p.nx - 2);
+    if (r < nrow) { j = r < p.nx - 2 ? 1 : p.ny - 2; i = 1 + (int)(r % (p.nx - 2)); }
+    else {
+      const long long q = r - nrow;
+      if (q >= 2LL * (p.ny - 2)) return;
+      j = 1 + (int)(q >> 1); i = (q & 1) ? p.nx - 2 : 1;
+    }
+    const size_t e = ca_e(x, j, i), off = ca_m(p, j, i);
+    x.upx[e] = u[off];
+    x.vpx[e] = v[off];
+  }
+}
+
+// ---- bulk kernels: the vectorised bodies of b2_swe_k12_body.cuh on whole groups -------------------
+__global__ void __launch_bounds__(SWE_THREADS, 2)
+swe_ca_bulk_k12(const B2SweParams p, const int cb1, const float* __restrict__ h, float* __restrict__ h_new,
+                const float* __restrict__ u, float* __restrict__ u_new, const float* __restrict__ v,
+                float* __restrict__ v_new, float* __restrict__ dh, float* __restrict__ du,
+                float* __restrict__ dv) {
+  const long long t = (long long)blockIdx.x * SWE_THREADS + threadIdx.x;
+  if (t >= ca_bulk_tasks(p, cb1)) return;
+  int j, i0;
+  ca_bulk_task(p, cb1, t, j, i0);
+  const bool m[4] = {true, true, true, true};
+  swe_k12_body(p, h, h_new, u, u_new, v, v_new, dh, du, dv, j, i0, m);
+}
+
+__global__ void __launch_bounds__(SWE_THREADS, 2)
+swe_ca_bulk_fric(const B2SweParams p, const int cb1, const float* __restrict__ u, float* __restrict__ u_new,
+                 const float* __restrict__ v, float* __restrict__ v_new) {
+  const long long t = (long long)blockIdx.x * SWE_THREADS + threadIdx.x;
+  if (t >= ca_bulk_tasks(p, cb1)) return;
+  int j, i0;
+  ca_bulk_task(p, cb1, t, j, i0);
+  swe_k345_body(p, u, u_new, v, v_new, j, i0, true);
+}
+
+// ---- X: three layers of (h', u', v') to all eight neighbours, flag-in-data (b2_halo_ll.cuh) -----
+// Pushes go straight from the arrays into the neighbours' receive buffers; the receiver polls the
+// data itself and scatters it into the ext arrays (all layers) and the main arrays' halo (layer 1).
+struct CAExt3 { float* a[CA_NF]; };
+
+__global__ void __launch_bounds__(CA_THREADS) b2_k_halo_ca(const B2DevComm c, const B2HaloDesc d,
+                                                           const CAExt3 ext, const int epitch) {
+  __shared__ unsigned s_rx[FS_NSIDES], s_tx[FS_NSIDES];
+  __shared__ int s_cnt[FS_NSIDES + 1];
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
+  const int ny = d.ny, nx = d.nx;
+  const size_t pitch = (size_t)d.pitch;
+  const int nb[FS_NSIDES] = {d.west, d.east, d.south, d.north, d.sw, d.se, d.nw, d.ne};
+  const int opp[FS_NSIDES] = {CA_E, CA_W, CA_N, CA_S, CA_NE, CA_NW, CA_SE, CA_SW};
+  if (threadIdx.x < FS_NSIDES) {
+    s_rx[threadIdx.x] = b2_ld_volatile(c.ticket + TK_RX + threadIdx.x);
+    s_tx[threadIdx.x] = b2_ld_volatile(c.ticket + TK_TX + threadIdx.x);
+  }
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < FS_NSIDES; ++k) {
+      s_cnt[k] = acc;
+      if (nb[k] >= 0) acc += ca_msg_count(ny, nx, k);     // |message towards k| == |message landing on k|
+    }
+    s_cnt[FS_NSIDES] = acc;
+  }
+  __syncthreads();
+  const int total = s_cnt[FS_NSIDES];
+  // ---------------- push ----------------
+  for (int k = gt; k < total; k += gn) {
+    int s = 0;
+    while (k >= s_cnt[s + 1]) ++s;
+    const int e = k - s_cnt[s], land = opp[s];
+    int f, js, is, jr, ir, layer;
+    ca_msg_elem(ny, nx, land, e, f, js, is, jr, ir, layer);
+    fz_put(fz_buf(c, nb[s], s_tx[s] & 1u, land) + e, d.field[f][(size_t)js * pitch + is], s_tx[s] + 1u);
+  }
+  // ---------------- poll + scatter ----------------
+  const int jlo = (d.south >= 0) ? 1 : 0, jhi = (d.north >= 0) ? ny - 1 : ny;
+  for (int k = gt; k < total; k += gn) {
+    int s = 0;
+    while (k >= s_cnt[s + 1]) ++s;
+    const int e = k - s_cnt[s];
+    const float val = fz_get(c, fz_buf(c, c.rank, s_rx[s] & 1u, s) + e, s_rx[s] + 1u, s);
+    ca_scatter(ny, nx, pitch, epitch, s, e, jlo, jhi, val, d.field, ext.a);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned old = atomicAdd(c.ticket + TK_FIN, 1u);
+    if (old == gridDim.x - 1) {
+      b2_st_volatile(c.ticket + TK_FIN, 0u);
+      for (int k = 0; k < FS_NSIDES; ++k)
+        if (nb[k] >= 0) {
+          b2_st_volatile(c.ticket + TK_RX + k, s_rx[k] + 1u);
+          b2_st_volatile(c.ticket + TK_TX + k, s_tx[k] + 1u);
+        }
+      __threadfence();
+    }
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_ev[4];
+
+static int ca_streams() {
+  if (g_side) return 0;
+  if (cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking) != cudaSuccess) {
+    b2_set_error("swe_ca: cudaStreamCreate failed");
+    g_side = nullptr;
+    return 1;
+  }
+  for (int k = 0; k < 4; ++k)
+    if (cudaEventCreateWithFlags(&g_ev[k], cudaEventDisableTiming) != cudaSuccess) {
+      b2_set_error("swe_ca: cudaEventCreate failed");
+      return 1;
+    }
+  return 0;
+}
+
+static int ca_done(B2Comm* c, const char* name) {
+  b2_count_launch(c);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    b2_set_error("%s: kernel launch failed: %s", name, cudaGetErrorString(err));
+    return 1000 + (int)err;
+  }
+  return 0;
+}
+static unsigned ca_blocks(long long tasks, int threads) { return (unsigned)((tasks + threads - 1) / threads); }
+
+static int ca_check(B2Comm* c, const B2SweParams& p, const B2SweCA& x) {
+  if (p.pitch % 4 != 0 || p.pitch < p.nx) {
+    b2_set_error("swe_ca: the row pitch must be a multiple of 4 floats and >= nx");
+    return B2_ERR_BAD_ARG;
+  }
+  if (x.epitch < p.nx + 4 || !x.hx || !x.upx || !x.vpx || !x.uppx || !x.vppx) {
+    b2_set_error("swe_ca: ext arrays missing or too narrow (epitch %d < nx + 4)", x.epitch);
+    return B2_ERR_BAD_ARG;
+  }
+  const size_t need = (size_t)CA_NF * CA_L * (size_t)(p.ny > p.nx ? p.ny : p.nx) * sizeof(uint2);
+  if (need > c->dev.lay.halo_ll_cap) {
+    b2_set_error("swe_ca: halo buffers too small (%zu > %zu); raise MPI4JAX_B200_HALO_BYTES", need,
+                 c->dev.lay.halo_ll_cap);
+    return B2_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
+static int ca_exchange(B2Comm* c, const B2HaloDesc& topo, const B2SweParams& p, const B2SweCA& x, float* f0,
+                       float* f1, float* f2, cudaStream_t s) {
+  B2HaloDesc d = topo;
+  d.ny = p.ny; d.nx = p.nx; d.pitch = p.pitch;
+  d.nfields = CA_NF;
+  d.field[0] = f0; d.kind[0] = 0;
+  d.field[1] = f1; d.kind[1] = 1;
+  d.field[2] = f2; d.kind[2] = 2;
+  CAExt3 ext;
+  ext.a[0] = x.hx; ext.a[1] = x.upx; ext.a[2] = x.vpx;
+  long long total = 0;
+  const int nb[8] = {d.west, d.east, d.south, d.north, d.sw, d.se, d.nw, d.ne};
+  for (int k = 0; k < 8; ++k) {
+    if (nb[k] < -1 || nb[k] >= c->dev.size) {
+      b2_set_error("swe_ca: invalid neighbour rank %d", nb[k]);
+      return B2_ERR_BAD_ARG;
+    }
+    if (nb[k] >= 0) total += ca_msg_count(p.ny, p.nx, k);
+  }
+  unsigned ctas = ca_blocks(total, CA_THREADS);          // pure latency: about one element per thread
+  if (ctas < 8) ctas = 8;
+  if (ctas > 120) ctas = 120;                            // all co-resident next to the bulk kernel's CTAs
+  b2_k_halo_ca<<<ctas, CA_THREADS, 0, s>>>(c->dev, d, ext, x.epitch);
+  return ca_done(c, "halo_ca");
+}
+
+extern "C" {
+
+// Fill the ext arrays from a state whose main arrays are complete (after reset / load_state):
+// deep exchange of (h, u, v), then fresh := exchanged and the ring mirror.  Collective.
+int b2_swe_ca_init(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const B2SweCA* x0,
+                   const B2HaloDesc* topo, cudaStream_t s) {
+  B2SweParams p = *p0;
+  B2SweCA x = *x0;
+  if (!swe_ca_supported(p)) return 0;
+  x.cb1 = swe_ca_cb1(p);
+  if (int rc = ca_check(c, p, x)) return rc;
+  if (int rc = ca_exchange(c, *topo, p, x, st->h0, st->u, st->v, s)) return rc;
+  const long long tasks = ca_ext_total(p) + 2LL * (p.nx - 2) + 2LL * (p.ny - 2);
+  swe_ca_init_ext<<<ca_blocks(tasks, CA_THREADS), CA_THREADS, 0, s>>>(p, x, st->u, st->v);
+  return ca_done(c, "swe_ca_init_ext");
+}
+
+int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const B2SweCA* x0,
+                        const B2HaloDesc* topo, int nsteps, int first_step, cudaStream_t s) {
+  // blocks too small for the bulk / frame split, or no friction step to bring u, v back home
+  if (!swe_ca_supported(*p0) || !(p0->viscosity > 0.f) || !st->u1 || !st->v1)
+    return b2_swe_multistep(c, p0, st, topo, nsteps, first_step, s);
+  B2SweParams p = *p0;
+  B2SweCA x = *x0;
+  x.cb1 = swe_ca_cb1(p);
+  if (int rc = ca_check(c, p, x)) return rc;
+  if (int rc = ca_streams()) return rc;
+  const cudaStream_t s2 = g_side;
+  const cudaEvent_t e0 = g_ev[0], eA = g_ev[1], eB = g_ev[2], eD = g_ev[3];
+  float* h = st->h0;
+  float* hn = st->h1;
+  const CAFrame f = ca_frame(p, x.cb1);
+  const unsigned bulk_blocks = ca_blocks(ca_bulk_tasks(p, x.cb1), SWE_THREADS);
+  const unsigned frame_blocks = ca_blocks(f.total, CA_THREADS);
+  const unsigned fric_blocks = ca_blocks(f.total + ca_ext_total(p), CA_THREADS);
+  int rc = 0;
+#define CA_RT(call)                                                              \
+  if (rc == 0) {                                                                 \
+    cudaError_t e_ = (call);                                                     \
+    if (e_ != cudaSuccess) {                                                     \
+      b2_set_error("swe_multistep_ca: %s failed: %s", #call, cudaGetErrorString(e_)); \
+      rc = 1000 + (int)e_;                                                       \
+    }                                                                            \
+  }
+  for (int it = 0; it < nsteps && rc == 0; ++it) {
+    p.first_step = (first_step && it == 0) ? 1 : 0;
+    CACtx ctx;
+    ctx.p = p; ctx.x = x;
+    ctx.h = h; ctx.ua = st->u; ctx.va = st->v;
+    ctx.hn = hn; ctx.ub = st->u1; ctx.vb = st->v1;
+    ctx.dh = st->dh; ctx.du = st->du; ctx.dv = st->dv;
+    CA_RT(cudaEventRecord(e0, s));
+    CA_RT(cudaStreamWaitEvent(s2, e0, 0));
+    if (rc) break;
+    // frame: tendencies
+    swe_ca_tend_frame<<<frame_blocks, CA_THREADS, 0, s2>>>(ctx, f);
+    if ((rc = ca_done(c, "swe_ca_tend_frame"))) break;
+    CA_RT(cudaEventRecord(eA, s2));
+    // bulk: tendencies
+    swe_ca_bulk_k12<<<bulk_blocks, SWE_THREADS, 0, s>>>(p, x.cb1, h, hn, st->u, st->u1, st->v, st->v1, st->dh,
+                                                        st->du, st->dv);
+    if ((rc = ca_done(c, "swe_ca_bulk_k12"))) break;
+    CA_RT(cudaEventRecord(eB, s));
+    // frame: the step's only exchange
+    if ((rc = ca_exchange(c, *topo, p, x, hn, st->u1, st->v1, s2))) break;
+    // bulk: friction (reads u', v' two cells into the frame)
+    CA_RT(cudaStreamWaitEvent(s, eA, 0));
+    if (rc) break;
+    swe_ca_bulk_fric<<<bulk_blocks, SWE_THREADS, 0, s>>>(p, x.cb1, st->u1, st->u, st->v1, st->v);
+    if ((rc = ca_done(c, "swe_ca_bulk_fric"))) break;
+    // frame: friction (reads u', v' up to five cells in: needs the bulk tendencies)
+    CA_RT(cudaStreamWaitEvent(s2, eB, 0));
+    if (rc) break;
+    swe_ca_fric_frame<<<fric_blocks, CA_THREADS, 0, s2>>>(ctx, f, st->u, st->v);
+    if ((rc = ca_done(c, "swe_ca_fric_frame"))) break;
+    CA_RT(cudaEventRecord(eD, s2));
+    CA_RT(cudaStreamWaitEvent(s, eD, 0));
+    float* t = h; h = hn; hn = t;
+  }
+  if (rc == 0 && h != st->h0)
+    CA_RT(cudaMemcpyAsync(st->h0, h, (size_t)p.ny * p.pitch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+#undef CA_RT
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+// mpi4jax_b200 -- shallow water, communication-avoiding step ("CA"): ONE halo exchange per model
+// step instead of the reference's twelve per-field rounds (three fused exchanges in b2_swe.cu).
+//
+// The reference's step (examples/shallow_water.py:270-403) alternates local stencils with halo
+// exchanges four times: fluxes -> exchange(fe, fn, q, ke) -> tendencies -> exchange(h', u', v')
+// -> friction-u -> exchange(fe2, fn2) -> friction-v.  At 8 GPUs a rank owns 2048 x 1024 cells
+// that live in L2; a step is ~20 us of arithmetic and every exchange costs one NVLink round
+// (~9 us), so the exchanges -- not the bandwidth -- bound the step.  Here the tendency phase's
+// result (h', u', v') is exchanged ONCE, three cells deep, and everything the other two exchanges
+// used to deliver is recomputed from it on a thin frame around the block:
+//
+//   frame kernel A   h', u', v' on the cells within 3 of the block edge.  The fluxes a ring cell
+//                    needs from its neighbours' side of the edge are evaluated locally, each
+//                    with the operands its OWNER would have used (see "views" below).
+//   exchange X       3 layers of (h', u', v') to all eight neighbours (b2_swe_ca.cu).
+//   frame kernel D   friction (u' -> u'', v' -> v'') on the frame, and the neighbours' u'', v''
+//                    one / two cells beyond the edge, which next step's halo fluxes need.
+//   bulk kernels     K12 and the fused friction kernel (b2_swe_k12_body.cuh) on everything else;
+//                    they touch no halo, so they run concurrently with A -> X -> D.
+//
+// Views.  The reference's discrete system is decomposition dependent: a rank computes its
+// fluxes from u, v whose HALO is stale by the friction update (the halo of u, v is exchanged
+// before the friction step and not after it).  A flux at a halo cell therefore has to be
+// evaluated as the cell's owner Q does: with the post-friction value u'' at cells Q owns and
+// the pre-friction value u' at cells Q only sees as halo.  `ca_vu(Q, d)` implements exactly
+// that; with it (and the explicit-rounding helpers of b2_swe_body.cuh) this pipeline and the
+// stand-alone one produce the same bits on the same decomposition
+// (tests/test_swe_host_emulation.py runs both on 1x1 .. 3x2 process grids).
+//
+// Storage.  The main (ny, pitch) arrays keep their meaning (1-cell halo; u, v halos stale).
+// Five "ext" arrays [(ny + 4) x epitch], cell (j, i) at (j + 2) * epitch + (i + 2), hold what
+// lies beyond: hx (h, layers 1..2), upx / vpx (u', v': layers 1..3 and a mirror of this rank's
+// own ring cells, i.e. every STALE value a view can ask for), uppx / vppx (u'', v'' of the
+// neighbours' cells, layers 1..2 / 1).  Only their outer cells are ever touched.
+#pragma once
+
+#include "b2_swe_k12_body.cuh"
+
+#define CA_L 3        // halo layers exchanged per step (layer 1 = the main arrays' halo cell)
+#define CA_NF 3       // fields per exchange: h', u', v'
+
+// everything a frame kernel dereferences
+struct CACtx {
+  B2SweParams p;
+  B2SweCA x;
+  const float *h;           // h of this step (halo fresh)
+  const float *ua, *va;     // u'', v'' of the previous step (interior; wall rows constant)
+  float *hn, *ub, *vb;      // h', u', v' (tendency phase output)
+  float *dh, *du, *dv;
+};
+
+__host__ __device__ inline bool swe_ca_supported(const B2SweParams& p) {
+  return p.ny >= 12 && p.nx >= 16;
+}
+__host__ __device__ inline int swe_ca_cb1(const B2SweParams& p) { return ((p.nx - 4) >> 2) << 2; }
+
+__host__ __device__ __forceinline__ int ca_rj(const B2SweParams& p, int j) { return j < 1 ? -1 : (j > p.ny - 2 ? 1 : 0); }
+__host__ __device__ __forceinline__ int ca_ri(const B2SweParams& p, int i) { return i < 1 ? -1 : (i > p.nx - 2 ? 1 : 0); }
+// rows beyond a physical wall (no rank owns them; the main arrays hold their constant values)
+__host__ __device__ __forceinline__ bool ca_wall_row(const B2SweParams& p, int j) {
+  return (j < 1 && p.south_wall) || (j > p.ny - 2 && p.north_wall);
+}
+__host__ __device__ __forceinline__ size_t ca_m(const B2SweParams& p, int j, int i) { return (size_t)j * p.pitch + i; }
+__host__ __device__ __forceinline__ size_t ca_e(const B2SweCA& x, int j, int i) {
+  return (size_t)(j + 2) * x.epitch + (i + 2);
+}
+__host__ __device__ __forceinline__ bool ca_mine(const B2SweParams& p, int j, int i) {
+  return j >= 1 && j <= p.ny - 2 && i >= 1 && i <= p.nx - 2;
+}
+
+// ---- accessors -------------------------------------------------------------------------------
+__device__ __forceinline__ float ca_h(const CACtx& c, int j, int i) {
+  if (ca_mine(c.p, j, i) || ca_wall_row(c.p, j)) return c.h[ca_m(c.p, j, i)];
+  return c.x.hx[ca_e(c.x, j, i)];
+}
+// u as cell-owner Q = (qj, qi) sees it at cell (j, i): fresh where Q owns the cell, stale elsewhere
+__device__ __forceinline__ float ca_vu(const CACtx& c, int qj, int qi, int j, int i) {
+  if (ca_wall_row(c.p, j)) return c.ua[ca_m(c.p, j, i)];
+  const int rj = ca_rj(c.p, j), ri = ca_ri(c.p, i);
+  if (rj == qj && ri == qi) return (rj == 0 && ri == 0) ? c.ua[ca_m(c.p, j, i)] : c.x.uppx[ca_e(c.x, j, i)];
+  return c.x.upx[ca_e(c.x, j, i)];
+}
+__device__ __forceinline__ float ca_vv(const CACtx& c, int qj, int qi, int j, int i) {
+  if (ca_wall_row(c.p, j)) return c.va[ca_m(c.p, j, i)];
+  const int rj = ca_rj(c.p, j), ri = ca_ri(c.p, i);
+  if (rj == qj && ri == qi) return (rj == 0 && ri == 0) ? c.va[ca_m(c.p, j, i)] : c.x.vppx[ca_e(c.x, j, i)];
+  return c.x.vpx[ca_e(c.x, j, i)];
+}
+
+// ---- the four flux-kernel quantities at cell (j, i) in [0, ny) x [0, nx), evaluated as the
+// cell's owner does (swe_k1_body's expressions; zero beyond a wall, where nothing is ever stored)
+__device__ __forceinline__ float ca_fe(const CACtx& c, int j, int i) {
+  if (ca_wall_row(c.p, j)) return 0.f;
+  const int qj = ca_rj(c.p, j), qi = ca_ri(c.p, i), hj = hc_row(c.p, j);
+  return swe_fe(ca_h(c, hj, i), ca_h(c, hj, i + 1), ca_vu(c, qj, qi, j, i));
+}
+__device__ __forceinline__ float ca_fn(const CACtx& c, int j, int i) {
+  if (ca_wall_row(c.p, j) || (c.p.north_wall && j == c.p.ny - 2)) return 0.f;      // "v" wall rule
+  const int qj = ca_rj(c.p, j), qi = ca_ri(c.p, i);
+  return swe_fn(ca_h(c, hc_row(c.p, j), i), ca_h(c, hc_row(c.p, j + 1), i), ca_vv(c, qj, qi, j, i));
+}
+__device__ __forceinline__ float ca_q(const CACtx& c, int j, int i) {
+  if (ca_wall_row(c.p, j)) return 0.f;
+  const int qj = ca_rj(c.p, j), qi = ca_ri(c.p, i), hj = hc_row(c.p, j), hj1 = hc_row(c.p, j + 1);
+  return swe_q(c.p, c.p.coriolis[j], ca_vv(c, qj, qi, j, i + 1), ca_vv(c, qj, qi, j, i), ca_vu(c, qj, qi, j + 1, i),
+               ca_vu(c, qj, qi, j, i), ca_h(c, hj, i), ca_h(c, hj, i + 1), ca_h(c, hj1, i), ca_h(c, hj1, i + 1));
+}
+__device__ __forceinline__ float ca_ke(const CACtx& c, int j, int i) {
+  if (ca_wall_row(c.p, j)) return 0.f;
+  const int qj = ca_rj(c.p, j), qi = ca_ri(c.p, i);
+  return swe_ke(ca_vu(c, qj, qi, j, i), ca_vu(c, qj, qi, j, i - 1), ca_vv(c, qj, qi, j, i), ca_vv(c, qj, qi, j - 1, i));
+}
+
+// ---- frame kernel A: flux + tendency update of one of this rank's cells ------------------------
+__device__ __forceinline__ void swe_ca_tend_cell(const CACtx& c, int j, int i) {
+  const B2SweParams& p = c.p;
+  const size_t off = ca_m(p, j, i);
+  SweK2In in;
+  in.fe_c = ca_fe(c, j, i); in.fe_w = ca_fe(c, j, i - 1); in.fen_c = ca_fe(c, j + 1, i); in.fen_w = ca_fe(c, j + 1, i - 1);
+  in.fn_c = ca_fn(c, j, i); in.fn_e = ca_fn(c, j, i + 1); in.fns_c = ca_fn(c, j - 1, i); in.fns_e = ca_fn(c, j - 1, i + 1);
+  in.q_c = ca_q(c, j, i); in.q_w = ca_q(c, j, i - 1); in.qs_c = ca_q(c, j - 1, i);
+  in.ke_c = ca_ke(c, j, i); in.ke_e = ca_ke(c, j, i + 1); in.ken_c = ca_ke(c, j + 1, i);
+  in.h_c = c.h[off]; in.h_e = ca_h(c, j, i + 1); in.h_n = ca_h(c, j + 1, i);
+  in.u_o = c.ua[off]; in.v_o = c.va[off];
+  in.dh_o = p.first_step ? 0.f : c.dh[off];
+  in.du_o = p.first_step ? 0.f : c.du[off];
+  in.dv_o = p.first_step ? 0.f : c.dv[off];
+  SweK2Out o = swe_k2_cell(p, in);
+  if (p.north_wall && j == p.ny - 2) o.v = 0.f;       // "v" wall rule, after the update
+  c.hn[off] = o.h; c.ub[off] = o.u; c.vb[off] = o.v;
+  c.dh[off] = o.dh; c.du[off] = o.du; c.dv[off] = o.dv;
+}
+
+// ---- frame kernel D: friction ------------------------------------------------------------------
+// u', v' anywhere within three cells of the block (mine: main arrays; beyond: the exchanged copy)
+__device__ __forceinline__ float ca_up(const CACtx& c, int j, int i) {
+  if (ca_mine(c.p, j, i) || ca_wall_row(c.p, j)) return c.ub[ca_m(c.p, j, i)];
+  return c.x.upx[ca_e(c.x, j, i)];
+}
+__device__ __forceinline__ float ca_vp(const CACtx& c, int j, int i) {
+  if (ca_mine(c.p, j, i) || ca_wall_row(c.p, j)) return c.vb[ca_m(c.p, j, i)];
+  return c.x.vpx[ca_e(c.x, j, i)];
+}
+// u'' of cell (j, i) (swe_k34_body's update; the wall rules are functions of the row only, and a
+// y neighbour's far wall is out of reach)
+__device__ __forceinline__ float ca_upp(const CACtx& c, int j, int i) {
+  const B2SweParams& p = c.p;
+  const bool fn_c_zero = p.north_wall && j == p.ny - 2, fn_s_zero = p.south_wall && j == 1;
+  // operands of a zeroed flux are not loaded (they may lie beyond a wall AND beyond the arrays)
+  const float u_n = fn_c_zero ? 0.f : ca_up(c, j + 1, i), u_s = fn_s_zero ? 0.f : ca_up(c, j - 1, i);
+  return swe_friction_u(p, ca_up(c, j, i), ca_up(c, j, i + 1), ca_up(c, j, i - 1), u_n, u_s, fn_c_zero, fn_s_zero);
+}
+// v'' of cell (j, i) given its own u'' (swe_k34_body's fluxes + swe_k5_body's update)
+__device__ __forceinline__ float ca_vpp(const CACtx& c, int j, int i, float upp_c) {
+  const B2SweParams& p = c.p;
+  const float v_c = ca_vp(c, j, i);
+  const float fe2_c = swe_visc_flux(p.viscosity, ca_vp(c, j, i + 1), upp_c, p.rdx);
+  const float fe2_w = swe_visc_flux(p.viscosity, v_c, ca_upp(c, j, i - 1), p.rdx);
+  const float fn2_c = (p.north_wall && j == p.ny - 2) ? 0.f : swe_visc_flux(p.viscosity, ca_vp(c, j + 1, i), upp_c, p.rdy);
+  const float fn2_s = (p.south_wall && j == 1) ? 0.f : swe_visc_flux(p.viscosity, v_c, ca_upp(c, j - 1, i), p.rdy);
+  return swe_apply_div(p, v_c, fe2_c, fe2_w, fn2_c, fn2_s);
+}
+
+// one of this rank's frame cells: u'' -> ua, v'' -> va; ring cells also mirror u', v' into the
+// stale store (what the neighbours see in their halo until the next exchange)
+__device__ __forceinline__ void swe_ca_fric_cell(const CACtx& c, float* __restrict__ ua_out,
+                                                 float* __restrict__ va_out, int j, int i) {
+  const B2SweParams& p = c.p;
+  const size_t off = ca_m(p, j, i);
+  const float upp = ca_upp(c, j, i);
+  ua_out[off] = upp;
+  va_out[off] = ca_vpp(c, j, i, upp);
+  if (j == 1 || j == p.ny - 2 || i == 1 || i == p.nx - 2) {
+    const size_t e = ca_e(c.x, j, i);
+    c.x.upx[e] = c.ub[off];
+    c.x.vpx[e] = c.vb[off];
+  }
+}
+// a neighbour's cell, one or two layers beyond the edge: its u'' (and v'' on layer 1).  Layer 1 is
+// also the main arrays' halo: u, v get the exchanged u', v' there -- stale by this friction step,
+// which is what the reference's in-place update leaves in the halo.
+__device__ __forceinline__ void swe_ca_fric_ext_cell(const CACtx& c, float* __restrict__ ua_out,
+                                                     float* __restrict__ va_out, int j, int i) {
+  const B2SweParams& p = c.p;
+  const float upp = ca_upp(c, j, i);
+  const size_t e = ca_e(c.x, j, i);
+  c.x.uppx[e] = upp;
+  if (j >= 0 && j <= p.ny - 1 && i >= 0 && i <= p.nx - 1) {
+    c.x.vppx[e] = ca_vpp(c, j, i, upp);
+    ua_out[ca_m(p, j, i)] = c.x.upx[e];
+    va_out[ca_m(p, j, i)] = c.x.vpx[e];
+  }
+}
+
+// ---- task enumeration ----------------------------------------------------------------------------
+// Bulk = rows [4, ny-5] x columns [4, cb1): whole float4 groups, no cell within 3 of the edge.
+// Frame = every other interior cell.
+struct CAFrame {
+  int nfull;          // cells in the six full rows
+  int per;            // frame cells per middle row
+  long long total;
+};
+__host__ __device__ inline CAFrame ca_frame(const B2SweParams& p, int cb1) {
+  CAFrame f;
+  f.nfull = 6 * (p.nx - 2);
+  f.per = 3 + (p.nx - 1 - cb1);
+  f.total = (long long)f.nfull + (long long)(p.ny - 8) * f.per;
+  return f;
+}
+__host__ __device__ inline bool ca_frame_cell(const B2SweParams& p, const CAFrame& f, int cb1, long long idx, int& j, int& i) {
+  if (idx >= f.total) return false;
+  if (idx < f.nfull) {
+    const int r = (int)(idx / (p.nx - 2));
+    i = 1 + (int)(idx % (p.nx - 2));
+    j = r < 3 ? 1 + r : (p.ny - 4) + (r - 3);
+  } else {
+    const long long t = idx - f.nfull;
+    const int s = (int)(t % f.per);
+    j = 4 + (int)(t / f.per);
+    i = s < 3 ? 1 + s : cb1 + (s - 3);
+  }
+  return true;
+}
+// the two layers of cells around the interior ("ext ring"): rows -1, 0, ny-1, ny (columns
+// -1 .. nx) and columns -1, 0, nx-1, nx of the rows in between; cells beyond a wall do not exist
+__host__ __device__ inline long long ca_ext_total(const B2SweParams& p) {
+  return 4LL * (p.nx + 2) + 4LL * (p.ny - 2);
+}
+__host__ __device__ inline bool ca_ext_cell(const B2SweParams& p, long long idx, int& j, int& i) {
+  const long long nrow = 4LL * (p.nx + 2);
+  if (idx < nrow) {
+    const int r = (int)(idx / (p.nx + 2));
+    i = -1 + (int)(idx % (p.nx + 2));
+    j = r == 0 ? -1 : r == 1 ? 0 : r == 2 ? p.ny - 1 : p.ny;
+  } else {
+    const long long t = idx - nrow;
+    if (t >= 4LL * (p.ny - 2)) return false;
+    const int s = (int)(t & 3);
+    j = 1 + (int)(t >> 2);
+    i = s == 0 ? -1 : s == 1 ? 0 : s == 2 ? p.nx - 1 : p.nx;
+  }
+  return !ca_wall_row(p, j);
+}
+__host__ __device__ inline long long ca_bulk_tasks(const B2SweParams& p, int cb1) {
+  return (long long)(p.ny - 8) * ((cb1 >> 2) - 1);
+}
+__host__ __device__ inline void ca_bulk_task(const B2SweParams& p, int cb1, long long idx, int& j, int& i0) {
+  const int ng = (cb1 >> 2) - 1;
+  j = 4 + (int)(idx / ng);
+  i0 = (1 + (int)(idx % ng)) << 2;
+}
+
+// ---- exchange geometry -----------------------------------------------------------------------------
+// Element e of the message that LANDS on receiver side `side` (FS_W = it comes from the west
+// neighbour, ...): field f, the sender's cell (js, is), the receiver's cell (jr, ir) and the layer
+// (0 = the main arrays' halo cell).  W / E messages are full height (rows 0 .. ny-1; at a y wall
+// the wall-row values ride along, as in b2_halo.cu), S / N messages cover the interior columns,
+// corner messages are CA_L x CA_L blocks.
+enum { CA_W = 0, CA_E, CA_S, CA_N, CA_SW, CA_SE, CA_NW, CA_NE };
+__host__ __device__ inline int ca_msg_count(int ny, int nx, int side) {
+  if (side <= CA_E) return CA_NF * CA_L * ny;
+  if (side <= CA_N) return CA_NF * CA_L * (nx - 2);
+  return CA_NF * CA_L * CA_L;
+}
+__host__ __device__ inline void ca_msg_elem(int ny, int nx, int side, int e, int& f, int& js, int& is, int& jr,
+                                            int& ir, int& layer) {
+  if (side <= CA_E) {
+    f = e / (CA_L * ny);
+    const int l = (e / ny) % CA_L, j = e % ny;
+    layer = l; js = jr = j;
+    if (side == CA_W) { is = nx - 2 - l; ir = -l; }
+    else              { is = 1 + l;      ir = nx - 1 + l; }
+  } else if (side <= CA_N) {
+    const int n = nx - 2;
+    f = e / (CA_L * n);
+    const int l = (e / n) % CA_L, i = 1 + e % n;
+    layer = l; is = ir = i;
+    if (side == CA_S) { js = ny - 2 - l; jr = -l; }
+    else              { js = 1 + l;      jr = ny - 1 + l; }
+  } else {
+    f = e / (CA_L * CA_L);
+    const int lj = (e / CA_L) % CA_L, li = e % CA_L;
+    layer = lj > li ? lj : li;
+    if (side == CA_SW)      { js = ny - 2 - lj; is = nx - 2 - li; jr = -lj;         ir = -li; }
+    else if (side == CA_SE) { js = ny - 2 - lj; is = 1 + li;      jr = -lj;         ir = nx - 1 + li; }
+    else if (side == CA_NW) { js = 1 + lj;      is = nx - 2 - li; jr = ny - 1 + lj; ir = -li; }
+    else                    { js = 1 + lj;      is = 1 + li;      jr = ny - 1 + lj; ir = nx - 1 + li; }
+  }
+}
+// where element e of the message landing on `side` goes on the receiver: every layer into the ext
+// arrays (W / E messages: interior rows only, the corner rows come from the diagonal neighbours),
+// layer 1 also into the main arrays' halo ([jlo, jhi) = the rows of the halo columns b2_halo.cu fills)
+__host__ __device__ inline void ca_scatter(int ny, int nx, size_t pitch, int epitch, int side, int e, int jlo,
+                                           int jhi, float val, float* const* field, float* const* ext) {
+  int f, js, is, jr, ir, layer;
+  ca_msg_elem(ny, nx, side, e, f, js, is, jr, ir, layer);
+  const size_t eoff = (size_t)(jr + 2) * epitch + (ir + 2);
+  if (side <= CA_E) {
+    if (jr >= 1 && jr <= ny - 2) ext[f][eoff] = val;
+    if (layer == 0 && jr >= jlo && jr < jhi) field[f][(size_t)jr * pitch + ir] = val;
+  } else {
+    ext[f][eoff] = val;
+    if (layer == 0) field[f][(size_t)jr * pitch + ir] = val;
+  }
+}

@@ -90,6 +90,11 @@ class B2SweState(Structure):
                 ("h0", "h1", "u", "v", "dh", "du", "dv", "fe", "fn", "q", "ke", "fe2", "fn2", "u1", "v1")]
 
 
+class B2SweCA(Structure):
+    _fields_ = [(name, c_void_p) for name in ("hx", "upx", "vpx", "uppx", "vppx")] + [
+        ("epitch", c_int), ("cb1", c_int)]
+
+
 class B2StatusRecord(Structure):
     _fields_ = [
         ("source", c_int),
@@ -174,10 +179,6 @@ _SIGNATURES = {
     "b2_swe_friction_u_flux_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 6 + [c_void_p]),
     "b2_swe_friction_u_fused": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 5 + [c_int, c_void_p]),
     "b2_swe_friction_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_void_p]),
-    "b2_swe_multistep_fused": (
-        c_int,
-        [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2HaloDesc), c_int, c_int, c_void_p],
-    ),
     "b2_swe_multistep_k12f": (
         c_int,
         [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2HaloDesc), c_int, c_int, c_void_p],
@@ -185,6 +186,15 @@ _SIGNATURES = {
     "b2_swe_multistep_k12": (
         c_int,
         [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2HaloDesc), c_int, c_int, c_void_p],
+    ),
+    "b2_swe_multistep_ca": (
+        c_int,
+        [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2SweCA), POINTER(B2HaloDesc), c_int, c_int,
+         c_void_p],
+    ),
+    "b2_swe_ca_init": (
+        c_int,
+        [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2SweCA), POINTER(B2HaloDesc), c_void_p],
     ),
     "b2_swe_multistep": (
         c_int,
@@ -194,15 +204,15 @@ _SIGNATURES = {
 
 
 #: must equal B2_ABI_VERSION in csrc/b2_common.h
-ABI_VERSION = 6
+ABI_VERSION = 7
 _ABI_FIELDS = ("abi_version", "sizeof_status_record", "sizeof_halo_desc", "sizeof_swe_params",
-               "sizeof_swe_state", "sizeof_error_record", "max_ranks", "p2p_nslot")
+               "sizeof_swe_state", "sizeof_error_record", "max_ranks", "p2p_nslot", "sizeof_swe_ca")
 
 
 def _abi_expected() -> dict:
     return {"abi_version": ABI_VERSION, "sizeof_status_record": ctypes.sizeof(B2StatusRecord),
             "sizeof_halo_desc": ctypes.sizeof(B2HaloDesc), "sizeof_swe_params": ctypes.sizeof(B2SweParams),
-            "sizeof_swe_state": ctypes.sizeof(B2SweState)}
+            "sizeof_swe_state": ctypes.sizeof(B2SweState), "sizeof_swe_ca": ctypes.sizeof(B2SweCA)}
 
 
 def _abi_native(handle) -> dict:

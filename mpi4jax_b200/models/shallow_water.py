@@ -41,6 +41,7 @@ from .._src.utils import get_default_comm
 ModelState = namedtuple("ModelState", "h, u, v, dh, du, dv")
 
 SUPPORTED_NPROC = (1, 2, 4, 6, 8, 16)
+_EXT_NAMES = ("hx", "upx", "vpx", "uppx", "vppx")
 
 
 @dataclass
@@ -77,7 +78,7 @@ class ShallowWaterConfig:
 class ShallowWaterModel:
     def __init__(self, config: Optional[ShallowWaterConfig] = None, comm: Optional[Comm] = None,
                  device: Optional[torch.device] = None, backend: str = "auto",
-                 fused: Optional[bool] = None, k12: Optional[bool] = None):
+                 k12: Optional[bool] = None, pipeline: Optional[str] = None):
         self.cfg = cfg = config or ShallowWaterConfig()
         self.comm = comm = comm or get_default_comm()
         self.device = torch.device(device) if device is not None else comm.device
@@ -88,17 +89,25 @@ class ShallowWaterModel:
         if backend == "native" and self.device.type != "cuda":
             raise ValueError("backend='native' needs a CUDA device")
         self.backend = backend
-        # k12=True: flux and tendency kernels fused, 21 instead of 32 array passes per step
-        # (csrc/b2_swe_k12.cu).  EXPERIMENTAL: written and host-emulated (tests/
-        # test_swe_host_emulation.py) but not yet measured on hardware; opt-in only.
-        # k12=2 / "full" additionally fuses the friction phase (16 passes).
-        if k12 is None:
-            raw = os.environ.get("MPI4JAX_B200_SWE_K12", "0").strip().lower()
-            k12 = 2 if raw in ("2", "full") else 1 if raw in ("1", "true", "on") else 0
-        self.k12 = 2 if k12 in (2, "full") else int(bool(k12))
-        # fused=True: halo exchange fused into the stencil kernels (csrc/b2_swe_fused.cu);
-        # default is the stand-alone exchange kernel, which currently measures faster (profiles/)
-        self.fused = env_flag("MPI4JAX_B200_SWE_FUSED", False) if fused is None else bool(fused)
+        # Native launch schedules (csrc/):
+        #   "ca"          communication-avoiding step: ONE three-cell-deep exchange per step, the rest
+        #                 recomputed on a thin frame, bulk and frame on two streams (b2_swe_ca.cu);
+        #                 16 array passes per step.  Default.
+        #   "standalone"  4 stencil kernels + 3 fused exchanges, 32 passes (b2_swe.cu): the oracle the
+        #                 other schedules are compared with bit for bit.
+        #   "k12" / "k12f"  three exchanges, flux+tendency (and friction) kernels fused on the bulk.
+        if pipeline is None:
+            pipeline = os.environ.get("MPI4JAX_B200_SWE_PIPELINE", "").strip().lower() or None
+        if pipeline is None and k12 is not None:
+            pipeline = {0: "standalone", 1: "k12", 2: "k12f"}[2 if k12 in (2, "full") else int(bool(k12))]
+        if pipeline is None:
+            raw = os.environ.get("MPI4JAX_B200_SWE_K12", "").strip().lower()
+            pipeline = ("k12f" if raw in ("2", "full") else "k12" if raw in ("1", "true", "on") else
+                        "standalone" if raw in ("0", "false", "off") else "ca")
+        if pipeline not in ("ca", "standalone", "k12", "k12f"):
+            raise ValueError(f"unknown shallow-water pipeline {pipeline!r}")
+        self.pipeline = pipeline
+        self.k12 = {"k12": 1, "k12f": 2}.get(pipeline, 0)
         size, rank = comm.Get_size(), comm.Get_rank()
         if size not in SUPPORTED_NPROC:
             raise RuntimeError(
@@ -198,6 +207,15 @@ class ShallowWaterModel:
             t.periodic_x = int(self.cfg.periodic_x)
             t.at_east_wall, t.at_north_wall = int(self.at_east_wall), int(self.at_north_wall)
             t.ny, t.nx, t.pitch = self.ny_local, self.nx_local, self.pitch
+            # "ext" arrays of the communication-avoiding step: what lies beyond the 1-cell halo
+            # (csrc/b2_swe_ca_body.cuh); only their outer cells are ever touched
+            self._epitch = self.nx_local + 4
+            self._ext = {name: torch.zeros((self.ny_local + 4, self._epitch), dtype=torch.float32, device=self.device)
+                         for name in _EXT_NAMES}
+            ca = self._ca = native.B2SweCA()
+            for name in _EXT_NAMES:
+                setattr(ca, name, self._ext[name].data_ptr())
+            ca.epitch, ca.cb1 = self._epitch, 0
 
     def initial_conditions_global(self):
         """Global (ny_global, nx_global) float32 fields of the balanced jet + perturbation
@@ -231,15 +249,49 @@ class ShallowWaterModel:
         self.steps_done = 0
 
     def _sync_partners(self) -> None:
-        """Ping-pong partners start as copies: identical wall rows / halos that no kernel writes."""
+        """Ping-pong partners start as copies: identical wall rows / halos that no kernel writes.
+        The communication-avoiding schedule also (re)derives its ext arrays from the main ones
+        (collective): the neighbours' cells beyond the halo, taken as not yet touched by a
+        friction step -- exact for an initial state, see :meth:`load_state` otherwise."""
         self._h1.copy_(self.h)
         self._u1.copy_(self.u)
         self._v1.copy_(self.v)
+        if self.backend == "native" and self.pipeline == "ca":
+            nc = self.comm._native_comm()
+            rc = native.lib.b2_swe_ca_init(
+                nc.handle, ctypes.byref(self._params), ctypes.byref(self._state), ctypes.byref(self._ca),
+                ctypes.byref(self._topo), torch.cuda.current_stream().cuda_stream)
+            nc._check(rc, "Halo")
 
-    def load_state(self, state: ModelState) -> None:
-        """Overwrite the prognostic fields (e.g. from pinned host memory, non-blocking)."""
+    def load_state(self, state: ModelState, ext: Optional[dict] = None) -> None:
+        """Overwrite the prognostic fields (e.g. from pinned host memory, non-blocking).
+
+        ``ext`` (from :meth:`ext_state`) restores the communication-avoiding schedule's frame
+        storage as well, which makes the continuation bit-identical to the uninterrupted run.
+        Without it the frame storage is re-derived from ``state`` as for an initial condition
+        (collective): the neighbours' u, v next to the block edge are then taken as fresh instead of
+        stale by one friction increment -- a rounding-level difference confined to the first step."""
         for dst, src in zip((self.h, self.u, self.v, self.dh, self.du, self.dv), state):
             dst.copy_(src, non_blocking=True)
+        if self.backend == "native" and self.pipeline == "ca":
+            self._sync_partners()
+            if ext is not None:
+                for name in _EXT_NAMES:
+                    self._ext_put(name, ext[name])
+
+    # the frame storage as four strips per array (rows / columns within 4 cells of the array edge)
+    def ext_state(self) -> Optional[dict]:
+        if not (self.backend == "native" and self.pipeline == "ca"):
+            return None
+        return {name: [a[:4].clone(), a[-4:].clone(), a[:, :4].clone(), a[:, -4:].clone()]
+                for name, a in self._ext.items()}
+
+    def _ext_put(self, name: str, strips) -> None:
+        a = self._ext[name]
+        a[:4].copy_(strips[0], non_blocking=True)
+        a[-4:].copy_(strips[1], non_blocking=True)
+        a[:, :4].copy_(strips[2], non_blocking=True)
+        a[:, -4:].copy_(strips[3], non_blocking=True)
 
     @property
     def state(self) -> ModelState:
@@ -295,13 +347,16 @@ class ShallowWaterModel:
             first_step = self.steps_done == 0
         if self.backend == "native":
             nc = self.comm._native_comm()
-            fn = (native.lib.b2_swe_multistep_fused if self.fused else
-                  native.lib.b2_swe_multistep_k12f if self.k12 == 2 else
-                  native.lib.b2_swe_multistep_k12 if self.k12 else native.lib.b2_swe_multistep)
-            rc = fn(
-                nc.handle, ctypes.byref(self._params), ctypes.byref(self._state),
-                ctypes.byref(self._topo), int(nsteps), int(bool(first_step)),
-                torch.cuda.current_stream().cuda_stream)
+            stream = torch.cuda.current_stream().cuda_stream
+            if self.pipeline == "ca":
+                rc = native.lib.b2_swe_multistep_ca(
+                    nc.handle, ctypes.byref(self._params), ctypes.byref(self._state), ctypes.byref(self._ca),
+                    ctypes.byref(self._topo), int(nsteps), int(bool(first_step)), stream)
+            else:
+                fn = (native.lib.b2_swe_multistep_k12f if self.k12 == 2 else
+                      native.lib.b2_swe_multistep_k12 if self.k12 else native.lib.b2_swe_multistep)
+                rc = fn(nc.handle, ctypes.byref(self._params), ctypes.byref(self._state),
+                        ctypes.byref(self._topo), int(nsteps), int(bool(first_step)), stream)
             nc._check(rc, "Halo")
         else:
             for it in range(nsteps):
@@ -402,6 +457,9 @@ class ShallowWaterModel:
         path = os.path.join(directory, f"rank{self.comm.Get_rank():04d}.pt")
         payload = {"meta": self._checkpoint_meta(), "steps_done": int(self.steps_done),
                    "state": {k: t.detach().to("cpu", copy=True) for k, t in self.state._asdict().items()}}
+        ext = self.ext_state()
+        if ext is not None:
+            payload["ext"] = {k: [t.cpu() for t in v] for k, v in ext.items()}
         torch.save(payload, path + ".tmp")
         os.replace(path + ".tmp", path)
         _ops.barrier(comm=self.comm)
@@ -420,8 +478,9 @@ class ShallowWaterModel:
         bad = {k: (have.get(k), v) for k, v in want.items() if have.get(k) != v}
         if bad:
             raise ValueError(f"checkpoint {path} does not match this model (checkpoint, model): {bad}")
-        self.load_state(ModelState(**payload["state"]))
-        self._sync_partners()
+        self.load_state(ModelState(**payload["state"]), ext=payload.get("ext"))
+        if not (self.backend == "native" and self.pipeline == "ca"):
+            self._sync_partners()
         self.steps_done = int(payload["steps_done"])
         return self.steps_done
 

@@ -15,7 +15,7 @@ static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c);
 struct FakeIdx { unsigned x; };
 static FakeIdx blockIdx, threadIdx;
 
-#include "b2_swe_k12_body.cuh"
+#include "b2_swe_ca_body.cuh"
 
 static void masks(const B2SweParams& p, int i0, bool m[4]) {
   for (int k = 0; k < 4; ++k) m[k] = (i0 + k >= 1) && (i0 + k <= p.nx - 2);
@@ -187,6 +187,112 @@ long long emu_frame_marks(const B2SweParams* p, int w, int* marks) {
     if (swe_frame_task(*p, f, t, j, i0, m)) marks[j * f.ngroups + (i0 >> 2)] += 1;
   }
   return f.total;
+}
+
+// ---- communication-avoiding step (csrc/b2_swe_ca_body.cuh): the kernels of b2_swe_ca.cu as loops ----
+// `reverse` walks the tasks backwards: a kernel whose threads only read what no thread of the same
+// launch writes gives the same bits in any order.
+static CACtx make_ctx(const B2SweParams* p, const B2SweCA* x, const float* h, const float* ua, const float* va,
+                      float* hn, float* ub, float* vb, float* dh, float* du, float* dv) {
+  CACtx c;
+  c.p = *p; c.x = *x; c.x.cb1 = swe_ca_cb1(*p);
+  c.h = h; c.ua = ua; c.va = va; c.hn = hn; c.ub = ub; c.vb = vb; c.dh = dh; c.du = du; c.dv = dv;
+  return c;
+}
+
+int emu_ca_supported(const B2SweParams* p) { return swe_ca_supported(*p) ? 1 : 0; }
+int emu_ca_cb1(const B2SweParams* p) { return swe_ca_cb1(*p); }
+
+void emu_ca_tend_frame(const B2SweParams* p, const B2SweCA* x, const float* h, const float* ua, const float* va,
+                       float* hn, float* ub, float* vb, float* dh, float* du, float* dv, int reverse) {
+  const CACtx c = make_ctx(p, x, h, ua, va, hn, ub, vb, dh, du, dv);
+  const CAFrame f = ca_frame(c.p, c.x.cb1);
+  for (long long k = 0; k < f.total; ++k) {
+    int j, i;
+    if (ca_frame_cell(c.p, f, c.x.cb1, reverse ? f.total - 1 - k : k, j, i)) swe_ca_tend_cell(c, j, i);
+  }
+}
+
+void emu_ca_fric_frame(const B2SweParams* p, const B2SweCA* x, float* ub, float* vb, float* ua_out, float* va_out,
+                       int reverse) {
+  const CACtx c = make_ctx(p, x, nullptr, nullptr, nullptr, nullptr, ub, vb, nullptr, nullptr, nullptr);
+  const CAFrame f = ca_frame(c.p, c.x.cb1);
+  const long long n = f.total + ca_ext_total(c.p);
+  for (long long k = 0; k < n; ++k) {
+    const long long t = reverse ? n - 1 - k : k;
+    int j, i;
+    if (t < f.total) {
+      ca_frame_cell(c.p, f, c.x.cb1, t, j, i);
+      swe_ca_fric_cell(c, ua_out, va_out, j, i);
+    } else if (ca_ext_cell(c.p, t - f.total, j, i)) {
+      swe_ca_fric_ext_cell(c, ua_out, va_out, j, i);
+    }
+  }
+}
+
+void emu_ca_bulk_k12(const B2SweParams* p, const float* h, float* h_new, const float* u, float* u_new,
+                     const float* v, float* v_new, float* dh, float* du, float* dv) {
+  const int cb1 = swe_ca_cb1(*p);
+  const bool m[4] = {true, true, true, true};
+  for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
+    int j, i0;
+    ca_bulk_task(*p, cb1, t, j, i0);
+    swe_k12_body(*p, h, h_new, u, u_new, v, v_new, dh, du, dv, j, i0, m);
+  }
+}
+
+void emu_ca_bulk_fric(const B2SweParams* p, const float* u, float* u_new, const float* v, float* v_new) {
+  const int cb1 = swe_ca_cb1(*p);
+  for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
+    int j, i0;
+    ca_bulk_task(*p, cb1, t, j, i0);
+    swe_k345_body(*p, u, u_new, v, v_new, j, i0, true);
+  }
+}
+
+// which interior cells do the bulk and frame enumerations cover?  marks[j * nx + i]: +1 frame, +16 bulk
+void emu_ca_marks(const B2SweParams* p, int* marks) {
+  const int cb1 = swe_ca_cb1(*p);
+  const CAFrame f = ca_frame(*p, cb1);
+  for (long long t = 0; t < f.total; ++t) {
+    int j, i;
+    if (ca_frame_cell(*p, f, cb1, t, j, i)) marks[j * p->nx + i] += 1;
+  }
+  for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
+    int j, i0;
+    ca_bulk_task(*p, cb1, t, j, i0);
+    for (int k = 0; k < 4; ++k) marks[j * p->nx + i0 + k] += 16;
+  }
+}
+
+// the message that lands on `side` of the receiver: read from the sender's arrays exactly as the push
+// loop of b2_k_halo_ca does, scattered exactly as its poll loop does (no transport in between)
+void emu_ca_deliver(int ny, int nx, int pitch, int epitch, int side, int recv_has_south, int recv_has_north,
+                    float* const* send_field, float* const* recv_field, float* const* recv_ext) {
+  const int jlo = recv_has_south ? 1 : 0, jhi = recv_has_north ? ny - 1 : ny;
+  for (int e = 0; e < ca_msg_count(ny, nx, side); ++e) {
+    int f, js, is, jr, ir, layer;
+    ca_msg_elem(ny, nx, side, e, f, js, is, jr, ir, layer);
+    ca_scatter(ny, nx, (size_t)pitch, epitch, side, e, jlo, jhi, send_field[f][(size_t)js * pitch + is], recv_field,
+               recv_ext);
+  }
+}
+
+// swe_ca_init_ext
+void emu_ca_init_ext(const B2SweParams* p, const B2SweCA* x, const float* u, const float* v) {
+  int j, i;
+  for (long long t = 0; t < ca_ext_total(*p); ++t)
+    if (ca_ext_cell(*p, t, j, i)) {
+      const size_t e = ca_e(*x, j, i);
+      x->uppx[e] = x->upx[e];
+      x->vppx[e] = x->vpx[e];
+    }
+  for (j = 1; j <= p->ny - 2; ++j)
+    for (i = 1; i <= p->nx - 2; ++i)
+      if (j == 1 || j == p->ny - 2 || i == 1 || i == p->nx - 2) {
+        x->upx[ca_e(*x, j, i)] = u[ca_m(*p, j, i)];
+        x->vpx[ca_e(*x, j, i)] = v[ca_m(*p, j, i)];
+      }
 }
 
 }  // extern "C"

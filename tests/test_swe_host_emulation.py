@@ -383,3 +383,118 @@ def test_emulated_fully_fused_pipeline_matches_standalone_pipeline(emu, grid):
             assert np.isfinite(rb[name]).all(), name
             tol = 5e-5 if name in ("h", "u", "v") else 1e-3
             assert _close(rb[name][1:-1, 1:-1], ra[name][1:-1, 1:-1], tol), (grid, name)
+
+
+# ---- communication-avoiding step (csrc/b2_swe_ca_body.cuh, b2_swe_ca.cu) -----------------------------
+class CAExt(ctypes.Structure):        # B2SweCA (csrc/b2_swe_body.cuh)
+    _fields_ = [(n, ctypes.c_void_p) for n in ("hx", "upx", "vpx", "uppx", "vppx")] + [
+        ("epitch", ctypes.c_int), ("cb1", ctypes.c_int)]
+
+
+_SIDES = ("w", "e", "s", "n", "sw", "se", "nw", "ne")        # CA_W .. CA_NE: where a message lands
+
+
+def _neighbours(r, PY, PX):
+    py, px = divmod(r, PX)
+
+    def at(dy_, dx_):
+        iy = py + dy_
+        return None if not 0 <= iy < PY else iy * PX + (px + dx_) % PX
+
+    return dict(w=at(0, -1), e=at(0, 1), s=at(-1, 0), n=at(1, 0), sw=at(-1, -1), se=at(-1, 1), nw=at(1, -1),
+                ne=at(1, 1))
+
+
+def _ca_exchange(emu, ranks, names, ny, nx, pitch, epitch, PY, PX):
+    """b2_k_halo_ca without the transport: every message read from the sender's arrays as the push loop
+    does and scattered as the poll loop does."""
+    F3 = ctypes.c_void_p * 3
+    for r, blk in enumerate(ranks):
+        nb = _neighbours(r, PY, PX)
+        for side, key in enumerate(_SIDES):
+            q = nb[key]
+            if q is None:
+                continue
+            send = F3(*[ranks[q][n].ctypes.data for n in names])
+            recv = F3(*[blk[n].ctypes.data for n in names])
+            ext = F3(blk["hx"].ctypes.data, blk["upx"].ctypes.data, blk["vpx"].ctypes.data)
+            emu.emu_ca_deliver(ny, nx, pitch, epitch, side, int(nb["s"] is not None), int(nb["n"] is not None),
+                               send, recv, ext)
+
+
+def _ca_ext(blk, epitch):
+    return CAExt(hx=blk["hx"].ctypes.data, upx=blk["upx"].ctypes.data, vpx=blk["vpx"].ctypes.data,
+                 uppx=blk["uppx"].ctypes.data, vppx=blk["vppx"].ctypes.data, epitch=epitch, cb1=0)
+
+
+def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0):
+    """The launch sequence of b2_swe_multistep_ca on a process grid (messages are read before any
+    rank scatters: all sends of a step come from h', u', v' frame cells, which no message writes)."""
+    from ._halo_sim import new_exchange
+
+    ranks, ny, nx, pitch = _blocks(model, PY, PX)
+    epitch = nx + 4
+    for name, kind in (("h", "h"), ("u", "u"), ("v", "v")):
+        new_exchange([r[name][:, :nx] for r in ranks], PY, PX, kind)
+    for r in ranks:
+        r["h1"][:], r["u1"][:], r["v1"][:] = r["h"], r["u"], r["v"]
+        for n in ("hx", "upx", "vpx", "uppx", "vppx"):
+            r[n] = np.full((ny + 4, epitch), np.nan, np.float32)     # NaN = never delivered / computed
+    B = ctypes.byref
+    _ca_exchange(emu, ranks, ("h", "u", "v"), ny, nx, pitch, epitch, PY, PX)       # b2_swe_ca_init
+    for i, r in enumerate(ranks):
+        p = _params(model, r, ny, nx, pitch, i // PX, PY, True)
+        x = _ca_ext(r, epitch)
+        emu.emu_ca_init_ext(B(p), B(x), _ptr(r["u"]), _ptr(r["v"]))
+    hk, hnk = "h", "h1"
+    for it in range(nsteps):
+        ps = [_params(model, r, ny, nx, pitch, i // PX, PY, it == 0) for i, r in enumerate(ranks)]
+        xs = [_ca_ext(r, epitch) for r in ranks]
+        for r, p, x in zip(ranks, ps, xs):
+            emu.emu_ca_tend_frame(B(p), B(x), _ptr(r[hk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r[hnk]), _ptr(r["u1"]),
+                                  _ptr(r["v1"]), _ptr(r["dh"]), _ptr(r["du"]), _ptr(r["dv"]), reverse)
+            emu.emu_ca_bulk_k12(B(p), _ptr(r[hk]), _ptr(r[hnk]), _ptr(r["u"]), _ptr(r["u1"]), _ptr(r["v"]),
+                                _ptr(r["v1"]), _ptr(r["dh"]), _ptr(r["du"]), _ptr(r["dv"]))
+        _ca_exchange(emu, ranks, (hnk, "u1", "v1"), ny, nx, pitch, epitch, PY, PX)
+        for r, p, x in zip(ranks, ps, xs):
+            emu.emu_ca_bulk_fric(B(p), _ptr(r["u1"]), _ptr(r["u"]), _ptr(r["v1"]), _ptr(r["v"]))
+            emu.emu_ca_fric_frame(B(p), B(x), _ptr(r["u1"]), _ptr(r["v1"]), _ptr(r["u"]), _ptr(r["v"]), reverse)
+        hk, hnk = hnk, hk
+    return [dict(h=r[hk][:, :nx], u=r["u"][:, :nx], v=r["v"][:, :nx], dh=r["dh"][:, :nx], du=r["du"][:, :nx],
+                 dv=r["dv"][:, :nx]) for r in ranks]
+
+
+@pytest.mark.parametrize("shape", [(12, 16), (26, 50), (13, 21), (40, 19), (31, 64)])
+def test_ca_bulk_and_frame_partition_the_interior(emu, shape):
+    ny, nx = shape
+    p, *_ = _setup(ny, nx, False, 0, 0)
+    assert emu.emu_ca_supported(ctypes.byref(p)) == 1
+    marks = np.zeros((ny, nx), np.int32)
+    emu.emu_ca_marks(ctypes.byref(p), marks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert (marks[1:-1, 1:-1] != 0).all() and set(np.unique(marks[1:-1, 1:-1])) <= {1, 16}   # exactly one owner
+    assert marks[0].sum() == marks[-1].sum() == marks[:, 0].sum() == marks[:, -1].sum() == 0
+    bulk = marks == 16
+    jj, ii = np.nonzero(bulk)
+    assert jj.min() >= 4 and jj.max() <= ny - 5 and ii.min() >= 4 and ii.max() <= nx - 5     # >= 3 cells from the edge
+
+
+@pytest.mark.parametrize("grid", [(1, 1), (2, 1), (1, 2), (2, 2), (3, 2), (2, 4)])
+def test_emulated_ca_pipeline_is_bit_identical_to_the_standalone_pipeline(emu, grid):
+    """One deep exchange per step + local recomputation (frame kernels with owner views) vs the three
+    exchanges of b2_swe_multistep, same decomposition: the same bits, walls, periodic wrap and the
+    reference's stale u / v halos included."""
+    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
+
+    PY, PX = grid
+    model = ShallowWaterModel(ShallowWaterConfig(nx=48 * PX, ny=24 * PY), device="cpu", backend="ops")
+    a = _emulate(emu, model, PY, PX, 6, k12=False)
+    b = _emulate_ca(emu, model, PY, PX, 6)
+    c = _emulate_ca(emu, model, PY, PX, 6, reverse=1)
+    for ra, rb, rc in zip(a, b, c):
+        for name in ra:
+            assert np.isfinite(rb[name][1:-1, 1:-1]).all(), (grid, name)
+            assert np.array_equal(ra[name][1:-1, 1:-1], rb[name][1:-1, 1:-1]), (grid, name)
+            assert np.array_equal(rb[name][1:-1, 1:-1], rc[name][1:-1, 1:-1]), (grid, name, "task order")
+            # the main arrays' halos as well (h fresh; u, v stale by the friction step)
+            if name in ("h", "u", "v"):
+                assert np.array_equal(ra[name], rb[name]), (grid, name, "halo")
