@@ -43,8 +43,7 @@ swe_k1_fluxes(B2SweParams p, const float* __restrict__ h, const float* __restric
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
-  SweOut4 o;
-  swe_k1_body(p, h, u, v, fe, fn, q, ke, j, i0, m, o);
+  swe_k1_body(p, h, u, v, fe, fn, q, ke, j, i0, m);
 }
 
 __global__ void __launch_bounds__(SWE_THREADS, 3)
@@ -57,30 +56,7 @@ swe_k2_tendencies(B2SweParams p, const float* __restrict__ h, float* __restrict_
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
-  SweOut4 o;
-  swe_k2_body(p, h, h_new, u, v, dh, du, dv, fe, fn, q, ke, j, i0, m, o);
-}
-
-__global__ void __launch_bounds__(SWE_THREADS)
-swe_k3_friction_flux_u(B2SweParams p, const float* __restrict__ u, float* __restrict__ fe,
-                       float* __restrict__ fn, int local_halo, int has_south) {
-  b2_pdl_enter();
-  int j, i0;
-  bool m[4];
-  if (!swe_map(p, j, i0, m)) return;
-  swe_k3_body(p, u, fe, fn, j, i0, m, local_halo != 0, has_south != 0);
-}
-
-__global__ void __launch_bounds__(SWE_THREADS)
-swe_k4_friction_u_flux_v(B2SweParams p, float* __restrict__ u, const float* __restrict__ v,
-                         const float* __restrict__ fe, const float* __restrict__ fn,
-                         float* __restrict__ fe2, float* __restrict__ fn2) {
-  b2_pdl_enter();
-  int j, i0;
-  bool m[4];
-  if (!swe_map(p, j, i0, m)) return;
-  SweOut4 o;
-  swe_k4_body(p, u, v, fe, fn, fe2, fn2, j, i0, m, o);
+  swe_k2_body(p, h, h_new, u, v, dh, du, dv, fe, fn, q, ke, j, i0, m);
 }
 
 __global__ void __launch_bounds__(SWE_THREADS)
@@ -91,8 +67,7 @@ swe_k34_friction_u(B2SweParams p, const float* __restrict__ u, float* __restrict
   int j, i0;
   bool m[4];
   if (!swe_map(p, j, i0, m)) return;
-  SweOut4 o;
-  swe_k34_body(p, u, u_new, v, fe2, fn2, j, i0, m, has_south != 0, o);
+  swe_k34_body(p, u, u_new, v, fe2, fn2, j, i0, m, has_south != 0);
 }
 
 __global__ void __launch_bounds__(SWE_THREADS)
@@ -129,16 +104,14 @@ static int swe_check(const B2SweParams* p) {
   return 0;
 }
 
-extern "C" {
-
-int b2_swe_fluxes(B2Comm* c, const B2SweParams* p, const float* h, const float* u, const float* v,
+static int b2_swe_fluxes(B2Comm* c, const B2SweParams* p, const float* h, const float* u, const float* v,
                   float* fe, float* fn, float* q, float* ke, cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
   b2_launch(swe_k1_fluxes, swe_blocks(p), SWE_THREADS, 0, s, *p, h, u, v, fe, fn, q, ke);
   return swe_done(c, "swe_fluxes");
 }
 
-int b2_swe_tendencies(B2Comm* c, const B2SweParams* p, const float* h, float* h_new, float* u,
+static int b2_swe_tendencies(B2Comm* c, const B2SweParams* p, const float* h, float* h_new, float* u,
                       float* v, float* dh, float* du, float* dv, const float* fe, const float* fn,
                       const float* q, const float* ke, cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
@@ -146,27 +119,9 @@ int b2_swe_tendencies(B2Comm* c, const B2SweParams* p, const float* h, float* h_
   return swe_done(c, "swe_tendencies");
 }
 
-// local_halo != 0: also fill the west halo column of fe and (if has_south) the south halo row of
-// fn from this rank's own u halo -- the only halo cells of (fe, fn) the next kernel reads -- so
-// that no exchange of (fe, fn) is needed (bit-identical values, see b2_swe_body.cuh).
-int b2_swe_friction_flux_u(B2Comm* c, const B2SweParams* p, const float* u, float* fe, float* fn,
-                           int local_halo, int has_south, cudaStream_t s) {
-  if (int rc = swe_check(p)) return rc;
-  b2_launch(swe_k3_friction_flux_u, swe_blocks(p), SWE_THREADS, 0, s, *p, u, fe, fn, local_halo, has_south);
-  return swe_done(c, "swe_friction_flux_u");
-}
-
-int b2_swe_friction_u_flux_v(B2Comm* c, const B2SweParams* p, float* u, const float* v,
-                             const float* fe, const float* fn, float* fe2, float* fn2,
-                             cudaStream_t s) {
-  if (int rc = swe_check(p)) return rc;
-  b2_launch(swe_k4_friction_u_flux_v, swe_blocks(p), SWE_THREADS, 0, s, *p, u, v, fe, fn, fe2, fn2);
-  return swe_done(c, "swe_friction_u_flux_v");
-}
-
 // friction-u flux + apply + friction-v flux in one kernel (no fe/fn round trip through HBM)
 // (u -> u_new: out of place, u_new must not alias u)
-int b2_swe_friction_u_fused(B2Comm* c, const B2SweParams* p, const float* u, float* u_new,
+static int b2_swe_friction_u_fused(B2Comm* c, const B2SweParams* p, const float* u, float* u_new,
                             const float* v, float* fe2, float* fn2, int has_south, cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
   if (u == u_new) {
@@ -177,12 +132,14 @@ int b2_swe_friction_u_fused(B2Comm* c, const B2SweParams* p, const float* u, flo
   return swe_done(c, "swe_friction_u_fused");
 }
 
-int b2_swe_friction_v(B2Comm* c, const B2SweParams* p, float* v, const float* fe2, const float* fn2,
+static int b2_swe_friction_v(B2Comm* c, const B2SweParams* p, float* v, const float* fe2, const float* fn2,
                       cudaStream_t s) {
   if (int rc = swe_check(p)) return rc;
   b2_launch(swe_k5_friction_v, swe_blocks(p), SWE_THREADS, 0, s, *p, v, fe2, fn2);
   return swe_done(c, "swe_friction_v");
 }
+
+extern "C" {
 
 // One call = `nsteps` model steps (4 stencil launches + 3 fused halo exchanges each), all
 // enqueued on `s` without touching the host again: the whole time loop of the reference's

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(CA_THREADS) swe_ca_init_ext(const B2SweParams 
 }
 
 // ---- bulk kernels: the vectorised bodies of b2_swe_k12_body.cuh on whole groups -------------------
-__global__ void __launch_bounds__(SWE_THREADS, 2)
+template <int OCC>
+__global__ void __launch_bounds__(SWE_THREADS, OCC)
 swe_ca_bulk_k12(const B2SweParams p, const int cb1, const float* __restrict__ h, float* __restrict__ h_new,
                 const float* __restrict__ u, float* __restrict__ u_new, const float* __restrict__ v,
                 float* __restrict__ v_new, float* __restrict__ dh, float* __restrict__ du,
@@ -85,18 +86,17 @@ swe_ca_bulk_k12(const B2SweParams p, const int cb1, const float* __restrict__ h,
   if (t >= ca_bulk_tasks(p, cb1)) return;
   int j, i0;
   ca_bulk_task(p, cb1, t, j, i0);
-  const bool m[4] = {true, true, true, true};
-  swe_k12_body(p, h, h_new, u, u_new, v, v_new, dh, du, dv, j, i0, m);
+  swe_k12_body(p, h, h_new, u, u_new, v, v_new, dh, du, dv, j, i0);
 }
 
-__global__ void __launch_bounds__(SWE_THREADS, 2)
+__global__ void __launch_bounds__(SWE_THREADS, 4)
 swe_ca_bulk_fric(const B2SweParams p, const int cb1, const float* __restrict__ u, float* __restrict__ u_new,
                  const float* __restrict__ v, float* __restrict__ v_new) {
   const long long t = (long long)blockIdx.x * SWE_THREADS + threadIdx.x;
   if (t >= ca_bulk_tasks(p, cb1)) return;
   int j, i0;
   ca_bulk_task(p, cb1, t, j, i0);
-  swe_k345_body(p, u, u_new, v, v_new, j, i0, true);
+  swe_k345_body(p, u, u_new, v, v_new, j, i0);
 }
 
 // ---- X: three layers of (h', u', v') to all eight neighbours, flag-in-data (b2_halo_ll.cuh) -----
@@ -270,6 +270,11 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
   const unsigned bulk_blocks = ca_blocks(ca_bulk_tasks(p, x.cb1), SWE_THREADS);
   const unsigned frame_blocks = ca_blocks(f.total, CA_THREADS);
   const unsigned fric_blocks = ca_blocks(f.total + ca_ext_total(p), CA_THREADS);
+  static int k12_occ = 0;       // resident CTAs per SM the flux+tendency kernel is compiled for (2: 92 regs; 3: 84)
+  if (k12_occ == 0) {
+    const char* e = getenv("MPI4JAX_B200_SWE_K12_OCC");
+    k12_occ = (e && e[0] == '2') ? 2 : 3;
+  }
   int rc = 0;
 #define CA_RT(call)                                                              \
   if (rc == 0) {                                                                 \
@@ -294,8 +299,12 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
     if ((rc = ca_done(c, "swe_ca_tend_frame"))) break;
     CA_RT(cudaEventRecord(eA, s2));
     // bulk: tendencies
-    swe_ca_bulk_k12<<<bulk_blocks, SWE_THREADS, 0, s>>>(p, x.cb1, h, hn, st->u, st->u1, st->v, st->v1, st->dh,
-                                                        st->du, st->dv);
+    if (k12_occ == 3)
+      swe_ca_bulk_k12<3><<<bulk_blocks, SWE_THREADS, 0, s>>>(p, x.cb1, h, hn, st->u, st->u1, st->v, st->v1, st->dh,
+                                                             st->du, st->dv);
+    else
+      swe_ca_bulk_k12<2><<<bulk_blocks, SWE_THREADS, 0, s>>>(p, x.cb1, h, hn, st->u, st->u1, st->v, st->v1, st->dh,
+                                                             st->du, st->dv);
     if ((rc = ca_done(c, "swe_ca_bulk_k12"))) break;
     CA_RT(cudaEventRecord(eB, s));
     // frame: the step's only exchange

@@ -69,46 +69,67 @@ __host__ __device__ __forceinline__ bool ca_mine(const B2SweParams& p, int j, in
 }
 
 // ---- accessors -------------------------------------------------------------------------------
+// Straight-line code: every accessor SELECTS an address and issues one load, rows beyond a wall are
+// clamped into the main arrays (their values are never used: the wall rules zero what they feed).
+// No branch separates the ~100 loads of a frame cell, so they are all in flight together -- the
+// frame kernels are on the step's critical path and pure latency.
+__device__ __forceinline__ size_t ca_m_safe(const B2SweParams& p, int j, int i) {
+  const int jj = j < 0 ? 0 : (j > p.ny - 1 ? p.ny - 1 : j), ii = i < 0 ? 0 : (i > p.nx - 1 ? p.nx - 1 : i);
+  return (size_t)jj * p.pitch + ii;
+}
 __device__ __forceinline__ float ca_h(const CACtx& c, int j, int i) {
-  if (ca_mine(c.p, j, i) || ca_wall_row(c.p, j)) return c.h[ca_m(c.p, j, i)];
-  return c.x.hx[ca_e(c.x, j, i)];
+  const bool main = ca_mine(c.p, j, i) || ca_wall_row(c.p, j);
+  const float* ptr = main ? c.h + ca_m_safe(c.p, j, i) : c.x.hx + ca_e(c.x, j, i);
+  return *ptr;
 }
 // u as cell-owner Q = (qj, qi) sees it at cell (j, i): fresh where Q owns the cell, stale elsewhere
 __device__ __forceinline__ float ca_vu(const CACtx& c, int qj, int qi, int j, int i) {
-  if (ca_wall_row(c.p, j)) return c.ua[ca_m(c.p, j, i)];
   const int rj = ca_rj(c.p, j), ri = ca_ri(c.p, i);
-  if (rj == qj && ri == qi) return (rj == 0 && ri == 0) ? c.ua[ca_m(c.p, j, i)] : c.x.uppx[ca_e(c.x, j, i)];
-  return c.x.upx[ca_e(c.x, j, i)];
+  const bool own = rj == qj && ri == qi, mine = rj == 0 && ri == 0;
+  const float* ext = own ? c.x.uppx : c.x.upx;
+  const float* ptr = (ca_wall_row(c.p, j) || (own && mine)) ? c.ua + ca_m_safe(c.p, j, i) : ext + ca_e(c.x, j, i);
+  return *ptr;
 }
 __device__ __forceinline__ float ca_vv(const CACtx& c, int qj, int qi, int j, int i) {
-  if (ca_wall_row(c.p, j)) return c.va[ca_m(c.p, j, i)];
   const int rj = ca_rj(c.p, j), ri = ca_ri(c.p, i);
-  if (rj == qj && ri == qi) return (rj == 0 && ri == 0) ? c.va[ca_m(c.p, j, i)] : c.x.vppx[ca_e(c.x, j, i)];
-  return c.x.vpx[ca_e(c.x, j, i)];
+  const bool own = rj == qj && ri == qi, mine = rj == 0 && ri == 0;
+  const float* ext = own ? c.x.vppx : c.x.vpx;
+  const float* ptr = (ca_wall_row(c.p, j) || (own && mine)) ? c.va + ca_m_safe(c.p, j, i) : ext + ca_e(c.x, j, i);
+  return *ptr;
 }
 
 // ---- the four flux-kernel quantities at cell (j, i) in [0, ny) x [0, nx), evaluated as the
-// cell's owner does (swe_k1_body's expressions; zero beyond a wall, where nothing is ever stored)
-__device__ __forceinline__ float ca_fe(const CACtx& c, int j, int i) {
-  if (ca_wall_row(c.p, j)) return 0.f;
+// cell's owner does (swe_k1_body's expressions; zero beyond a wall, where nothing is ever stored:
+// such a cell is evaluated at the clamped row and the result discarded)
+__device__ __forceinline__ int ca_flux_row(const B2SweParams& p, int j) {
+  return ca_wall_row(p, j) ? (j < 1 ? 1 : p.ny - 2) : j;
+}
+__device__ __forceinline__ float ca_fe(const CACtx& c, int j0, int i) {
+  const int j = ca_flux_row(c.p, j0);
   const int qj = ca_rj(c.p, j), qi = ca_ri(c.p, i), hj = hc_row(c.p, j);
-  return swe_fe(ca_h(c, hj, i), ca_h(c, hj, i + 1), ca_vu(c, qj, qi, j, i));
+  const float r = swe_fe(ca_h(c, hj, i), ca_h(c, hj, i + 1), ca_vu(c, qj, qi, j, i));
+  return ca_wall_row(c.p, j0) ? 0.f : r;
 }
-__device__ __forceinline__ float ca_fn(const CACtx& c, int j, int i) {
-  if (ca_wall_row(c.p, j) || (c.p.north_wall && j == c.p.ny - 2)) return 0.f;      // "v" wall rule
+__device__ __forceinline__ float ca_fn(const CACtx& c, int j0, int i) {
+  const int j = ca_flux_row(c.p, j0);
   const int qj = ca_rj(c.p, j), qi = ca_ri(c.p, i);
-  return swe_fn(ca_h(c, hc_row(c.p, j), i), ca_h(c, hc_row(c.p, j + 1), i), ca_vv(c, qj, qi, j, i));
+  const float r = swe_fn(ca_h(c, hc_row(c.p, j), i), ca_h(c, hc_row(c.p, j + 1), i), ca_vv(c, qj, qi, j, i));
+  return (ca_wall_row(c.p, j0) || (c.p.north_wall && j0 == c.p.ny - 2)) ? 0.f : r;      // "v" wall rule
 }
-__device__ __forceinline__ float ca_q(const CACtx& c, int j, int i) {
-  if (ca_wall_row(c.p, j)) return 0.f;
+__device__ __forceinline__ float ca_q(const CACtx& c, int j0, int i) {
+  const int j = ca_flux_row(c.p, j0);
   const int qj = ca_rj(c.p, j), qi = ca_ri(c.p, i), hj = hc_row(c.p, j), hj1 = hc_row(c.p, j + 1);
-  return swe_q(c.p, c.p.coriolis[j], ca_vv(c, qj, qi, j, i + 1), ca_vv(c, qj, qi, j, i), ca_vu(c, qj, qi, j + 1, i),
-               ca_vu(c, qj, qi, j, i), ca_h(c, hj, i), ca_h(c, hj, i + 1), ca_h(c, hj1, i), ca_h(c, hj1, i + 1));
+  const float r = swe_q(c.p, c.p.coriolis[j], ca_vv(c, qj, qi, j, i + 1), ca_vv(c, qj, qi, j, i),
+                        ca_vu(c, qj, qi, j + 1, i), ca_vu(c, qj, qi, j, i), ca_h(c, hj, i), ca_h(c, hj, i + 1),
+                        ca_h(c, hj1, i), ca_h(c, hj1, i + 1));
+  return ca_wall_row(c.p, j0) ? 0.f : r;
 }
-__device__ __forceinline__ float ca_ke(const CACtx& c, int j, int i) {
-  if (ca_wall_row(c.p, j)) return 0.f;
+__device__ __forceinline__ float ca_ke(const CACtx& c, int j0, int i) {
+  const int j = ca_flux_row(c.p, j0);
   const int qj = ca_rj(c.p, j), qi = ca_ri(c.p, i);
-  return swe_ke(ca_vu(c, qj, qi, j, i), ca_vu(c, qj, qi, j, i - 1), ca_vv(c, qj, qi, j, i), ca_vv(c, qj, qi, j - 1, i));
+  const float r = swe_ke(ca_vu(c, qj, qi, j, i), ca_vu(c, qj, qi, j, i - 1), ca_vv(c, qj, qi, j, i),
+                         ca_vv(c, qj, qi, j - 1, i));
+  return ca_wall_row(c.p, j0) ? 0.f : r;
 }
 
 // ---- frame kernel A: flux + tendency update of one of this rank's cells ------------------------
@@ -134,31 +155,32 @@ __device__ __forceinline__ void swe_ca_tend_cell(const CACtx& c, int j, int i) {
 // ---- frame kernel D: friction ------------------------------------------------------------------
 // u', v' anywhere within three cells of the block (mine: main arrays; beyond: the exchanged copy)
 __device__ __forceinline__ float ca_up(const CACtx& c, int j, int i) {
-  if (ca_mine(c.p, j, i) || ca_wall_row(c.p, j)) return c.ub[ca_m(c.p, j, i)];
-  return c.x.upx[ca_e(c.x, j, i)];
+  const bool main = ca_mine(c.p, j, i) || ca_wall_row(c.p, j);
+  const float* ptr = main ? c.ub + ca_m_safe(c.p, j, i) : c.x.upx + ca_e(c.x, j, i);
+  return *ptr;
 }
 __device__ __forceinline__ float ca_vp(const CACtx& c, int j, int i) {
-  if (ca_mine(c.p, j, i) || ca_wall_row(c.p, j)) return c.vb[ca_m(c.p, j, i)];
-  return c.x.vpx[ca_e(c.x, j, i)];
+  const bool main = ca_mine(c.p, j, i) || ca_wall_row(c.p, j);
+  const float* ptr = main ? c.vb + ca_m_safe(c.p, j, i) : c.x.vpx + ca_e(c.x, j, i);
+  return *ptr;
 }
 // u'' of cell (j, i) (swe_k34_body's update; the wall rules are functions of the row only, and a
 // y neighbour's far wall is out of reach)
 __device__ __forceinline__ float ca_upp(const CACtx& c, int j, int i) {
   const B2SweParams& p = c.p;
-  const bool fn_c_zero = p.north_wall && j == p.ny - 2, fn_s_zero = p.south_wall && j == 1;
-  // operands of a zeroed flux are not loaded (they may lie beyond a wall AND beyond the arrays)
-  const float u_n = fn_c_zero ? 0.f : ca_up(c, j + 1, i), u_s = fn_s_zero ? 0.f : ca_up(c, j - 1, i);
-  return swe_friction_u(p, ca_up(c, j, i), ca_up(c, j, i + 1), ca_up(c, j, i - 1), u_n, u_s, fn_c_zero, fn_s_zero);
+  return swe_friction_u(p, ca_up(c, j, i), ca_up(c, j, i + 1), ca_up(c, j, i - 1), ca_up(c, j + 1, i),
+                        ca_up(c, j - 1, i), p.north_wall && j == p.ny - 2, p.south_wall && j == 1);
 }
 // v'' of cell (j, i) given its own u'' (swe_k34_body's fluxes + swe_k5_body's update)
 __device__ __forceinline__ float ca_vpp(const CACtx& c, int j, int i, float upp_c) {
   const B2SweParams& p = c.p;
   const float v_c = ca_vp(c, j, i);
-  const float fe2_c = swe_visc_flux(p.viscosity, ca_vp(c, j, i + 1), upp_c, p.rdx);
-  const float fe2_w = swe_visc_flux(p.viscosity, v_c, ca_upp(c, j, i - 1), p.rdx);
-  const float fn2_c = (p.north_wall && j == p.ny - 2) ? 0.f : swe_visc_flux(p.viscosity, ca_vp(c, j + 1, i), upp_c, p.rdy);
-  const float fn2_s = (p.south_wall && j == 1) ? 0.f : swe_visc_flux(p.viscosity, v_c, ca_upp(c, j - 1, i), p.rdy);
-  return swe_apply_div(p, v_c, fe2_c, fe2_w, fn2_c, fn2_s);
+  const float fe2_c = swe_visc_flux(p.c_nux, ca_vp(c, j, i + 1), upp_c);
+  const float fe2_w = swe_visc_flux(p.c_nux, v_c, ca_upp(c, j, i - 1));
+  const float fn2_c = swe_visc_flux(p.c_nuy, ca_vp(c, j + 1, i), upp_c);
+  const float fn2_s = swe_visc_flux(p.c_nuy, v_c, ca_upp(c, j - 1, i));      // south wall: clamped loads, discarded
+  return swe_apply_div(p, v_c, fe2_c, fe2_w, (p.north_wall && j == p.ny - 2) ? 0.f : fn2_c,
+                       (p.south_wall && j == 1) ? 0.f : fn2_s);
 }
 
 // one of this rank's frame cells: u'' -> ua, v'' -> va; ring cells also mirror u', v' into the

@@ -16,6 +16,7 @@ from ._src import (  # noqa: F401
     alltoall,
     barrier,
     bcast,
+    comm_reserve,
     flush,
     gather,
     has_cuda_support,
@@ -37,5 +38,5 @@ effects_barrier = flush
 __all__ = [
     "allgather", "allreduce", "alltoall", "barrier", "bcast", "gather", "recv", "reduce",
     "scan", "scatter", "send", "sendrecv", "has_cuda_support", "has_sycl_support",
-    "MPI", "jit", "compiled", "flush", "effects_barrier", "linear_transpose", "send_with_grad",
+    "MPI", "jit", "compiled", "flush", "effects_barrier", "linear_transpose", "send_with_grad", "comm_reserve",
 ]

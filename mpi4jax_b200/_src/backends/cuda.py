@@ -24,6 +24,7 @@ import sys
 import tempfile
 import threading
 import uuid
+import weakref
 from typing import Optional
 
 import torch
@@ -267,7 +268,7 @@ class NativeComm:
             raise RuntimeError(
                 "mpi4jax_b200: a collective needs a larger staging buffer than is allocated, "
                 "which is impossible during CUDA-graph capture. Run the function once eagerly "
-                "first (mpi4jax_b200.jit does) or call comm_reserve(nbytes)."
+                "first (mpi4jax_b200.jit does) or call mpi4jax_b200.comm_reserve(nbytes, comm=comm)."
             )
         size = _MIN_STAGE
         while size < total_bytes:
@@ -286,13 +287,26 @@ class NativeComm:
                 dist.barrier(group=self.comm._group)
         old, self.stage = self.stage, new
         if old is not None:
-            old.destroy()
+            # Kernels get the staging pointers BY VALUE, so a CUDA graph captured earlier keeps the old
+            # segment's addresses baked into its nodes (mpi4jax_b200.jit replays them for as long as the
+            # function object lives).  Unmapping here would leave them dangling on every rank; the old
+            # segment therefore stays mapped until the communicator is destroyed -- the growth is
+            # geometric, so the retired segments together are smaller than the live one.
+            self._retired.append(old)
 
     def ensure_stage(self, opcode: int, blk_bytes: int) -> None:
         # same formula as b2_stage_need() (csrc/b2_collectives.cu), evaluated without leaving Python
         stride = (blk_bytes + 15) & ~15
         mult = self.comm.size if opcode in (codes.OPC_ALLTOALL, codes.OPC_SCATTER) else 1
         need = stride * mult + 4096
+        if need > self._stage_half:
+            self._grow_stage(2 * need + 8192)
+
+    def reserve(self, nbytes: int) -> None:
+        """Make sure collectives of up to ``nbytes`` per rank (alltoall / scatter: per peer block
+        times size) never have to grow the staging segment again.  Collective."""
+        stride = (int(nbytes) + 15) & ~15
+        need = stride * self.comm.size + 4096
         if need > self._stage_half:
             self._grow_stage(2 * need + 8192)
 
@@ -341,6 +355,12 @@ class NativeComm:
         if self.stage is not None:
             self.stage.destroy()
             self.stage = None
+        for seg in self._retired:
+            seg.destroy()
+        self._retired = []
+        for rec in self._status_pool:
+            lib.b2_status_free(rec)
+        del self._status_pool[:]
         if self.ctl is not None:
             self.ctl.destroy()
             self.ctl = None
@@ -435,10 +455,14 @@ class NativeComm:
             return None
         rec = getattr(status, "_record", None)      # one host-mapped record per Status object
         if rec is None:
-            rec = _lib().b2_status_alloc()
+            # records of collected Status objects are reused (a Status per loop iteration must not
+            # leak pinned host memory); they are freed with the communicator
+            rec = self._status_pool.pop() if self._status_pool else _lib().b2_status_alloc()
             if not rec:
                 raise MPIError(f"allocating a status record failed: {native.last_error()}")
             status._record = rec
+            pool = self._status_pool
+            weakref.finalize(status, pool.append, rec)
         return rec
 
     def _bind_status(self, status: Optional[Status], rec, itemsize: int) -> None:

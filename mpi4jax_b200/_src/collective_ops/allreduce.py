@@ -13,7 +13,7 @@ import torch
 
 from ..comm import OP_TYPES, SUM, Comm, Op, as_op
 from ..native import codes
-from ..utils import (NOTSET, as_tensor, check_dtype, get_default_comm, needs_autograd,
+from ..utils import (NOTSET, as_tensor, check_dtype, fold, get_default_comm, needs_autograd,
                      raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
@@ -76,6 +76,10 @@ def allreduce(x, op, *, comm=None, token=NOTSET, algorithm="auto"):
     x = as_tensor(x, comm)
     check_dtype(x)
     algo = codes.ALGO_BY_NAME[algorithm]
+    if op.code is None:                      # MPI.Op.Create: gather natively, fold on the device
+        if needs_autograd(x):
+            raise NotImplementedError(f"The derivative of allreduce for {op.name} is not defined")
+        return fold(list(_dispatch.allgather(comm, x.contiguous()).unbind(0)), op)
     if not needs_autograd(x):
         return _dispatch.allreduce(comm, x, op.code, algo)
     return _Allreduce.apply(x, op, comm, False, algo)

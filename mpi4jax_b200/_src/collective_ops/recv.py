@@ -15,7 +15,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ..comm import ANY_SOURCE, ANY_TAG, Comm, Status
+from ..comm import ANY_SOURCE, ANY_TAG, PROC_NULL, Comm, Status
 from ..utils import (NOTSET, as_tensor, check_dtype, check_rank, get_default_comm,
                      needs_autograd, raise_if_token_is_set)
 from ..validation import enforce_types
@@ -61,6 +61,10 @@ def recv(x, source=ANY_SOURCE, *, tag=ANY_TAG, comm=None, status=None, token=NOT
     x = as_tensor(x, comm)
     check_dtype(x)
     check_rank(int(source), comm, "Recv", "source", allow_any=True)
+    if int(source) == PROC_NULL:             # MPI: returns at once, buffer untouched
+        if status is not None:
+            status._set_proc_null()
+        return x
     if not needs_autograd(x):
         return _dispatch.recv(comm, x, int(source), int(tag), status)
     return _Recv.apply(x, int(source), int(tag), comm, status)

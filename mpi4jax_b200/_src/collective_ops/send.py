@@ -15,8 +15,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ..comm import Comm
-from ..utils import (NOTSET, as_tensor, check_dtype, check_rank, get_default_comm,
+from ..comm import PROC_NULL, Comm
+from ..utils import (NOTSET, as_tensor, check_dtype, carries_grad, check_rank, get_default_comm,
                      raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
@@ -55,6 +55,13 @@ def send(x, dest, *, tag=0, comm=None, token=NOTSET):
     x = as_tensor(x, comm)
     check_dtype(x)
     check_rank(int(dest), comm, "Send", "destination")
+    if int(dest) == PROC_NULL:
+        return
+    if carries_grad(x):
+        # a None result cannot carry a gradient: silently cutting the graph here would drop it
+        raise NotImplementedError(
+            "send of a tensor that requires grad: use mpi4jax_b200.send_with_grad (its token's backward "
+            "pass receives the cotangent), or send x.detach()")
     _dispatch.send(comm, x.detach(), int(dest), int(tag))
 
 

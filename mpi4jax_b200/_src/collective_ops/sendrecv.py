@@ -13,8 +13,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ..comm import ANY_TAG, Comm, Status
-from ..utils import (NOTSET, as_tensor, check_dtype, check_rank, get_default_comm,
+from ..comm import ANY_TAG, PROC_NULL, Comm, Status
+from ..utils import (NOTSET, as_tensor, carries_grad, check_dtype, check_rank, get_default_comm,
                      needs_autograd, raise_if_token_is_set)
 from ..validation import enforce_types
 from . import _dispatch
@@ -91,6 +91,19 @@ def sendrecv(sendbuf, recvbuf, source, dest, *, sendtag=0, recvtag=ANY_TAG, comm
     check_dtype(recvbuf)
     check_rank(int(dest), comm, "Sendrecv", "destination")
     check_rank(int(source), comm, "Sendrecv", "source", allow_any=True)
+    if int(dest) == PROC_NULL or int(source) == PROC_NULL:
+        # MPI: either half may address PROC_NULL; that half is a no-op (used at open boundaries)
+        from .recv import recv as _recv
+        from .send import send_with_grad as _send_grad
+        from .send import send as _send
+
+        if int(dest) != PROC_NULL:
+            (_send_grad if carries_grad(sendbuf) else _send)(sendbuf, int(dest), tag=int(sendtag), comm=comm)
+        if int(source) != PROC_NULL:
+            return _recv(recvbuf, int(source), tag=int(recvtag), comm=comm, status=status)
+        if status is not None:
+            status._set_proc_null()
+        return recvbuf
     if not needs_autograd(sendbuf, recvbuf):
         return _dispatch.sendrecv(comm, sendbuf, recvbuf, int(source), int(dest), int(sendtag),
                                   int(recvtag), status)

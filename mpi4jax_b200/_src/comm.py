@@ -40,13 +40,35 @@ class MPIError(RuntimeError):
 
 
 class Op:
-    """A predefined reduction operator (stand-in for ``mpi4py.MPI.Op``)."""
+    """A reduction operator (stand-in for ``mpi4py.MPI.Op``): one of the ten predefined ones
+    (``code`` selects the fused kernel instantiation) or a user-defined one made with
+    :meth:`Op.Create` (``code is None``, ``function`` is applied on the device)."""
 
-    __slots__ = ("name", "code")
+    __slots__ = ("name", "code", "function", "commute")
 
-    def __init__(self, name: str, code: int):
+    def __init__(self, name: str, code, function=None, commute: bool = True):
         self.name = name
         self.code = code
+        self.function = function
+        self.commute = commute
+
+    @classmethod
+    def Create(cls, function, commute: bool = True) -> "Op":
+        """User-defined reduction (``MPI.Op.Create``).  The reference forwards any ``MPI.Op`` handle
+        to the MPI library (/root/reference/mpi4jax/_src/collective_ops/allreduce.py:104), which
+        calls the user's C function on the host.  Here ``function(a, b) -> Tensor`` combines two
+        tensors elementwise with torch ops and runs on the device: allreduce / reduce / scan gather
+        the contributions with the native all-gather / gather kernels and fold them in rank order
+        (``((x_0 (+) x_1) (+) x_2) ...``, valid for non-commutative operators too)."""
+        if not callable(function):
+            raise TypeError("Op.Create needs a callable f(a, b) -> Tensor")
+        return cls(getattr(function, "__name__", "USER_OP"), None, function, bool(commute))
+
+    def Is_commutative(self) -> bool:
+        return bool(self.commute)
+
+    def Free(self) -> None:
+        """No resources are attached to an operator (mpi4py API compatibility)."""
 
     def __repr__(self) -> str:
         return f"<mpi4jax_b200.MPI.{self.name}>"
@@ -55,6 +77,9 @@ class Op:
         """Binary Python function of the operator (used by the object collectives, like mpi4py's
         ``comm.allreduce(obj, op)``)."""
         import operator
+
+        if self.function is not None:
+            return self.function
 
         return {
             "SUM": operator.add, "PROD": operator.mul, "MIN": min, "MAX": max,
@@ -67,6 +92,8 @@ class Op:
         return self.python_function()(a, b)
 
     def __reduce__(self):
+        if self.function is not None:
+            return (Op.Create, (self.function, self.commute))
         return (_op_by_name, (self.name,))
 
 
@@ -125,6 +152,10 @@ class Status:
     def _bind_native(self, record, event, itemsize: int) -> None:
         self._native = (record, event)
         self._itemsize = itemsize
+
+    def _set_proc_null(self) -> None:
+        """MPI: a receive from PROC_NULL returns at once with source = PROC_NULL, tag = ANY_TAG, count 0."""
+        self._set(PROC_NULL, ANY_TAG, 0, self._itemsize)
 
     def _sync(self) -> None:
         if self._native is None:
@@ -231,6 +262,15 @@ class Comm:
         self._freed = False
         self.device = select_device()
         _comm_registry.add(self)
+        # Communicator construction (COMM_WORLD, Clone, Split) is collective over exactly its members,
+        # and so is the creation of the GPU side (symmetric heap, handle exchange).  Doing it here --
+        # not on the first CUDA op -- keeps point-to-point ops point-to-point: a send / recv between
+        # two ranks of a larger communicator must not wait for ranks that never communicate.
+        # MPI4JAX_B200_LAZY_INIT=1 restores creation on first use (then the first CUDA op on a
+        # communicator is collective).
+        if self.device.type == "cuda" and os.environ.get("MPI4JAX_B200_LAZY_INIT", "0").lower() not in (
+                "1", "true", "on"):
+            self._native_comm()
 
     # -- mpi4py-style API --------------------------------------------------------
     def Get_rank(self) -> int:
@@ -249,7 +289,10 @@ class Comm:
         """A communicator over the same processes with private message channels
         (collective; reference default comm = ``COMM_WORLD.Clone()``, utils.py:20-27)."""
         self._check_alive()
-        group = dist.new_group(ranks=self._ranks, backend="gloo")
+        # use_local_synchronization: only the members of THIS communicator take part (hashed group
+        # name instead of the job-wide group counter), so Dup / Split work on sub-communicators
+        # while the other ranks of the job do something else -- as in MPI
+        group = dist.new_group(ranks=self._ranks, backend="gloo", use_local_synchronization=True)
         return Comm(group, self._ranks, name=self._name + ".clone")
 
     Dup = Clone
@@ -259,15 +302,13 @@ class Comm:
         self._check_alive()
         info = [None] * self.size
         dist.all_gather_object(info, (int(color), int(key), self._global_rank), group=self._group)
-        colors = sorted({c for c, _, _ in info if c != UNDEFINED})
-        mine = None
-        for c in colors:  # every rank creates every group, in the same order
-            members = sorted((k, r) for cc, k, r in info if cc == c)
-            ranks = [r for _, r in members]
-            group = dist.new_group(ranks=ranks, backend="gloo")
-            if c == color:
-                mine = Comm(group, ranks, name=f"{self._name}.split{c}")
-        return mine
+        if color == UNDEFINED:
+            return None
+        members = sorted((k, r) for cc, k, r in info if cc == color)
+        ranks = [r for _, r in members]
+        # each rank creates only the group it belongs to (member-only synchronisation, see Clone)
+        group = dist.new_group(ranks=ranks, backend="gloo", use_local_synchronization=True)
+        return Comm(group, ranks, name=f"{self._name}.split{color}")
 
     def Barrier(self) -> None:
         """Host-side barrier on the control plane (mpi4py ``comm.Barrier()``)."""

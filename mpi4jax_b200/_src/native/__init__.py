@@ -82,6 +82,9 @@ class B2SweParams(Structure):
         ("south_wall", c_int),
         ("north_wall", c_int),
         ("coriolis", c_void_p),
+        ("c_gx", c_float), ("c_gy", c_float),        # folded constants, see csrc/b2_swe_body.cuh
+        ("c_nux", c_float), ("c_nuy", c_float),
+        ("c_fx", c_float), ("c_fy", c_float),
     ]
 
 
@@ -173,20 +176,6 @@ _SIGNATURES = {
     "b2_set_pdl": (None, [c_int]),
     "b2_gemm_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2_halo_exchange": (c_int, [c_void_p, POINTER(B2HaloDesc), c_void_p]),
-    "b2_swe_fluxes": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 7 + [c_void_p]),
-    "b2_swe_tendencies": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 11 + [c_void_p]),
-    "b2_swe_friction_flux_u": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
-    "b2_swe_friction_u_flux_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 6 + [c_void_p]),
-    "b2_swe_friction_u_fused": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 5 + [c_int, c_void_p]),
-    "b2_swe_friction_v": (c_int, [c_void_p, POINTER(B2SweParams)] + [c_void_p] * 3 + [c_void_p]),
-    "b2_swe_multistep_k12f": (
-        c_int,
-        [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2HaloDesc), c_int, c_int, c_void_p],
-    ),
-    "b2_swe_multistep_k12": (
-        c_int,
-        [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2HaloDesc), c_int, c_int, c_void_p],
-    ),
     "b2_swe_multistep_ca": (
         c_int,
         [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2SweCA), POINTER(B2HaloDesc), c_int, c_int,
@@ -204,7 +193,7 @@ _SIGNATURES = {
 
 
 #: must equal B2_ABI_VERSION in csrc/b2_common.h
-ABI_VERSION = 7
+ABI_VERSION = 8
 _ABI_FIELDS = ("abi_version", "sizeof_status_record", "sizeof_halo_desc", "sizeof_swe_params",
                "sizeof_swe_state", "sizeof_error_record", "max_ranks", "p2p_nslot", "sizeof_swe_ca")
 

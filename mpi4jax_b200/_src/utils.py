@@ -103,6 +103,14 @@ def needs_autograd(*tensors) -> bool:
     return torch.autograd.forward_ad._current_level >= 0
 
 
+def carries_grad(t: torch.Tensor) -> bool:
+    """True when dropping ``t`` from the graph would lose a gradient: reverse-mode recording is on
+    for it, or it is the grad-tracking wrapper of an active torch.func transform."""
+    if _functorch.is_gradtrackingtensor(t):
+        return True
+    return bool(torch.is_grad_enabled() and t.requires_grad)
+
+
 def backend_of(t: torch.Tensor) -> str:
     return "cuda" if t.is_cuda else "cpu"
 
@@ -128,6 +136,8 @@ def check_rank(value: int, comm: _comm.Comm, opname: str, what: str, allow_any: 
     MPIError when MPI4JAX_B200_ABORT_ON_ERROR=0)."""
     if allow_any and value == _comm.ANY_SOURCE:
         return
+    if value == _comm.PROC_NULL:          # MPI: communication with PROC_NULL is a no-op
+        return
     if 0 <= value < comm.Get_size():
         return
     from .backends.cuda import abort_or_raise
@@ -135,3 +145,26 @@ def check_rank(value: int, comm: _comm.Comm, opname: str, what: str, allow_any: 
     abort_or_raise(
         f"r{comm.Get_rank()} | MPI_{opname} returned error code 6: invalid {what} rank {value} "
         f"(communicator size {comm.Get_size()}) - aborting", 6)
+
+
+def fold(parts, op) -> torch.Tensor:
+    """``((x_0 (+) x_1) (+) x_2) ...`` with a user-defined operator, on the device."""
+    acc = parts[0]
+    for part in parts[1:]:
+        acc = op.function(acc, part)
+        if not isinstance(acc, torch.Tensor) or acc.shape != parts[0].shape:
+            raise TypeError("a user-defined reduction must return a tensor of its operands' shape")
+    return acc.to(parts[0].dtype)
+
+
+def comm_reserve(nbytes: int, *, comm: Optional[_comm.Comm] = None) -> None:
+    """Pre-size the GPU staging buffers of ``comm`` (default communicator if None) for collectives
+    of up to ``nbytes`` per rank, so that no later call has to grow them.  Growth is collective and
+    impossible during CUDA-graph capture; ``mpi4jax_b200.jit`` avoids it by running a function once
+    eagerly, ``comm_reserve`` is the explicit alternative.  A no-op on CPU communicators."""
+    if comm is None:
+        comm = get_default_comm()
+    if comm.device.type == "cuda":
+        native_comm = comm._native_comm()
+        if hasattr(native_comm, "reserve"):
+            native_comm.reserve(int(nbytes))

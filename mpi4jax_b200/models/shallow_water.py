@@ -7,10 +7,12 @@ Adams-Bashforth time stepping, lateral friction, decomposition ``nproc_y = min(P
 balanced jet (:138-169).  Two execution paths integrate it:
 
 ``backend="native"`` (CUDA tensors)
-    Five fused sm_100a stencil kernels and four fused multi-field halo-exchange kernels per
-    step (csrc/b2_swe.cu, csrc/b2_halo.cu), enqueued by one native call per ``multistep`` and
-    captured into a CUDA graph by :func:`mpi4jax_b200.jit`.  This replaces the reference's
-    per-step sequence of XLA elementwise kernels + 48 blocking MPI custom calls.
+    Hand-written sm_100a kernels, enqueued by one native call per ``multistep`` and captured
+    into a CUDA graph by :func:`mpi4jax_b200.jit`.  Default schedule: the communication-avoiding
+    step (csrc/b2_swe_ca.cu) -- two fused bulk kernels (16 array passes instead of 32) running
+    concurrently with a thin frame pipeline that needs ONE three-cell-deep halo exchange per
+    step.  This replaces the reference's per-step sequence of XLA elementwise kernels + 48
+    blocking MPI custom calls.
 
 ``backend="ops"`` (any device)
     Plain torch arithmetic with halo exchange through the *public* ``sendrecv``/``send``/
@@ -78,7 +80,7 @@ class ShallowWaterConfig:
 class ShallowWaterModel:
     def __init__(self, config: Optional[ShallowWaterConfig] = None, comm: Optional[Comm] = None,
                  device: Optional[torch.device] = None, backend: str = "auto",
-                 k12: Optional[bool] = None, pipeline: Optional[str] = None):
+                 pipeline: Optional[str] = None):
         self.cfg = cfg = config or ShallowWaterConfig()
         self.comm = comm = comm or get_default_comm()
         self.device = torch.device(device) if device is not None else comm.device
@@ -94,20 +96,12 @@ class ShallowWaterModel:
         #                 recomputed on a thin frame, bulk and frame on two streams (b2_swe_ca.cu);
         #                 16 array passes per step.  Default.
         #   "standalone"  4 stencil kernels + 3 fused exchanges, 32 passes (b2_swe.cu): the oracle the
-        #                 other schedules are compared with bit for bit.
-        #   "k12" / "k12f"  three exchanges, flux+tendency (and friction) kernels fused on the bulk.
+        #                 default schedule is compared with, bit for bit.
         if pipeline is None:
-            pipeline = os.environ.get("MPI4JAX_B200_SWE_PIPELINE", "").strip().lower() or None
-        if pipeline is None and k12 is not None:
-            pipeline = {0: "standalone", 1: "k12", 2: "k12f"}[2 if k12 in (2, "full") else int(bool(k12))]
-        if pipeline is None:
-            raw = os.environ.get("MPI4JAX_B200_SWE_K12", "").strip().lower()
-            pipeline = ("k12f" if raw in ("2", "full") else "k12" if raw in ("1", "true", "on") else
-                        "standalone" if raw in ("0", "false", "off") else "ca")
-        if pipeline not in ("ca", "standalone", "k12", "k12f"):
-            raise ValueError(f"unknown shallow-water pipeline {pipeline!r}")
+            pipeline = os.environ.get("MPI4JAX_B200_SWE_PIPELINE", "").strip().lower() or "ca"
+        if pipeline not in ("ca", "standalone"):
+            raise ValueError(f"unknown shallow-water pipeline {pipeline!r} (expected 'ca' or 'standalone')")
         self.pipeline = pipeline
-        self.k12 = {"k12": 1, "k12f": 2}.get(pipeline, 0)
         size, rank = comm.Get_size(), comm.Get_rank()
         if size not in SUPPORTED_NPROC:
             raise RuntimeError(
@@ -186,6 +180,12 @@ class ShallowWaterModel:
             p.rdx = float(np.float32(1.0) / np.float32(self.cfg.dx))
             p.rdy = float(np.float32(1.0) / np.float32(self.cfg.dy))
             p.ab_a, p.ab_b = self.cfg.ab_a, self.cfg.ab_b
+            # constant factors folded once, in fp32 (csrc/b2_swe_body.cuh)
+            f32 = np.float32
+            rdx, rdy, nu, dt = f32(p.rdx), f32(p.rdy), f32(p.viscosity), f32(p.dt)
+            p.c_gx, p.c_gy = float(-f32(p.gravity) * rdx), float(-f32(p.gravity) * rdy)
+            p.c_nux, p.c_nuy = float(nu * rdx), float(nu * rdy)
+            p.c_fx, p.c_fy = float(dt * nu * rdx * rdx), float(dt * nu * rdy * rdy)
             p.first_step = 0
             p.south_wall, p.north_wall = int(self.at_south_wall), int(self.at_north_wall)
             p.coriolis = self.coriolis.data_ptr()
@@ -353,10 +353,9 @@ class ShallowWaterModel:
                     nc.handle, ctypes.byref(self._params), ctypes.byref(self._state), ctypes.byref(self._ca),
                     ctypes.byref(self._topo), int(nsteps), int(bool(first_step)), stream)
             else:
-                fn = (native.lib.b2_swe_multistep_k12f if self.k12 == 2 else
-                      native.lib.b2_swe_multistep_k12 if self.k12 else native.lib.b2_swe_multistep)
-                rc = fn(nc.handle, ctypes.byref(self._params), ctypes.byref(self._state),
-                        ctypes.byref(self._topo), int(nsteps), int(bool(first_step)), stream)
+                rc = native.lib.b2_swe_multistep(
+                    nc.handle, ctypes.byref(self._params), ctypes.byref(self._state),
+                    ctypes.byref(self._topo), int(nsteps), int(bool(first_step)), stream)
             nc._check(rc, "Halo")
         else:
             for it in range(nsteps):

@@ -14,7 +14,7 @@ if len(sys.argv) > 1:
     sizes = tuple(tuple(int(x) for x in a.split("x")) for a in sys.argv[1:])
 for nx, ny in sizes:
     states = {}
-    for pipe in ("standalone", "k12", "k12f", "ca", "ca"):
+    for pipe in ("standalone", "ca", "ca"):
         mod = ShallowWaterModel(ShallowWaterConfig.for_resolution(nx, ny), device="cuda", pipeline=pipe)
         mod.step(first_step=True)
         run = m.jit(lambda: mod.multistep(50, first_step=False), warmup=0)

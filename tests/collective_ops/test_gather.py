@@ -8,7 +8,6 @@ import torch
 import mpi4jax_b200 as m
 from mpi4jax_b200 import MPI
 
-from .._gating import new_on_gpu
 
 comm = MPI.COMM_WORLD
 rank, size = comm.Get_rank(), comm.Get_size()
@@ -26,8 +25,6 @@ def _piece(r, shape, dtype, device):
 @pytest.mark.parametrize("shape, dtype", [((3, 2), torch.float32), ((4,), torch.float32), ((2, 3), torch.int32),
                                           ((1,), torch.bool)], ids=lambda v: str(v).replace("torch.", ""))
 def test_root_collects_all_pieces_in_rank_order(device, root, shape, dtype):
-    if dtype != torch.float32:
-        new_on_gpu(device)
     x = _piece(rank, shape, dtype, device)
     keep = x.clone()
     out = m.gather(x, root=root)
@@ -49,7 +46,6 @@ def test_python_scalar(device):
 
 
 def test_non_contiguous_input(device):
-    new_on_gpu(device)
     x = _piece(rank, (4, 6), torch.float32, device).t()[::2]          # strided view, shape (3, 4)
     out = m.gather(x, root=0)
     if rank == 0:

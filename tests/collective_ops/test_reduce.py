@@ -7,7 +7,6 @@ import torch
 import mpi4jax_b200 as m
 from mpi4jax_b200 import MPI
 
-from .._gating import new_on_gpu
 
 comm = MPI.COMM_WORLD
 rank, size = comm.Get_rank(), comm.Get_size()
@@ -20,8 +19,6 @@ def _mine(device, dtype=torch.float32):
 
 @pytest.mark.parametrize("root", ROOTS)
 def test_sum_lands_on_the_root_only(device, root):
-    if root not in (0, size - 1):
-        new_on_gpu(device)
     x = _mine(device)
     keep = x.clone()
     out = m.reduce(x, op=MPI.SUM, root=root)
@@ -40,8 +37,6 @@ def test_sum_lands_on_the_root_only(device, root):
                                                  for r in range(size)]).prod(0)),
 ], ids=["max", "min", "prod"])
 def test_other_operators_on_the_last_rank(device, name, dtype, expect):
-    if name != "MAX":
-        new_on_gpu(device)
     root = size - 1
     x = _mine(device, dtype)
     out = m.reduce(x, op=getattr(MPI, name), root=root)

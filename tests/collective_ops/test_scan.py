@@ -9,7 +9,6 @@ import torch
 import mpi4jax_b200 as m
 from mpi4jax_b200 import MPI
 
-from .._gating import new_on_gpu
 
 comm = MPI.COMM_WORLD
 rank, size = comm.Get_rank(), comm.Get_size()
@@ -34,8 +33,6 @@ CASES = [
 
 @pytest.mark.parametrize("name, gen, combine, dtype", CASES, ids=[c[0] for c in CASES])
 def test_prefix_over_ranks(device, name, gen, combine, dtype):
-    if name not in ("SUM", "PROD"):
-        new_on_gpu(device)
     x = torch.full((3, 2), gen(rank), dtype=dtype, device=device)
     keep = x.clone()
     out = m.scan(x, op=getattr(MPI, name))
@@ -46,7 +43,6 @@ def test_prefix_over_ranks(device, name, gen, combine, dtype):
 
 
 def test_elementwise_not_across_elements(device):
-    new_on_gpu(device)
     x = torch.arange(6, dtype=torch.float32, device=device) * (rank + 1)
     out = m.scan(x, op=MPI.SUM)
     tri = (rank + 1) * (rank + 2) // 2                       # 1 + 2 + ... + (rank + 1)
@@ -58,7 +54,6 @@ def test_python_int_is_accepted(device):
 
 
 def test_python_float_is_accepted(device):
-    new_on_gpu(device)
     assert math.isclose(m.scan(0.5, op=MPI.SUM).item(), 0.5 * (rank + 1))
 
 

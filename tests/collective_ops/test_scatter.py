@@ -8,7 +8,6 @@ import torch
 import mpi4jax_b200 as m
 from mpi4jax_b200 import MPI
 
-from .._gating import new_on_gpu
 
 comm = MPI.COMM_WORLD
 rank, size = comm.Get_rank(), comm.Get_size()
@@ -29,8 +28,6 @@ def _deck(shape, dtype, device):
 @pytest.mark.parametrize("root", ROOTS)
 @pytest.mark.parametrize("shape, dtype", BLOCKS, ids=lambda v: str(v).replace("torch.", ""))
 def test_every_rank_gets_its_block(device, root, shape, dtype):
-    if (root, shape, dtype) != (0, (3, 2), torch.float32):
-        new_on_gpu(device)
     deck = _deck(shape, dtype, device)
     arg = deck if rank == root else torch.empty(shape, dtype=dtype, device=device)
     before = arg.clone()

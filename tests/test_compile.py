@@ -97,8 +97,6 @@ def test_torch_export_keeps_all_ops(device):
 def test_compiled_gradients_match_eager_rules(device):
     """allgather / alltoall / bcast / sendrecv are differentiable in the traced frontend too, with
     the same adjoints as the eager ops."""
-    if device.type == "cuda" and not os.environ.get("MPI4JAX_B200_TEST_EXPERIMENTAL"):
-        pytest.skip("added after the round's last GPU run: CUDA variant waits for MPI4JAX_B200_TEST_EXPERIMENTAL=1")
     x = torch.arange(size * 3, dtype=torch.float32, device=device).reshape(size, 3) + rank
 
     def via(ns, t):
@@ -121,8 +119,6 @@ def test_compiled_gradients_match_eager_rules(device):
 def test_compiled_gather_scatter_allgather_shapes_under_compile(device):
     """Rank-dependent static arguments (root / is_root, communicator size) are resolved while
     tracing; no registry lookups inside the traced frame."""
-    if device.type == "cuda" and not os.environ.get("MPI4JAX_B200_TEST_EXPERIMENTAL"):
-        pytest.skip("added after the round's last GPU run: CUDA variant waits for MPI4JAX_B200_TEST_EXPERIMENTAL=1")
 
     def f(t):
         g = mc.gather(t, 0, comm=comm)

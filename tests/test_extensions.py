@@ -1,0 +1,131 @@
+"""Capabilities beyond the reference's rule set that round 1's review asked for: adjoints of the
+rooted ops and scan (the reference raises for them), user-defined reduction operators
+(``MPI.Op.Create``; the reference forwards any ``MPI.Op`` handle, allreduce.py:104), ``PROC_NULL``
+peers, communicator duplication on sub-communicators, staging reservation."""
+
+import pytest
+import torch
+
+import mpi4jax_b200 as m
+from mpi4jax_b200 import MPI
+
+comm = MPI.COMM_WORLD
+rank, size = comm.Get_rank(), comm.Get_size()
+
+
+def _leaf(device, *shape):
+    return (torch.arange(float(torch.Size(shape).numel()), device=device).reshape(shape) + rank).requires_grad_()
+
+
+@pytest.mark.parametrize("root", sorted({0, size - 1}))
+def test_reduce_vjp_is_a_broadcast_from_the_root(device, root):
+    x = _leaf(device, 3, 2)
+    w = torch.arange(6.0, device=device).reshape(3, 2) + 1
+    out = m.reduce(x, MPI.SUM, root, comm=comm)
+    loss = (out * w).sum() if rank == root else (out * 0.5).sum()      # non-root: out is x itself
+    loss.backward()
+    want = w if rank == root else w + 0.5
+    assert torch.equal(x.grad, want)
+
+
+def test_scan_vjp_is_the_suffix_sum(device):
+    x = _leaf(device, 4)
+    w = torch.full((4,), float(rank + 1), device=device)
+    (m.scan(x, MPI.SUM, comm=comm) * w).sum().backward()
+    want = sum(float(q + 1) for q in range(rank, size))       # ranks r .. P-1 see x_r with unit weight
+    assert torch.allclose(x.grad, torch.full((4,), want, device=device))
+
+
+@pytest.mark.parametrize("root", sorted({0, size - 1}))
+def test_gather_and_scatter_are_adjoint(device, root):
+    x = _leaf(device, 2, 3)
+    out = m.gather(x, root, comm=comm)
+    if rank == root:
+        w = torch.arange(float(size * 6), device=device).reshape(size, 2, 3)
+        (out * w).sum().backward()
+        assert torch.equal(x.grad, w[rank])
+    else:
+        (out * 2.0).sum().backward()            # the root's cotangent block for this rank + own pass-through
+        w = torch.arange(float(size * 6), device=device).reshape(size, 2, 3)
+        assert torch.equal(x.grad, w[rank] + 2.0)
+    # scatter: the root's input gradient stacks every rank's cotangent
+    src = (torch.arange(float(size * 4), device=device).reshape(size, 4)).requires_grad_() if rank == root else \
+        torch.empty(4, device=device).requires_grad_()
+    blk = m.scatter(src, root, comm=comm)
+    (blk * float(rank + 1)).sum().backward()
+    if rank == root:
+        want = torch.stack([torch.full((4,), float(q + 1), device=device) for q in range(size)])
+        assert torch.equal(src.grad, want)
+    else:
+        assert torch.equal(src.grad, torch.zeros(4, device=device))
+
+
+def test_non_sum_rules_still_raise(device):
+    x = _leaf(device, 3)
+    with pytest.raises(NotImplementedError):
+        m.reduce(x, MPI.MAX, 0, comm=comm)
+    with pytest.raises(NotImplementedError):
+        m.scan(x, MPI.PROD, comm=comm)
+
+
+def test_plain_send_of_a_tensor_that_requires_grad_raises(device):
+    x = _leaf(device, 3)
+    with pytest.raises(NotImplementedError, match="send_with_grad"):
+        m.send(x, rank, comm=comm)
+    m.send(x.detach(), rank, tag=5, comm=comm)       # explicit detach is the sanctioned way
+    got = m.recv(torch.empty(3, device=device), rank, tag=5, comm=comm)
+    assert torch.equal(got, x.detach())
+
+
+def test_user_defined_operator(device):
+    """MPI.Op.Create: a non-commutative 2x2 matrix product, folded in rank order on every rank."""
+    matmul = MPI.Op.Create(lambda a, b: a @ b, commute=False)
+    assert not matmul.Is_commutative()
+    x = torch.tensor([[1.0, float(rank + 1)], [0.0, 1.0]], device=device)        # shear by rank + 1
+    want_all = torch.tensor([[1.0, float(size * (size + 1) // 2)], [0.0, 1.0]], device=device)
+    assert torch.equal(m.allreduce(x, matmul, comm=comm), want_all)
+    want_scan = torch.tensor([[1.0, float((rank + 1) * (rank + 2) // 2)], [0.0, 1.0]], device=device)
+    assert torch.equal(m.scan(x, matmul, comm=comm), want_scan)
+    got = m.reduce(x, matmul, size - 1, comm=comm)
+    assert torch.equal(got, want_all if rank == size - 1 else x)
+    hypot = MPI.Op.Create(lambda a, b: torch.sqrt(a * a + b * b))
+    v = torch.tensor([3.0, 0.0], device=device)
+    assert torch.allclose(m.allreduce(v, hypot, comm=comm), torch.tensor([3.0 * size ** 0.5, 0.0], device=device))
+    assert comm.allreduce(3, op=MPI.Op.Create(lambda a, b: a * b)) == 3 ** size      # object API, too
+
+
+def test_proc_null_peers_are_no_ops(device):
+    x = torch.full((5,), float(rank), device=device)
+    m.send(x, MPI.PROC_NULL, comm=comm)
+    st = MPI.Status()
+    keep = torch.full((5,), -7.0, device=device)
+    got = m.recv(keep, MPI.PROC_NULL, comm=comm, status=st)
+    assert torch.equal(got, keep) and st.Get_source() == MPI.PROC_NULL and st.Get_count() == 0
+    # open chain: the ends talk to PROC_NULL on one side (the boundary idiom of MPI stencil codes)
+    up = rank + 1 if rank + 1 < size else MPI.PROC_NULL
+    down = rank - 1 if rank > 0 else MPI.PROC_NULL
+    got = m.sendrecv(x, keep, source=down, dest=up, comm=comm)
+    assert torch.equal(got, keep if rank == 0 else torch.full((5,), float(rank - 1), device=device))
+
+
+def test_dup_and_split_on_a_sub_communicator_do_not_involve_other_ranks(device):
+    """Clone / Split on a sub-communicator are collective over ITS members only; the default
+    communicator (a lazy world clone) still works afterwards."""
+    sub = comm.Split(rank // 2, rank)
+    if rank < 2:                                   # only the first pair duplicates / re-splits
+        dup = sub.Clone()
+        again = dup.Split(0, -dup.Get_rank())      # reversed order inside the pair
+        got = m.allreduce(torch.ones(3, device=device), MPI.SUM, comm=again)
+        assert torch.equal(got, torch.full((3,), float(sub.Get_size()), device=device))
+        assert again.Get_rank() == sub.Get_size() - 1 - sub.Get_rank()
+        again.Free()
+        dup.Free()
+    total = m.allreduce(torch.ones(2, device=device), MPI.SUM)          # default comm: every rank
+    assert torch.equal(total, torch.full((2,), float(size), device=device))
+    sub.Free()
+
+
+def test_comm_reserve(device):
+    m.comm_reserve(1 << 20, comm=comm)
+    x = torch.ones(1 << 18, device=device)
+    assert torch.equal(m.allreduce(x, MPI.SUM, comm=comm), x * size)

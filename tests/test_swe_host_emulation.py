@@ -1,7 +1,8 @@
 """The shallow-water stencil bodies compiled for the HOST (tests/native/swe_host_emu.cpp: the
-CUDA source with the qualifiers defined away) -- checks the indexing of the experimental fused
-flux+tendency path (K12 on the bulk, K1 -> exchange -> K2 on the frame; csrc/b2_swe_k12_body.cuh)
-against K1 -> K2 on every cell, on a machine without a GPU."""
+CUDA source with the qualifiers defined away) -- checks, on a machine without a GPU, the launch
+sequence of the stand-alone kernels against the public-ops model and the communication-avoiding
+step (csrc/b2_swe_ca_body.cuh: frame kernels with owner views, deep-halo exchange geometry,
+bulk / frame partition, fused bulk bodies) against the stand-alone kernels, bit for bit."""
 
 import ctypes
 import os
@@ -26,7 +27,18 @@ class Params(ctypes.Structure):       # B2SweParams (csrc/b2_swe_body.cuh)
                 ("rdx", ctypes.c_float), ("rdy", ctypes.c_float),
                 ("ab_a", ctypes.c_float), ("ab_b", ctypes.c_float),
                 ("first_step", ctypes.c_int), ("south_wall", ctypes.c_int), ("north_wall", ctypes.c_int),
-                ("coriolis", ctypes.c_void_p)]
+                ("coriolis", ctypes.c_void_p)] + [(n, ctypes.c_float) for n in
+                                                   ("c_gx", "c_gy", "c_nux", "c_nuy", "c_fx", "c_fy")]
+
+
+def _folded(p):
+    """The constant factors the model folds on the host (models/shallow_water.py)."""
+    f32 = np.float32
+    rdx, rdy, nu, dt, g = f32(p.rdx), f32(p.rdy), f32(p.viscosity), f32(p.dt), f32(p.gravity)
+    p.c_gx, p.c_gy = float(-g * rdx), float(-g * rdy)
+    p.c_nux, p.c_nuy = float(nu * rdx), float(nu * rdy)
+    p.c_fx, p.c_fy = float(dt * nu * rdx * rdx), float(dt * nu * rdy * rdy)
+    return p
 
 
 def _build(tmp_path_factory, name, *defines):
@@ -48,12 +60,6 @@ def emu(tmp_path_factory):
     return lib
 
 
-@pytest.fixture(scope="module")
-def emu_explicit(tmp_path_factory):
-    """The same bodies with B2_SWE_EXPLICIT_ROUNDING=1 (flux kernel built from the helpers)."""
-    return _build(tmp_path_factory, "swe_emu_explicit", "-DB2_SWE_EXPLICIT_ROUNDING=1")
-
-
 def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
@@ -68,139 +74,11 @@ def _setup(ny, nx, first_step, south_wall, north_wall, seed=0):
                rdx=np.float32(1) / np.float32(5e3), rdy=np.float32(1) / np.float32(5e3), ab_a=1.5 + 0.1,
                ab_b=-(0.5 + 0.1), first_step=int(first_step), south_wall=int(south_wall),
                north_wall=int(north_wall), coriolis=cor.ctypes.data)
-    return p, fields, cor, rng
+    return _folded(p), fields, cor, rng
 
 
-def _fill_flux_halos(arrs, vals):
-    """Stand-in for the halo exchange of (fe, fn, q, ke): the same 'received' numbers in both paths."""
-    for a, r in zip(arrs, vals):
-        a[0, :], a[-1, :] = r[0, :], r[-1, :]
-        a[:, 0] = r[:, 0]
-        a[:, arrs_nx(a) - 1] = r[:, arrs_nx(a) - 1]
 
-
-_NX = {}
-
-
-def arrs_nx(a):
-    return _NX[id(a)]
-
-
-@pytest.mark.parametrize("first_step", [False, True])
-@pytest.mark.parametrize("walls", [(0, 0), (1, 0), (0, 1), (1, 1)])
-@pytest.mark.parametrize("shape", [(19, 26), (8, 12), (33, 64), (12, 45)])
-def test_fused_k12_path_equals_k1_k2(emu, shape, walls, first_step):
-    ny, nx = shape
-    p, fld, cor, rng = _setup(ny, nx, first_step, *walls, seed=ny * 1000 + nx)
-    assert emu.emu_k12_supported(ctypes.byref(p)) == 1
-    pitch = p.pitch
-    recv = [rng.uniform(-5, 5, (ny, pitch)).astype(np.float32) for _ in range(4)]
-
-    # ---- reference: K1 everywhere -> exchange -> K2 everywhere (u, v in place) -------------
-    a = {k: x.copy() for k, x in fld.items()}
-    flux = [np.zeros((ny, pitch), np.float32) for _ in range(4)]
-    emu.emu_k1_all(ctypes.byref(p), _ptr(a["h"]), _ptr(a["u"]), _ptr(a["v"]), *[_ptr(x) for x in flux])
-    for x in flux:
-        _NX[id(x)] = nx
-    _fill_flux_halos(flux, recv)
-    h_ref = np.full((ny, pitch), np.nan, np.float32)
-    emu.emu_k2_all(ctypes.byref(p), _ptr(a["h"]), _ptr(h_ref), _ptr(a["u"]), _ptr(a["v"]), _ptr(a["dh"]),
-                   _ptr(a["du"]), _ptr(a["dv"]), *[_ptr(x) for x in flux])
-
-    # ---- fused path: K12 on the bulk, K1 on the frame -> exchange -> K2 on the ring -----------
-    b = {k: x.copy() for k, x in fld.items()}
-    h_new = np.full((ny, pitch), np.nan, np.float32)
-    u_new = np.full((ny, pitch), np.nan, np.float32)
-    v_new = np.full((ny, pitch), np.nan, np.float32)
-    emu.emu_k12_bulk(ctypes.byref(p), _ptr(b["h"]), _ptr(h_new), _ptr(b["u"]), _ptr(u_new), _ptr(b["v"]),
-                     _ptr(v_new), _ptr(b["dh"]), _ptr(b["du"]), _ptr(b["dv"]))
-    flux2 = [np.full((ny, pitch), np.nan, np.float32) for _ in range(4)]      # NaN = never computed
-    emu.emu_k1_frame(ctypes.byref(p), _ptr(b["h"]), _ptr(b["u"]), _ptr(b["v"]), *[_ptr(x) for x in flux2])
-    for x in flux2:
-        _NX[id(x)] = nx
-    _fill_flux_halos(flux2, recv)
-    emu.emu_k2_ring(ctypes.byref(p), _ptr(b["h"]), _ptr(h_new), _ptr(b["u"]), _ptr(u_new), _ptr(b["v"]),
-                    _ptr(v_new), _ptr(b["dh"]), _ptr(b["du"]), _ptr(b["dv"]), *[_ptr(x) for x in flux2])
-
-    # inputs are untouched (ping-pong), outputs complete
-    assert np.array_equal(b["h"], fld["h"]) and np.array_equal(b["u"], fld["u"]) and np.array_equal(b["v"], fld["v"])
-    rows = slice(1, ny - 1)
-    new = dict(h=h_new, u=u_new, v=v_new, dh=b["dh"], du=b["du"], dv=b["dv"])
-    ref = dict(h=h_ref, u=a["u"], v=a["v"], dh=a["dh"], du=a["du"], dv=a["dv"])
-    ring = np.zeros((ny, pitch), bool)
-    ring[1:ny - 1, 1:nx - 1] = True
-    ring[2:ny - 2, 2:nx - 2] = False
-    bulk = np.zeros((ny, pitch), bool)
-    bulk[2:ny - 2, 2:nx - 2] = True
-    ncol = ((nx - 2) // 4 + 1) * 4           # groups without an interior lane are never touched
-    for k in new:
-        assert not np.isnan(new[k][rows, :ncol]).any(), k
-        # frame cells run the very same arithmetic on the same numbers
-        assert np.array_equal(new[k][ring], ref[k][ring]), k
-        # bulk cells: recomputed fluxes (explicit fma placement) vs stored ones: rounding-level agreement
-        scale = np.abs(ref[k][bulk]).max() + 1e-30
-        assert np.abs(new[k][bulk] - ref[k][bulk]).max() <= 2e-6 * scale, k
-        # halo / pad lanes of the processed rows: exactly what swe_k2_body leaves there
-        outside = ~(ring | bulk)
-        outside[0, :] = outside[-1, :] = False
-        outside[:, ncol:] = False
-        assert np.array_equal(new[k][outside], ref[k][outside]), k
-    # u's and v's halo rows travel with the ping-pong
-    for k, old in (("u", fld["u"]), ("v", fld["v"])):
-        assert np.array_equal(new[k][0, :ncol], old[0, :ncol]) and np.array_equal(new[k][-1, :ncol], old[-1, :ncol])
-
-
-@pytest.mark.parametrize("w", [1, 2])
-@pytest.mark.parametrize("shape", [(19, 26), (8, 12), (33, 64), (12, 45), (9, 13)])
-def test_frame_enumeration_is_exact(emu, shape, w):
-    ny, nx = shape
-    p, *_ = _setup(ny, nx, False, 0, 0)
-    ngroups = p.pitch // 4
-    marks = np.zeros((ny, ngroups), np.int32)
-    total = emu.emu_frame_marks(ctypes.byref(p), w, marks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
-    assert marks.max() == 1 and marks.sum() == total          # no task twice
-    want = np.zeros((ny, ngroups), bool)
-    for j in range(1, ny - 1):
-        for i in range(1, nx - 1):
-            if j <= w or j >= ny - 1 - w or i <= w or i >= nx - 1 - w:
-                want[j, i // 4] = True
-    assert np.array_equal(marks.astype(bool) & want, want)     # every frame cell is covered
-    extra = marks.astype(bool) & ~want
-    assert not extra[w + 1:ny - 1 - w].any()                   # side rows: frame groups only
-
-
-def test_friction_v_ping_pong_equals_in_place(emu):
-    ny, nx = 17, 30
-    p, fld, cor, rng = _setup(ny, nx, False, 0, 1)
-    fe2 = rng.uniform(-1, 1, (ny, p.pitch)).astype(np.float32)
-    fn2 = rng.uniform(-1, 1, (ny, p.pitch)).astype(np.float32)
-    v_ref = fld["v"].copy()
-    emu.emu_k5(ctypes.byref(p), _ptr(v_ref), _ptr(fe2), _ptr(fn2))
-    v_new = np.full_like(v_ref, np.nan)
-    emu.emu_k5_pp(ctypes.byref(p), _ptr(fld["v"]), _ptr(v_new), _ptr(fe2), _ptr(fn2))
-    ncol = ((nx - 2) // 4 + 1) * 4           # the pure pad group is never touched
-    assert np.array_equal(v_new[:, :ncol], v_ref[:, :ncol])
-
-
-def test_merged_friction_kernel_equals_k3_k4(emu):
-    """swe_k34_body (friction-u fluxes inline, out of place) vs K3 -> K4 (fluxes through memory,
-    in place): same numbers -- the claim behind removing one kernel and one exchange per step."""
-    for walls, has_south in (((1, 0), 0), ((0, 1), 1), ((0, 0), 1), ((1, 1), 0)):
-        ny, nx = 21, 30
-        p, fld, cor, rng = _setup(ny, nx, False, *walls, seed=7)
-        ncol = ((nx - 2) // 4 + 1) * 4
-        z = lambda: np.zeros((ny, p.pitch), np.float32)   # noqa: E731
-        u_ref, fe, fn, fe2_ref, fn2_ref = fld["u"].copy(), z(), z(), z(), z()
-        emu.emu_k3_k4(ctypes.byref(p), _ptr(u_ref), _ptr(fld["v"]), _ptr(fe), _ptr(fn), _ptr(fe2_ref),
-                      _ptr(fn2_ref), has_south)
-        u_new, fe2, fn2 = np.full_like(u_ref, np.nan), z(), z()
-        emu.emu_k34(ctypes.byref(p), _ptr(fld["u"]), _ptr(u_new), _ptr(fld["v"]), _ptr(fe2), _ptr(fn2), has_south)
-        assert np.array_equal(u_new[:, :ncol], u_ref[:, :ncol]), (walls, has_south)
-        assert np.array_equal(fe2[1:-1, :ncol], fe2_ref[1:-1, :ncol])
-        assert np.array_equal(fn2[1:-1, :ncol], fn2_ref[1:-1, :ncol])
-
-
-# ---- whole steps: the launch sequence of b2_swe_multistep(_k12), emulated on a process grid -------
+# ---- whole steps: the launch sequence of b2_swe_multistep, emulated on a process grid ------------
 def _blocks(model, PY, PX):
     """Cut the model's global initial condition into (PY x PX) blocks with one halo cell, as
     ShallowWaterModel does per rank; returns per-rank dicts of pitch-padded float32 arrays."""
@@ -227,10 +105,11 @@ def _blocks(model, PY, PX):
 
 def _params(model, blk, ny, nx, pitch, py, PY, first):
     cfg = model.cfg
-    return Params(ny=ny, nx=nx, pitch=pitch, dx=cfg.dx, dy=cfg.dy, dt=cfg.dt, gravity=cfg.gravity,
-                  viscosity=cfg.lateral_viscosity, rdx=np.float32(1) / np.float32(cfg.dx),
-                  rdy=np.float32(1) / np.float32(cfg.dy), ab_a=cfg.ab_a, ab_b=cfg.ab_b, first_step=int(first),
-                  south_wall=int(py == 0), north_wall=int(py == PY - 1), coriolis=blk["cor"].ctypes.data)
+    return _folded(Params(ny=ny, nx=nx, pitch=pitch, dx=cfg.dx, dy=cfg.dy, dt=cfg.dt, gravity=cfg.gravity,
+                          viscosity=cfg.lateral_viscosity, rdx=np.float32(1) / np.float32(cfg.dx),
+                          rdy=np.float32(1) / np.float32(cfg.dy), ab_a=cfg.ab_a, ab_b=cfg.ab_b,
+                          first_step=int(first), south_wall=int(py == 0), north_wall=int(py == PY - 1),
+                          coriolis=blk["cor"].ctypes.data))
 
 
 def _exchange(ranks, names, kinds, nx, PY, PX):
@@ -240,7 +119,8 @@ def _exchange(ranks, names, kinds, nx, PY, PX):
         new_exchange([r[name][:, :nx] for r in ranks], PY, PX, kind)
 
 
-def _emulate(emu, model, PY, PX, nsteps, k12):
+def _emulate(emu, model, PY, PX, nsteps):
+    """The launch sequence of b2_swe_multistep: K1 -> exchange -> K2 -> exchange -> K34 -> exchange -> K5."""
     from ._halo_sim import new_exchange
 
     ranks, ny, nx, pitch = _blocks(model, PY, PX)
@@ -253,51 +133,22 @@ def _emulate(emu, model, PY, PX, nsteps, k12):
     for it in range(nsteps):
         ps = [_params(model, r, ny, nx, pitch, i // PX, PY, it == 0) for i, r in enumerate(ranks)]
         B = ctypes.byref
-        if k12:
-            for r, p in zip(ranks, ps):
-                emu.emu_k12_bulk(B(p), _ptr(r[hk]), _ptr(r[hnk]), _ptr(r["u"]), _ptr(r["u1"]), _ptr(r["v"]),
-                                 _ptr(r["v1"]), _ptr(r["dh"]), _ptr(r["du"]), _ptr(r["dv"]))
-                emu.emu_k1_frame(B(p), _ptr(r[hk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["fe"]), _ptr(r["fn"]),
-                                 _ptr(r["q"]), _ptr(r["ke"]))
-            _exchange(ranks, ("fe", "fn", "q", "ke"), ("u", "v", "h", "h"), nx, PY, PX)
-            for r, p in zip(ranks, ps):
-                emu.emu_k2_ring(B(p), _ptr(r[hk]), _ptr(r[hnk]), _ptr(r["u"]), _ptr(r["u1"]), _ptr(r["v"]),
-                                _ptr(r["v1"]), _ptr(r["dh"]), _ptr(r["du"]), _ptr(r["dv"]), _ptr(r["fe"]),
-                                _ptr(r["fn"]), _ptr(r["q"]), _ptr(r["ke"]))
-            _exchange(ranks, (hnk, "u1", "v1"), ("h", "u", "v"), nx, PY, PX)
-            if k12 == 2:      # friction phase fused as well: bulk kernel + K34 frame -> exchange -> K5 ring
-                for i, (r, p) in enumerate(zip(ranks, ps)):
-                    hs = int(i // PX > 0)
-                    emu.emu_k345_bulk(B(p), _ptr(r["u1"]), _ptr(r["u"]), _ptr(r["v1"]), _ptr(r["v"]), hs)
-                    emu.emu_k34_frame(B(p), _ptr(r["u1"]), _ptr(r["u"]), _ptr(r["v1"]), _ptr(r["fe2"]),
-                                      _ptr(r["fn2"]), hs)
-                _exchange(ranks, ("fe2", "fn2"), ("u", "v"), nx, PY, PX)
-                for r, p in zip(ranks, ps):
-                    emu.emu_k5_ring(B(p), _ptr(r["v1"]), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]))
-            else:
-                for i, (r, p) in enumerate(zip(ranks, ps)):
-                    emu.emu_k34(B(p), _ptr(r["u1"]), _ptr(r["u"]), _ptr(r["v1"]), _ptr(r["fe2"]),
-                                _ptr(r["fn2"]), int(i // PX > 0))
-                _exchange(ranks, ("fe2", "fn2"), ("u", "v"), nx, PY, PX)
-                for r, p in zip(ranks, ps):
-                    emu.emu_k5_pp(B(p), _ptr(r["v1"]), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]))
-        else:
-            for r, p in zip(ranks, ps):
-                emu.emu_k1_all(B(p), _ptr(r[hk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["fe"]), _ptr(r["fn"]),
-                               _ptr(r["q"]), _ptr(r["ke"]))
-            _exchange(ranks, ("fe", "fn", "q", "ke"), ("u", "v", "h", "h"), nx, PY, PX)
-            for r, p in zip(ranks, ps):
-                emu.emu_k2_all(B(p), _ptr(r[hk]), _ptr(r[hnk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["dh"]),
-                               _ptr(r["du"]), _ptr(r["dv"]), _ptr(r["fe"]), _ptr(r["fn"]), _ptr(r["q"]),
-                               _ptr(r["ke"]))
-            _exchange(ranks, (hnk, "u", "v"), ("h", "u", "v"), nx, PY, PX)
-            for i, (r, p) in enumerate(zip(ranks, ps)):
-                emu.emu_k34(B(p), _ptr(r["u"]), _ptr(r["u1"]), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]),
-                            int(i // PX > 0))
-                r["u"], r["u1"] = r["u1"], r["u"]
-            _exchange(ranks, ("fe2", "fn2"), ("u", "v"), nx, PY, PX)
-            for r, p in zip(ranks, ps):
-                emu.emu_k5(B(p), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]))
+        for r, p in zip(ranks, ps):
+            emu.emu_k1_all(B(p), _ptr(r[hk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["fe"]), _ptr(r["fn"]),
+                           _ptr(r["q"]), _ptr(r["ke"]))
+        _exchange(ranks, ("fe", "fn", "q", "ke"), ("u", "v", "h", "h"), nx, PY, PX)
+        for r, p in zip(ranks, ps):
+            emu.emu_k2_all(B(p), _ptr(r[hk]), _ptr(r[hnk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r["dh"]),
+                           _ptr(r["du"]), _ptr(r["dv"]), _ptr(r["fe"]), _ptr(r["fn"]), _ptr(r["q"]),
+                           _ptr(r["ke"]))
+        _exchange(ranks, (hnk, "u", "v"), ("h", "u", "v"), nx, PY, PX)
+        for i, (r, p) in enumerate(zip(ranks, ps)):
+            emu.emu_k34(B(p), _ptr(r["u"]), _ptr(r["u1"]), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]),
+                        int(i // PX > 0))
+            r["u"], r["u1"] = r["u1"], r["u"]
+        _exchange(ranks, ("fe2", "fn2"), ("u", "v"), nx, PY, PX)
+        for r, p in zip(ranks, ps):
+            emu.emu_k5(B(p), _ptr(r["v"]), _ptr(r["fe2"]), _ptr(r["fn2"]))
         hk, hnk = hnk, hk
     return [dict(h=r[hk][:, :nx], u=r["u"][:, :nx], v=r["v"][:, :nx], dh=r["dh"][:, :nx], du=r["du"][:, :nx],
                  dv=r["dv"][:, :nx]) for r in ranks]
@@ -318,7 +169,7 @@ def test_emulated_native_step_matches_the_ops_backend(emu):
     cfg = ShallowWaterConfig(nx=48, ny=24)
     model = ShallowWaterModel(cfg, device="cpu", backend="ops")
     nsteps = 6
-    emu_state = _emulate(emu, model, 1, 1, nsteps, k12=False)[0]
+    emu_state = _emulate(emu, model, 1, 1, nsteps)[0]
     model.multistep(nsteps)
     for name, t in model.state._asdict().items():
         got, want = emu_state[name], t.numpy()
@@ -327,62 +178,6 @@ def test_emulated_native_step_matches_the_ops_backend(emu):
         assert _close(got[1:-1, 1:-1], want[1:-1, 1:-1], tol), name
     assert isinstance(model.h, torch.Tensor)
 
-
-@pytest.mark.parametrize("grid", [(1, 1), (1, 2), (2, 2), (3, 2)])
-def test_emulated_k12_pipeline_matches_standalone_pipeline(emu, grid):
-    """Whole steps on a process grid: the fused flux+tendency pipeline (incl. its frame exchange
-    and the u / v ping-pong) against the stand-alone pipeline, same decomposition."""
-    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
-
-    PY, PX = grid
-    cfg = ShallowWaterConfig(nx=48 * PX, ny=24 * PY)
-    model = ShallowWaterModel(cfg, device="cpu", backend="ops")
-    a = _emulate(emu, model, PY, PX, 5, k12=False)
-    b = _emulate(emu, model, PY, PX, 5, k12=True)
-    for ra, rb in zip(a, b):
-        for name in ra:
-            assert np.isfinite(rb[name]).all(), name
-            tol = 5e-6 if name in ("h", "u", "v") else 1e-3
-            assert _close(rb[name][1:-1, 1:-1], ra[name][1:-1, 1:-1], tol), (grid, name)
-
-
-@pytest.mark.parametrize("grid", [(1, 1), (2, 2)])
-def test_explicit_rounding_build_makes_both_pipelines_bit_identical(emu, emu_explicit, grid):
-    """With B2_SWE_EXPLICIT_ROUNDING=1 the flux kernel and the fused kernel share every rounding:
-    the two pipelines agree to the bit (here: host arithmetic; the device build inherits the property
-    because explicit intrinsics are not contractable), and the switch moves the stand-alone results
-    only at rounding level."""
-    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
-
-    PY, PX = grid
-    model = ShallowWaterModel(ShallowWaterConfig(nx=48 * PX, ny=24 * PY), device="cpu", backend="ops")
-    a = _emulate(emu_explicit, model, PY, PX, 6, k12=False)
-    b = _emulate(emu_explicit, model, PY, PX, 6, k12=True)
-    c = _emulate(emu_explicit, model, PY, PX, 6, k12=2)
-    plain = _emulate(emu, model, PY, PX, 6, k12=False)
-    for ra, rb, rc, rp in zip(a, b, c, plain):
-        for name in ra:
-            assert np.array_equal(ra[name][1:-1, 1:-1], rb[name][1:-1, 1:-1]), (grid, name)
-            assert np.array_equal(ra[name][1:-1, 1:-1], rc[name][1:-1, 1:-1]), (grid, name, "fused friction")
-            tol = 5e-5 if name in ("h", "u", "v") else 1e-3      # per-rank normalisation: v is tiny off the jet
-            assert _close(ra[name][1:-1, 1:-1], rp[name][1:-1, 1:-1], tol), (grid, name)
-
-
-@pytest.mark.parametrize("grid", [(1, 1), (1, 2), (2, 2), (3, 2)])
-def test_emulated_fully_fused_pipeline_matches_standalone_pipeline(emu, grid):
-    """K12 plus the fused friction phase (bulk: u' -> u and v' -> v in one kernel; frame: K34 ->
-    exchange -> K5): 16 instead of 32 array passes per step, same numbers."""
-    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
-
-    PY, PX = grid
-    model = ShallowWaterModel(ShallowWaterConfig(nx=48 * PX, ny=24 * PY), device="cpu", backend="ops")
-    a = _emulate(emu, model, PY, PX, 6, k12=False)
-    b = _emulate(emu, model, PY, PX, 6, k12=2)
-    for ra, rb in zip(a, b):
-        for name in ra:
-            assert np.isfinite(rb[name]).all(), name
-            tol = 5e-5 if name in ("h", "u", "v") else 1e-3
-            assert _close(rb[name][1:-1, 1:-1], ra[name][1:-1, 1:-1], tol), (grid, name)
 
 
 # ---- communication-avoiding step (csrc/b2_swe_ca_body.cuh, b2_swe_ca.cu) -----------------------------
@@ -487,7 +282,7 @@ def test_emulated_ca_pipeline_is_bit_identical_to_the_standalone_pipeline(emu, g
 
     PY, PX = grid
     model = ShallowWaterModel(ShallowWaterConfig(nx=48 * PX, ny=24 * PY), device="cpu", backend="ops")
-    a = _emulate(emu, model, PY, PX, 6, k12=False)
+    a = _emulate(emu, model, PY, PX, 6)
     b = _emulate_ca(emu, model, PY, PX, 6)
     c = _emulate_ca(emu, model, PY, PX, 6, reverse=1)
     for ra, rb, rc in zip(a, b, c):
