@@ -67,7 +67,39 @@ struct B2MoveArgs {
   int dst_blk[B2_MAX_RANKS];
   int opcode;
   int vec_ok;           // out and every block offset are 16-byte aligned -> batched vector pulls
+  // strided input ("fused pack"): when lay.nd > 0 the blocks are gathered element by element from a
+  // non-contiguous tensor while they are staged -- what the reference leaves to an XLA transpose /
+  // copy kernel in front of MPI_Alltoall (tests/collective_ops/test_alltoall.py:43-65)
+  B2Strided lay;
+  long long in_blk_stride;   // bytes between consecutive input blocks (strided input only)
 };
+
+// stage `len` bytes of a block, starting at byte `off` of its row-major order, from strided memory
+__device__ __forceinline__ void b2_gather_bytes(char* __restrict__ dst, const char* __restrict__ base,
+                                                const B2Strided& L, size_t off, size_t len) {
+  const size_t es = (size_t)L.esize;
+  const size_t e0 = off / es, n = len / es;          // chunks are multiples of 16 bytes >= esize
+  for (size_t k = threadIdx.x; k < n; k += blockDim.x) {
+    size_t lin = e0 + k;
+    long long src = 0;
+#pragma unroll
+    for (int d = 3; d >= 0; --d)
+      if (d < L.nd) {
+        const size_t q = lin / (size_t)L.shape[d];
+        src += (long long)(lin - q * (size_t)L.shape[d]) * L.stride[d];
+        lin = q;
+      }
+    const char* sp = base + src * (long long)es;
+    char* dp = dst + k * es;
+    switch (L.esize) {
+      case 1: *dp = *sp; break;
+      case 2: *(unsigned short*)dp = *(const unsigned short*)sp; break;
+      case 4: *(unsigned*)dp = *(const unsigned*)sp; break;
+      case 8: *(unsigned long long*)dp = *(const unsigned long long*)sp; break;
+      default: *(ulonglong2*)dp = *(const ulonglong2*)sp; break;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(B2_THREADS)
 b2_k_move(const B2DevComm c, const B2MoveArgs a) {
@@ -82,9 +114,12 @@ b2_k_move(const B2DevComm c, const B2MoveArgs a) {
   for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const size_t off = ch * a.chunk;
     const size_t len = (a.blk_bytes - off < a.chunk) ? (a.blk_bytes - off) : a.chunk;
-    for (int j = 0; j < a.nin; ++j)
-      b2_copy_bytes<false>(mine + (size_t)j * a.blk_stride + off,
-                           in + (size_t)j * a.blk_bytes + off, len);
+    for (int j = 0; j < a.nin; ++j) {
+      if (a.lay.nd > 0)
+        b2_gather_bytes(mine + (size_t)j * a.blk_stride + off, in + (long long)j * a.in_blk_stride, a.lay, off, len);
+      else
+        b2_copy_bytes<false>(mine + (size_t)j * a.blk_stride + off, in + (size_t)j * a.blk_bytes + off, len);
+    }
     b2_barrier_all(c, ++e, a.opcode);
     if (a.vec_ok) {
       // all sources of a vector are loaded before any is stored: the NVLink round trips of the
@@ -151,6 +186,38 @@ __device__ __forceinline__ void b2_mc_st(void* mc, uint4 v) {
                "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// in-switch reduction of this rank's sub-slice of a chunk, broadcast back through the switch
+template <int DT>
+__device__ __forceinline__ void b2_nvls_slice(const B2DevComm& c, char* mc, size_t off, size_t len) {
+  const int t = threadIdx.x, nt = blockDim.x;
+  const size_t nv = (len + 15) >> 4;
+  const size_t per = (nv + c.size - 1) / c.size;
+  size_t v0 = per * (size_t)c.rank;
+  if (v0 > nv) v0 = nv;
+  size_t v1 = v0 + per;
+  if (v1 > nv) v1 = nv;
+  size_t i = v0 + t;
+  for (; i + 3 * (size_t)nt < v1; i += 4 * (size_t)nt) {
+    uint4 r0 = b2_mc_ld_reduce<DT>(mc + off + (i << 4));
+    uint4 r1 = b2_mc_ld_reduce<DT>(mc + off + ((i + nt) << 4));
+    uint4 r2 = b2_mc_ld_reduce<DT>(mc + off + ((i + 2 * (size_t)nt) << 4));
+    uint4 r3 = b2_mc_ld_reduce<DT>(mc + off + ((i + 3 * (size_t)nt) << 4));
+    b2_mc_st(mc + off + (i << 4), r0);
+    b2_mc_st(mc + off + ((i + nt) << 4), r1);
+    b2_mc_st(mc + off + ((i + 2 * (size_t)nt) << 4), r2);
+    b2_mc_st(mc + off + ((i + 3 * (size_t)nt) << 4), r3);
+  }
+  for (; i < v1; i += nt) b2_mc_st(mc + off + (i << 4), b2_mc_ld_reduce<DT>(mc + off + (i << 4)));
+}
+
+// Software-pipelined over the chunks of a CTA (all CTAs co-resident, chunk k of CTA b is chunk
+// b + k * grid on every rank):
+//
+//   stage(0) A1(0) | stage(1) W1(0) nvls(0) A2(0) A1(1) | stage(2) W2(0) out(0) W1(1) nvls(1) A2(1) A1(2) | ...
+//
+// A = arrive (flags to the peers), W = wait.  The local HBM copies (stage the next chunk, copy
+// the previous result out) sit between an arrive and its wait, so they hide the flag round trip,
+// and CTAs drift to different phases, so HBM copies overlap other CTAs' NVLink phases.
 template <int DT>
 __global__ void __launch_bounds__(B2_THREADS)
 b2_k_allreduce_nvls(const B2DevComm c, const B2ReduceArgs a) {
@@ -162,34 +229,100 @@ b2_k_allreduce_nvls(const B2DevComm c, const B2ReduceArgs a) {
   char* mine = c.stage[c.rank] + par;
   char* mc = c.stage_mc + par;
   const size_t nchunks = (a.nbytes + a.chunk - 1) / a.chunk;
-  const int t = threadIdx.x, nt = blockDim.x;
+  const int t = threadIdx.x;
+#define CH_OFF(ch) ((ch) * a.chunk)
+#define CH_LEN(ch) ((a.nbytes - CH_OFF(ch) < a.chunk) ? (a.nbytes - CH_OFF(ch)) : a.chunk)
+  size_t ch = blockIdx.x;
+  if (ch < nchunks) {
+    b2_copy_bytes<false>(mine + CH_OFF(ch), in + CH_OFF(ch), CH_LEN(ch));
+    b2_barrier_arrive(c, ++e);                                   // A1(0)
+    unsigned e_a1 = e;
+    for (; ch < nchunks; ch += gridDim.x) {
+      const size_t nxt = ch + gridDim.x;
+      const bool more = nxt < nchunks;
+      if (more) b2_copy_bytes<false>(mine + CH_OFF(nxt), in + CH_OFF(nxt), CH_LEN(nxt));
+      b2_barrier_wait(c, e_a1, a.opcode);                        // W1: every rank staged this chunk
+      b2_nvls_slice<DT>(c, mc, CH_OFF(ch), CH_LEN(ch));
+      b2_barrier_arrive(c, ++e);                                 // A2
+      const unsigned e_a2 = e;
+      if (more) {                                                // A1 of the next chunk (staged above)
+        b2_barrier_arrive(c, ++e);
+        e_a1 = e;
+      }
+      b2_barrier_wait(c, e_a2, a.opcode);                        // W2: every sub-slice has landed here
+      b2_copy_bytes<true>(out + CH_OFF(ch), mine + CH_OFF(ch), CH_LEN(ch));
+    }
+  }
+#undef CH_OFF
+#undef CH_LEN
+  __syncthreads();
+  if (t == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
+  b2_finish_bump(c.ticket, c.ticket + 1, 1u, gridDim.x);
+}
 
+// ---------------------------------------------------------------------------
+// bcast: the root writes its data ONCE with multimem.st -- the NVSwitch replicates it into every
+// rank's staging -- instead of P-1 peers pulling P-1 copies over the root's links
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(B2_THREADS)
+b2_k_bcast_mc(const B2DevComm c, const B2MoveArgs a, const int root) {
+  const unsigned ticket = b2_ticket_read(c.ticket);
+  const size_t par = (size_t)(ticket & 1u) * c.stage_half;
+  unsigned e = b2_ld_volatile(c.epoch + blockIdx.x);
+  const char* in = (const char*)a.in;
+  char* out = (char*)a.out;
+  char* mine = c.stage[c.rank] + par;
+  char* mc = c.stage_mc + par;
+  const size_t nchunks = (a.blk_bytes + a.chunk - 1) / a.chunk;
+  const int t = threadIdx.x, nt = blockDim.x;
+  for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const size_t off = ch * a.chunk;
+    const size_t len = (a.blk_bytes - off < a.chunk) ? (a.blk_bytes - off) : a.chunk;
+    if (c.rank == root) {
+      const size_t nv = len >> 4, tail = len & 15;
+      for (size_t i = t; i < nv; i += nt) b2_mc_st(mc + off + (i << 4), b2_ld_stream16(in + off + (i << 4)));
+      if (tail && t == 0) {
+        alignas(16) unsigned char tmp[16] = {0};
+        for (size_t k = 0; k < tail; ++k) tmp[k] = ((const unsigned char*)in)[off + (nv << 4) + k];
+        b2_mc_st(mc + off + (nv << 4), *reinterpret_cast<const uint4*>(tmp));
+      }
+    }
+    b2_barrier_all(c, ++e, a.opcode);
+    if (c.rank != root) b2_copy_bytes<true>(out + off, mine + off, len);
+  }
+  __syncthreads();
+  if (t == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
+  b2_finish_bump(c.ticket, c.ticket + 1, 1u, gridDim.x);
+}
+
+// reduce (SUM, f32 / bf16 / f16): the root reads the in-switch sum of all ranks' staging with
+// multimem.ld_reduce -- one stream of S bytes into the root instead of P-1
+template <int DT>
+__global__ void __launch_bounds__(B2_THREADS)
+b2_k_reduce_root_nvls(const B2DevComm c, const B2ReduceArgs a) {
+  const unsigned ticket = b2_ticket_read(c.ticket);
+  const size_t par = (size_t)(ticket & 1u) * c.stage_half;
+  unsigned e = b2_ld_volatile(c.epoch + blockIdx.x);
+  const char* in = (const char*)a.in;
+  char* out = (char*)a.out;
+  char* mine = c.stage[c.rank] + par;
+  const char* mc = c.stage_mc + par;
+  const size_t nchunks = (a.nbytes + a.chunk - 1) / a.chunk;
+  const int t = threadIdx.x, nt = blockDim.x;
   for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const size_t off = ch * a.chunk;
     const size_t len = (a.nbytes - off < a.chunk) ? (a.nbytes - off) : a.chunk;
-    const size_t nv = (len + 15) >> 4;
     b2_copy_bytes<false>(mine + off, in + off, len);
     b2_barrier_all(c, ++e, a.opcode);
-    const size_t per = (nv + c.size - 1) / c.size;
-    size_t v0 = per * (size_t)c.rank;
-    if (v0 > nv) v0 = nv;
-    size_t v1 = v0 + per;
-    if (v1 > nv) v1 = nv;
-    size_t i = v0 + t;
-    // in-switch reduction of my sub-slice, broadcast back through the switch
-    for (; i + 3 * (size_t)nt < v1; i += 4 * (size_t)nt) {
-      uint4 r0 = b2_mc_ld_reduce<DT>(mc + off + (i << 4));
-      uint4 r1 = b2_mc_ld_reduce<DT>(mc + off + ((i + nt) << 4));
-      uint4 r2 = b2_mc_ld_reduce<DT>(mc + off + ((i + 2 * (size_t)nt) << 4));
-      uint4 r3 = b2_mc_ld_reduce<DT>(mc + off + ((i + 3 * (size_t)nt) << 4));
-      b2_mc_st(mc + off + (i << 4), r0);
-      b2_mc_st(mc + off + ((i + nt) << 4), r1);
-      b2_mc_st(mc + off + ((i + 2 * (size_t)nt) << 4), r2);
-      b2_mc_st(mc + off + ((i + 3 * (size_t)nt) << 4), r3);
+    if (a.has_out) {
+      const size_t nv = (len + 15) >> 4;
+      for (size_t i = t; i < nv; i += nt) {
+        const uint4 r = b2_mc_ld_reduce<DT>(mc + off + (i << 4));
+        const size_t b = i << 4;
+        if (b + 16 <= len) b2_st16(out + off + b, r);
+        else b2_store_partial(out + off + b, r, (int)(len - b));
+      }
     }
-    for (; i < v1; i += nt) b2_mc_st(mc + off + (i << 4), b2_mc_ld_reduce<DT>(mc + off + (i << 4)));
-    b2_barrier_all(c, ++e, a.opcode);
-    b2_copy_bytes<true>(out + off, mine + off, len);
   }
   __syncthreads();
   if (t == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
@@ -201,16 +334,19 @@ b2_k_allreduce_nvls(const B2DevComm c, const B2ReduceArgs a) {
 // ---------------------------------------------------------------------------
 static size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
-// Same answer on every rank: depends only on (nbytes, size, sm_count, max_blocks).
+// Same answer on every rank: depends only on (nbytes, size, max_blocks).  max_blocks is the number of
+// CTAs of a 512-thread collective kernel that are co-resident (one per SM): every CTA of a launch
+// is then resident at once, so the block-paired barriers cannot wait for a CTA that has not been
+// scheduled yet -- independent of the order in which the hardware dispatches CTAs.
 static void pick_chunks(const B2Comm* c, size_t nbytes, size_t* chunk_out, int* grid_out) {
   const size_t unit = 16 * (size_t)c->dev.size;
   const size_t min_chunk = round_up(16 * 1024, unit);
   const size_t max_chunk = round_up(512 * 1024, unit);
   const size_t target = (size_t)c->max_blocks;
-  // large messages: ~4 chunks per CTA, so that CTAs sit at different phases (copy-in / reduce-
-  // scatter / all-gather / copy-out) and local HBM traffic overlaps both NVLink directions;
-  // below 64 MiB one chunk per CTA is faster (latency regime; measured, profiles/README.md)
-  const size_t per_cta = nbytes >= ((size_t)64 << 20) ? 4 : 1;
+  // >= 4 MiB: at least two chunks per CTA, so that the software pipeline of the kernels (stage the
+  // next chunk / copy the previous one out while the flags of this one travel) has something to
+  // overlap and CTAs drift to different phases; below that one chunk per CTA (latency regime)
+  const size_t per_cta = nbytes >= ((size_t)64 << 20) ? 4 : nbytes >= ((size_t)4 << 20) ? 2 : 1;
   size_t chunk = round_up((nbytes + per_cta * target - 1) / (per_cta * target), unit);
   if (chunk < min_chunk) chunk = min_chunk;
   if (chunk > max_chunk) chunk = max_chunk;
@@ -309,6 +445,12 @@ static int reduce_common(B2Comm* c, const void* in, void* out, size_t count, int
       return B2_ERR_BAD_ARG;
     }
     a.algo = B2_ALGO_NVLS;
+    if (opcode == B2_OPC_REDUCE) {
+      if (dtype == B2_F32) b2_k_reduce_root_nvls<B2_F32><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
+      else if (dtype == B2_BF16) b2_k_reduce_root_nvls<B2_BF16><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
+      else b2_k_reduce_root_nvls<B2_F16><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
+      return finish_launch(c, cudaGetLastError(), name);
+    }
     if (dtype == B2_F32) b2_k_allreduce_nvls<B2_F32><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
     else if (dtype == B2_BF16) b2_k_allreduce_nvls<B2_BF16><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
     else b2_k_allreduce_nvls<B2_F16><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
@@ -339,7 +481,10 @@ extern "C" int b2_reduce(B2Comm* c, const void* in, void* out, size_t count, int
     b2_set_error("reduce: invalid root %d", root);
     rc = B2_ERR_BAD_ARG;
   } else {
-    rc = reduce_common(c, in, out, count, dtype, op, B2_ALGO_ONESHOT, 0, c->dev.size,
+    const size_t nbytes = count * b2_dtype_size(dtype);
+    const bool nvls = c->dev.stage_mc != nullptr && op == B2_SUM && c->dev.size > 2 &&
+                      (dtype == B2_F32 || dtype == B2_BF16 || dtype == B2_F16) && nbytes >= c->nvls_min;
+    rc = reduce_common(c, in, out, count, dtype, op, nvls ? B2_ALGO_NVLS : B2_ALGO_ONESHOT, 0, c->dev.size,
                        c->dev.rank == root, B2_OPC_REDUCE, "reduce", stream);
   }
   b2_debug_end(dbg, rc);
@@ -351,10 +496,34 @@ extern "C" int b2_scan(B2Comm* c, const void* in, void* out, size_t count, int d
   char det[96];
   snprintf(det, sizeof det, "with %zu items", count);
   B2DebugScope* dbg = b2_debug_begin(c, "Scan", det, stream);
-  int rc = reduce_common(c, in, out, count, dtype, op, B2_ALGO_ONESHOT, 0, c->dev.rank + 1, 1,
-                         B2_OPC_SCAN, "scan", stream);
+  // small: rank r pulls the copies of ranks 0..r (one phase); large: rank s computes ALL prefixes of
+  // sub-slice s and pushes prefix q to rank q (two phases, S bytes in and out per rank instead of
+  // up to P * S into the last rank)
+  const size_t nbytes = count * b2_dtype_size(dtype);
+  const int algo = (c->dev.size > 2 && nbytes > c->oneshot_max) ? B2_ALGO_TWOSHOT : B2_ALGO_ONESHOT;
+  int rc = reduce_common(c, in, out, count, dtype, op, algo, 0, c->dev.rank + 1, 1, B2_OPC_SCAN, "scan", stream);
   b2_debug_end(dbg, rc);
   return rc;
+}
+
+static int set_layout(B2MoveArgs& a, const B2Strided* lay, const char* name) {
+  a.lay.nd = 0;
+  a.in_blk_stride = 0;
+  if (lay == nullptr || lay->nd == 0) return 0;
+  const int es = lay->esize;
+  if (lay->nd < 0 || lay->nd > 4 || !(es == 1 || es == 2 || es == 4 || es == 8 || es == 16)) {
+    b2_set_error("%s: unsupported strided layout (nd=%d, element size %d)", name, lay->nd, es);
+    return B2_ERR_BAD_ARG;
+  }
+  long long n = 1;
+  for (int d = 0; d < lay->nd; ++d) n *= lay->shape[d];
+  if ((size_t)n * (size_t)es != a.blk_bytes) {
+    b2_set_error("%s: strided layout does not match the block size", name);
+    return B2_ERR_BAD_ARG;
+  }
+  a.lay = *lay;
+  a.in_blk_stride = lay->blk_stride * es;
+  return 0;
 }
 
 static int move_common(B2Comm* c, B2MoveArgs& a, const char* name, cudaStream_t stream) {
@@ -369,7 +538,7 @@ static int move_common(B2Comm* c, B2MoveArgs& a, const char* name, cudaStream_t 
   return finish_launch(c, cudaGetLastError(), name);
 }
 
-extern "C" int b2_allgather(B2Comm* c, const void* in, void* out, size_t blk_bytes,
+extern "C" int b2_allgather(B2Comm* c, const void* in, void* out, size_t blk_bytes, const B2Strided* lay,
                             cudaStream_t stream) {
   char det[96];
   snprintf(det, sizeof det, "sending %zu bytes", blk_bytes);
@@ -380,12 +549,13 @@ extern "C" int b2_allgather(B2Comm* c, const void* in, void* out, size_t blk_byt
   a.nin = 1;
   a.nsrc = c->dev.size;
   for (int q = 0; q < c->dev.size; ++q) { a.src_rank[q] = q; a.src_blk[q] = 0; a.dst_blk[q] = q; }
-  int rc = move_common(c, a, "allgather", stream);
+  int rc = set_layout(a, lay, "allgather");
+  if (rc == 0) rc = move_common(c, a, "allgather", stream);
   b2_debug_end(dbg, rc);
   return rc;
 }
 
-extern "C" int b2_alltoall(B2Comm* c, const void* in, void* out, size_t blk_bytes,
+extern "C" int b2_alltoall(B2Comm* c, const void* in, void* out, size_t blk_bytes, const B2Strided* lay,
                            cudaStream_t stream) {
   char det[96];
   snprintf(det, sizeof det, "sending %zu bytes per peer", blk_bytes);
@@ -398,12 +568,13 @@ extern "C" int b2_alltoall(B2Comm* c, const void* in, void* out, size_t blk_byte
   for (int q = 0; q < c->dev.size; ++q) {
     a.src_rank[q] = q; a.src_blk[q] = c->dev.rank; a.dst_blk[q] = q;
   }
-  int rc = move_common(c, a, "alltoall", stream);
+  int rc = set_layout(a, lay, "alltoall");
+  if (rc == 0) rc = move_common(c, a, "alltoall", stream);
   b2_debug_end(dbg, rc);
   return rc;
 }
 
-extern "C" int b2_bcast(B2Comm* c, const void* in, void* out, size_t nbytes, int root,
+extern "C" int b2_bcast(B2Comm* c, const void* in, void* out, size_t nbytes, int root, const B2Strided* lay,
                         cudaStream_t stream) {
   char det[96];
   snprintf(det, sizeof det, "%zu bytes from root %d", nbytes, root);
@@ -418,13 +589,32 @@ extern "C" int b2_bcast(B2Comm* c, const void* in, void* out, size_t nbytes, int
     a.in = in; a.out = out; a.blk_bytes = nbytes; a.opcode = B2_OPC_BCAST;
     if (c->dev.rank == root) { a.nin = 1; a.nsrc = 0; }
     else { a.nin = 0; a.nsrc = 1; a.src_rank[0] = root; a.src_blk[0] = 0; a.dst_blk[0] = 0; }
-    rc = move_common(c, a, "bcast", stream);
+    rc = set_layout(a, c->dev.rank == root ? lay : nullptr, "bcast");
+    // through the switch (one multimem.st stream from the root) once the root's links would be the
+    // bottleneck of P-1 pulls; contiguous 16-byte aligned root buffers only (every rank must take
+    // the same path: the decision uses sizes only, the root's layout is normalised by the caller)
+    const bool mc = c->dev.stage_mc != nullptr && c->dev.size > 2 && nbytes >= c->bcast_mc_min;
+    if (rc == 0 && mc && nbytes > 0) {
+      if ((rc = check_stage(c, a.opcode, a.blk_bytes, "bcast")) == 0) {
+        if (c->dev.rank == root && (a.lay.nd > 0 || (((uintptr_t)in) & 15) != 0)) {
+          b2_set_error("bcast: the multicast path needs a contiguous 16-byte aligned root buffer");
+          rc = B2_ERR_BAD_ARG;
+        } else {
+          int grid;
+          pick_chunks(c, a.blk_bytes, &a.chunk, &grid);
+          b2_k_bcast_mc<<<grid, B2_THREADS, 0, stream>>>(c->dev, a, root);
+          rc = finish_launch(c, cudaGetLastError(), "bcast");
+        }
+      }
+    } else if (rc == 0) {
+      rc = move_common(c, a, "bcast", stream);
+    }
   }
   b2_debug_end(dbg, rc);
   return rc;
 }
 
-extern "C" int b2_gather(B2Comm* c, const void* in, void* out, size_t blk_bytes, int root,
+extern "C" int b2_gather(B2Comm* c, const void* in, void* out, size_t blk_bytes, int root, const B2Strided* lay,
                          cudaStream_t stream) {
   char det[96];
   snprintf(det, sizeof det, "sending %zu bytes to root %d", blk_bytes, root);
@@ -442,13 +632,14 @@ extern "C" int b2_gather(B2Comm* c, const void* in, void* out, size_t blk_bytes,
       a.nsrc = c->dev.size;
       for (int q = 0; q < c->dev.size; ++q) { a.src_rank[q] = q; a.src_blk[q] = 0; a.dst_blk[q] = q; }
     }
-    rc = move_common(c, a, "gather", stream);
+    rc = set_layout(a, lay, "gather");
+    if (rc == 0) rc = move_common(c, a, "gather", stream);
   }
   b2_debug_end(dbg, rc);
   return rc;
 }
 
-extern "C" int b2_scatter(B2Comm* c, const void* in, void* out, size_t blk_bytes, int root,
+extern "C" int b2_scatter(B2Comm* c, const void* in, void* out, size_t blk_bytes, int root, const B2Strided* lay,
                           cudaStream_t stream) {
   char det[96];
   snprintf(det, sizeof det, "%zu bytes per rank from root %d", blk_bytes, root);
@@ -464,7 +655,8 @@ extern "C" int b2_scatter(B2Comm* c, const void* in, void* out, size_t blk_bytes
     a.nin = (c->dev.rank == root) ? c->dev.size : 0;
     a.nsrc = 1;
     a.src_rank[0] = root; a.src_blk[0] = c->dev.rank; a.dst_blk[0] = 0;
-    rc = move_common(c, a, "scatter", stream);
+    rc = set_layout(a, c->dev.rank == root ? lay : nullptr, "scatter");
+    if (rc == 0) rc = move_common(c, a, "scatter", stream);
   }
   b2_debug_end(dbg, rc);
   return rc;

@@ -156,6 +156,28 @@ __device__ __forceinline__ void b2_barrier_all(const B2DevComm& c, unsigned e, i
   __syncthreads();
 }
 
+// The two halves of b2_barrier_all, for software pipelining: local work placed between the
+// arrive and the wait (staging the next chunk, copying the previous one out) hides the NVLink
+// round trip of the flags.  Epochs of one CTA must still be used in increasing order.
+__device__ __forceinline__ void b2_barrier_arrive(const B2DevComm& c, unsigned e) {
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < c.size) {
+    unsigned* remote =
+        (unsigned*)(c.heap[t] + c.lay.flags_off) + (size_t)blockIdx.x * B2_MAX_RANKS + c.rank;
+    b2_st_release_sys(remote, e);
+  }
+}
+__device__ __forceinline__ void b2_barrier_wait(const B2DevComm& c, unsigned e, int opcode) {
+  const int t = threadIdx.x;
+  if (t < c.size) {
+    const unsigned* local =
+        (const unsigned*)(c.heap[c.rank] + c.lay.flags_off) + (size_t)blockIdx.x * B2_MAX_RANKS + t;
+    b2_wait_ge(c, local, e, opcode, t);
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // ticket: one value per kernel launch, identical on every CTA, advanced by the
 // LAST CTA TO FINISH (so every CTA has already read it).  Lives in local device

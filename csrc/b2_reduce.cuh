@@ -74,6 +74,24 @@ b2_k_reduce_chunked(const B2DevComm c, const B2ReduceArgs a) {
       if (v0 > nv) v0 = nv;
       size_t v1 = v0 + per;
       if (v1 > nv) v1 = nv;
+      if (a.opcode == B2_OPC_SCAN) {
+        // two-phase scan: all P copies of a vector are loaded BEFORE the prefixes overwrite them
+        // (prefix q lands where rank q staged its own contribution; this rank is the only reader)
+        for (size_t i = v0 + t; i < v1; i += nt) {
+          uint4 v[B2_MAX_RANKS];
+#pragma unroll
+          for (int q = 0; q < B2_MAX_RANKS; ++q)
+            if (q < c.size) v[q] = b2_ld_peer16(c.stage[q] + par + off + (i << 4));
+          B2Vec<T> acc;
+          acc.load(v[0]);
+#pragma unroll
+          for (int q = 1; q < B2_MAX_RANKS; ++q)
+            if (q < c.size) {
+              acc.template accumulate<OP>(v[q]);
+              b2_st16(c.stage[q] + par + off + (i << 4), acc.store());
+            }
+        }
+      } else
       for (size_t i = v0 + t; i < v1; i += nt) {
         B2Vec<T> acc;
         acc.load(b2_ld_peer16(c.stage[0] + par + off + (i << 4)));

@@ -430,7 +430,10 @@ extern "C" B2Comm* b2_comm_create(int device, int rank, int nranks, B2Seg* ctl, 
   c->ll_max = 64 * 1024;
   c->oneshot_max = 512 * 1024;
   c->nvls_min = 64 * 1024 + 1;
-  c->max_blocks = c->sm_count * 2;
+  c->bcast_mc_min = 256 * 1024;
+  // one 512-thread CTA of the collective kernels (<= 128 registers per thread) fits per SM: grids are
+  // capped at the co-resident count (see pick_chunks in b2_collectives.cu)
+  c->max_blocks = c->sm_count;
   if (c->max_blocks > B2_MAX_BLOCKS) c->max_blocks = B2_MAX_BLOCKS;
   cudaDeviceSynchronize();
   return c;

@@ -52,6 +52,7 @@ struct B2Comm {
   size_t ll_max;
   size_t oneshot_max;
   size_t nvls_min;
+  size_t bcast_mc_min;          // bcast: root multimem.st from this size on
   int max_blocks;
   B2ErrorRecord* err_host;      // host pointer of the mapped error record
   int launches;                 // kernels launched through this communicator
@@ -109,6 +110,16 @@ int b2_comm_check_error(B2Comm* c, char* buf, int buflen);     // 0 = ok
 int b2_comm_destroy(B2Comm* c);
 size_t b2_stage_need(int opcode, int nranks, size_t blk_bytes); // staging half needed by an op
 
+// Layout of a non-contiguous input (elements, innermost dimension last); nd == 0: contiguous.
+// Dimension 0 of an alltoall / scatter input (the per-peer blocks) is described separately.
+struct B2Strided {
+  int nd;
+  int esize;                 // element size in bytes: 1, 2, 4, 8 or 16
+  long long shape[4];
+  long long stride[4];       // in elements
+  long long blk_stride;      // elements between consecutive blocks
+};
+
 // --- collectives (all enqueue on `stream`, never synchronise the host) --------
 int b2_barrier(B2Comm* c, cudaStream_t stream);
 int b2_allreduce(B2Comm* c, const void* in, void* out, size_t count, int dtype, int op, int algo,
@@ -117,12 +128,16 @@ int b2_reduce(B2Comm* c, const void* in, void* out, size_t count, int dtype, int
               cudaStream_t stream);
 int b2_scan(B2Comm* c, const void* in, void* out, size_t count, int dtype, int op,
             cudaStream_t stream);
-int b2_allgather(B2Comm* c, const void* in, void* out, size_t blk_bytes, cudaStream_t stream);
-int b2_alltoall(B2Comm* c, const void* in, void* out, size_t blk_bytes, cudaStream_t stream);
-int b2_bcast(B2Comm* c, const void* in, void* out, size_t nbytes, int root, cudaStream_t stream);
-int b2_gather(B2Comm* c, const void* in, void* out, size_t blk_bytes, int root,
+// `lay` (may be null = contiguous) describes a strided input; the pack is fused into the staging copy
+int b2_allgather(B2Comm* c, const void* in, void* out, size_t blk_bytes, const B2Strided* lay,
+                 cudaStream_t stream);
+int b2_alltoall(B2Comm* c, const void* in, void* out, size_t blk_bytes, const B2Strided* lay,
+                cudaStream_t stream);
+int b2_bcast(B2Comm* c, const void* in, void* out, size_t nbytes, int root, const B2Strided* lay,
+             cudaStream_t stream);
+int b2_gather(B2Comm* c, const void* in, void* out, size_t blk_bytes, int root, const B2Strided* lay,
               cudaStream_t stream);
-int b2_scatter(B2Comm* c, const void* in, void* out, size_t blk_bytes, int root,
+int b2_scatter(B2Comm* c, const void* in, void* out, size_t blk_bytes, int root, const B2Strided* lay,
                cudaStream_t stream);
 
 // --- point to point ----------------------------------------------------------

@@ -112,7 +112,7 @@ def _allgather_bytes(comm: Comm, x: torch.Tensor) -> list:
         return [flat.clone()]
     outs = [torch.empty_like(flat) for _ in range(comm.size)]
     dist.all_gather(outs, flat, group=comm._group)
-    return outs
+    return comm._in_rank_order(outs)
 
 
 def _gather_stack(comm: Comm, x: torch.Tensor) -> torch.Tensor:

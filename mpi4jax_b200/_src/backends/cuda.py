@@ -74,7 +74,7 @@ def _all_gather_obj(comm: Comm, obj):
     if comm.size == 1:
         return [obj]
     dist.all_gather_object(out, obj, group=comm._group)
-    return out
+    return comm._in_rank_order(out)
 
 
 def _exchange_fds(comm: Comm, fd: Optional[int]) -> dict:
@@ -398,20 +398,20 @@ class NativeComm:
         return out
 
     def allgather(self, x: torch.Tensor) -> torch.Tensor:
-        x = _prep(x)
+        x, lay = _layout(x)
         out = torch.empty((self.comm.size, *x.shape), dtype=x.dtype, device=x.device)
         nb = x.numel() * x.element_size()
         self.ensure_stage(codes.OPC_ALLGATHER, nb)
-        self._check(_lib().b2_allgather(self.handle, x.data_ptr(), out.data_ptr(), nb, self._stream()),
+        self._check(_lib().b2_allgather(self.handle, x.data_ptr(), out.data_ptr(), nb, _ref(lay), self._stream()),
                     "Allgather")
         return out
 
     def alltoall(self, x: torch.Tensor) -> torch.Tensor:
-        x = _prep(x)
-        out = torch.empty_like(x)
+        x, lay = _layout(x, lead=True)
+        out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
         nb = (x.numel() // self.comm.size) * x.element_size()
         self.ensure_stage(codes.OPC_ALLTOALL, nb)
-        self._check(_lib().b2_alltoall(self.handle, x.data_ptr(), out.data_ptr(), nb, self._stream()),
+        self._check(_lib().b2_alltoall(self.handle, x.data_ptr(), out.data_ptr(), nb, _ref(lay), self._stream()),
                     "Alltoall")
         return out
 
@@ -422,19 +422,19 @@ class NativeComm:
         out = x if is_root else torch.empty_like(x)
         self.ensure_stage(codes.OPC_BCAST, nb)
         rc = _lib().b2_bcast(self.handle, x.data_ptr() if is_root else None,
-                             None if is_root else out.data_ptr(), nb, root, self._stream())
+                             None if is_root else out.data_ptr(), nb, root, None, self._stream())
         self._check(rc, "Bcast")
         return out
 
     def gather(self, x: torch.Tensor, root: int) -> Optional[torch.Tensor]:
-        x = _prep(x)
+        x, lay = _layout(x)
         nb = x.numel() * x.element_size()
         is_root = self.comm.rank == root
         out = (torch.empty((self.comm.size, *x.shape), dtype=x.dtype, device=x.device)
                if is_root else None)
         self.ensure_stage(codes.OPC_GATHER, nb)
         rc = _lib().b2_gather(self.handle, x.data_ptr(), out.data_ptr() if is_root else None, nb,
-                              root, self._stream())
+                              root, _ref(lay), self._stream())
         self._check(rc, "Gather")
         return out
 
@@ -442,10 +442,10 @@ class NativeComm:
         is_root = self.comm.rank == root
         out = torch.empty(out_shape, dtype=dtype, device=self.comm.device)
         nb = out.numel() * out.element_size()
-        src = _prep(x) if is_root else None
+        src, lay = _layout(x, lead=True) if is_root else (None, None)
         self.ensure_stage(codes.OPC_SCATTER, nb)
         rc = _lib().b2_scatter(self.handle, src.data_ptr() if is_root else None, out.data_ptr(), nb,
-                               root, self._stream())
+                               root, _ref(lay), self._stream())
         self._check(rc, "Scatter")
         return out
 
@@ -571,6 +571,44 @@ class _NullEvent:
 
     def synchronize(self):
         torch.cuda.synchronize(self.device)
+
+
+def _layout(x: torch.Tensor, lead: bool = False):
+    """(tensor to pass, B2Strided or None).  A non-contiguous input of a data-movement collective is
+    NOT materialised by a separate torch copy kernel: its strides travel to the native kernel, which
+    gathers the elements while it stages them (the fused pack of SURVEY C5).  ``lead``: dimension 0
+    indexes the per-peer blocks (alltoall, scatter on the root).  Layouts the kernel cannot describe
+    (more than 4 non-mergeable dimensions, overlapping / negative strides) fall back to a copy."""
+    if x.numel() == 0 or (x.is_contiguous() and x.data_ptr() % 16 == 0):
+        return x, None
+    if x.is_contiguous():
+        return x.clone(), None
+    shape, stride = list(x.shape), list(x.stride())
+    blk_stride = 0
+    if lead:
+        blk_stride = stride[0]
+        shape, stride = shape[1:], stride[1:]
+    dims = [(n, st) for n, st in zip(shape, stride) if n != 1]
+    merged = []
+    for n, st in dims:                       # merge dimensions that are contiguous with respect to each other
+        if merged and merged[-1][1] == st * n:
+            merged[-1] = (merged[-1][0] * n, st)
+        else:
+            merged.append((n, st))
+    if not merged:
+        merged = [(1, 1)]
+    if len(merged) > 4 or any(st < 0 for _, st in merged) or blk_stride < 0:
+        return x.contiguous(), None
+    lay = native.B2Strided()
+    lay.nd, lay.esize = len(merged), x.element_size()
+    for d, (n, st) in enumerate(merged):
+        lay.shape[d], lay.stride[d] = n, st
+    lay.blk_stride = blk_stride
+    return x, lay
+
+
+def _ref(lay):
+    return ctypes.byref(lay) if lay is not None else None
 
 
 def _prep(x: torch.Tensor) -> torch.Tensor:

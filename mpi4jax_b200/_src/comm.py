@@ -254,6 +254,11 @@ class Comm:
         self._ranks = list(ranks)
         self._global_rank = dist.get_rank()
         self._rank = self._ranks.index(self._global_rank)
+        # torch.distributed numbers the members of a group by ascending global rank, whatever order
+        # `ranks` was given in; a communicator made by Split(color, key) orders them by key.
+        # _order[r] = torch's group index of the member with communicator rank r.
+        by_global = sorted(self._ranks)
+        self._order = [by_global.index(g) for g in self._ranks]
         self._name = name
         _comm_counter += 1
         self._id = _comm_counter
@@ -302,6 +307,7 @@ class Comm:
         self._check_alive()
         info = [None] * self.size
         dist.all_gather_object(info, (int(color), int(key), self._global_rank), group=self._group)
+        info = self._in_rank_order(info)
         if color == UNDEFINED:
             return None
         members = sorted((k, r) for cc, k, r in info if cc == color)
@@ -348,7 +354,7 @@ class Comm:
         if self.size == 1:
             return [obj]
         dist.all_gather_object(out, obj, group=self._group)
-        return out
+        return self._in_rank_order(out)
 
     def gather(self, obj, root: int = 0):
         everything = self.allgather(obj)           # gloo's gather_object needs the same traffic
@@ -413,6 +419,10 @@ class Comm:
 
     def _global(self, rank_in_comm: int) -> int:
         return self._ranks[rank_in_comm]
+
+    def _in_rank_order(self, gathered: list) -> list:
+        """Results of a torch.distributed all_gather on this group, reordered by communicator rank."""
+        return [gathered[self._order[r]] for r in range(len(self._ranks))]
 
     def _native_comm(self):
         """The native (GPU) side of the communicator; created collectively on first use."""

@@ -64,6 +64,17 @@ class B2HaloDesc(Structure):
     ]
 
 
+class B2Strided(Structure):
+    """Layout of a non-contiguous input of a data-movement collective (csrc/b2_runtime.h)."""
+    _fields_ = [
+        ("nd", c_int),
+        ("esize", c_int),
+        ("shape", c_longlong * 4),
+        ("stride", c_longlong * 4),
+        ("blk_stride", c_longlong),
+    ]
+
+
 class B2SweParams(Structure):
     _fields_ = [
         ("ny", c_int),
@@ -157,11 +168,11 @@ _SIGNATURES = {
     "b2_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "b2_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "b2_scan": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
-    "b2_allgather": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "b2_alltoall": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "b2_bcast": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
-    "b2_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
-    "b2_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "b2_allgather": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, POINTER(B2Strided), c_void_p]),
+    "b2_alltoall": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, POINTER(B2Strided), c_void_p]),
+    "b2_bcast": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, POINTER(B2Strided), c_void_p]),
+    "b2_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, POINTER(B2Strided), c_void_p]),
+    "b2_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, POINTER(B2Strided), c_void_p]),
     "b2_status_alloc": (POINTER(B2StatusRecord), []),
     "b2_status_free": (None, [POINTER(B2StatusRecord)]),
     "b2_send": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
@@ -193,7 +204,7 @@ _SIGNATURES = {
 
 
 #: must equal B2_ABI_VERSION in csrc/b2_common.h
-ABI_VERSION = 8
+ABI_VERSION = 9
 _ABI_FIELDS = ("abi_version", "sizeof_status_record", "sizeof_halo_desc", "sizeof_swe_params",
                "sizeof_swe_state", "sizeof_error_record", "max_ranks", "p2p_nslot", "sizeof_swe_ca")
 

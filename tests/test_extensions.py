@@ -118,6 +118,10 @@ def test_dup_and_split_on_a_sub_communicator_do_not_involve_other_ranks(device):
         got = m.allreduce(torch.ones(3, device=device), MPI.SUM, comm=again)
         assert torch.equal(got, torch.full((3,), float(sub.Get_size()), device=device))
         assert again.Get_rank() == sub.Get_size() - 1 - sub.Get_rank()
+        # key order, not launch order, numbers the ranks: order-sensitive results follow it
+        mine = torch.tensor([float(again.Get_rank())], device=device)
+        assert torch.equal(m.allgather(mine, comm=again)[:, 0], torch.arange(float(again.Get_size()), device=device))
+        assert again.allgather(again.Get_rank()) == list(range(again.Get_size()))
         again.Free()
         dup.Free()
     total = m.allreduce(torch.ones(2, device=device), MPI.SUM)          # default comm: every rank
