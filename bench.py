@@ -162,6 +162,8 @@ def main() -> int:
     comm.Barrier()
     ms = max_over_ranks(start.elapsed_time(end), comm)
     steps_per_s = K / (ms * 1e-3)
+    nproc_y, nproc_x, ny_local, nx_local, pipeline = (model.nproc_y, model.nproc_x, model.ny_local, model.nx_local,
+                                                      model.pipeline)
     finite = bool(torch.isfinite(model.h).all().item())
     mass = model.total_mass().item()
     checks["finite"] = finite
@@ -209,6 +211,35 @@ def main() -> int:
     e2e_s = max_over_ranks(t1 - t0, comm)
     e2e_value = K / e2e_s
 
+    # ---- extras: the reference-style USER program (BASELINE config 3) --------------------------
+    # the same discrete system written with torch arithmetic and the PUBLIC sendrecv / send / recv
+    # ops in the reference's message order (models/shallow_water.py, backend="ops"), under jit
+    ops_rate = None
+    try:
+        ops_model = ShallowWaterModel(ShallowWaterConfig.for_resolution(ns.grid, ns.grid), comm=comm, device=dev,
+                                      backend="ops")
+        ops_model.step(first_step=True)
+        n_ops = 5
+        ops_fn = m.jit(lambda: ops_model.multistep(n_ops, first_step=False), warmup=1)
+        ops_fn()
+        ops_fn()
+        torch.cuda.synchronize()
+        comm.Barrier()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m.barrier(comm=comm)
+        s0.record()
+        ops_fn()
+        ops_fn()
+        e0.record()
+        torch.cuda.synchronize()
+        ops_ms = max_over_ranks(s0.elapsed_time(e0), comm) / (2 * n_ops)
+        ops_rate = {"steps_per_s": round(1e3 / ops_ms, 1), "ms_per_step": round(ops_ms, 4),
+                    "note": "backend='ops': torch stencils + public sendrecv/send/recv (48 p2p ops per step at 8 "
+                            "ranks, as the reference issues them), captured by mpi4jax_b200.jit"}
+        del ops_model, ops_fn
+    except Exception as exc:  # pragma: no cover
+        ops_rate = {"error": str(exc)[:200]}
+
     # ---- extras: allreduce bus bandwidth sweep (N > 1) -----------------------------------------
     sweep = None
     if size > 1 and not ns.no_sweep:
@@ -234,11 +265,11 @@ def main() -> int:
                 "model": "examples/shallow_water.py (non-linear shallow water, C-grid, AB2)",
                 "global_batch": f"{ns.grid}x{ns.grid} grid (the demo's 1800 km x 900 km domain)",
                 "seq_len": None,
-                "parallelism": f"2-D domain decomposition {model.nproc_y}x{model.nproc_x}",
+                "parallelism": f"2-D domain decomposition {nproc_y}x{nproc_x}",
                 "l2": ("L2 flushed before the timed region; per-rank state "
-                       f"{13 * model.ny_local * model.nx_local * 4 / 2**20:.0f} MiB vs 126 MiB L2"),
+                       f"{13 * ny_local * nx_local * 4 / 2**20:.0f} MiB vs 126 MiB L2"),
                 "graph_chunk_steps": C,
-                "kernel_path": model.pipeline,
+                "kernel_path": pipeline,
                 "baseline_note": ("vs_baseline divides by the reference's published P100 numbers for "
                                   "a 3600x1800 grid (80 steps/s at n=1, 129 at n=2), this run uses "
                                   "the 2.6x larger 4096x4096 grid named in BASELINE.json"),
@@ -257,6 +288,7 @@ def main() -> int:
             },
             "checks": checks,
         }
+        out["public_ops_shallow_water"] = ops_rate
         if sweep is not None:
             out["allreduce_busbw_gbs"] = sweep
         print(json.dumps(out))

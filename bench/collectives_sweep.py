@@ -3,6 +3,7 @@
 * allreduce 1 KB - 1 GB, fp32 + bf16, every transport (ll / oneshot / twoshot / nvls / auto)
   next to NCCL on the same box                                   (configs 2)
 * allgather and alltoall 1 KB - 1 GB per-rank payload vs NCCL     (config 4)
+* bcast, reduce, gather, scatter (root = last rank) vs NCCL, scan (no NCCL counterpart)
 * sendrecv ring, halo exchange latency
 
 Timing: ``reps`` back-to-back ops captured in ONE CUDA graph, one replay timed with CUDA
@@ -31,7 +32,8 @@ from mpi4jax_b200.utils import max_over_ranks  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--max-bytes", type=int, default=1 << 30)
 ap.add_argument("--out", default="gpurun_out/collectives_sweep.json")
-ap.add_argument("--quick", action="store_true")
+ap.add_argument("--quick", action="store_true", help="every fourth size")
+ap.add_argument("--skip-allreduce-algos", action="store_true", help="time only the automatic choice")
 ns = ap.parse_args()
 
 comm = MPI.COMM_WORLD
@@ -119,7 +121,7 @@ for dtype, dname in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
         x = torch.ones(nbytes // torch.empty((), dtype=dtype).element_size(), dtype=dtype, device=dev)
         row = {}
         reps = reps_for(nbytes)
-        for algo in ("auto", "ll", "oneshot", "twoshot", "nvls"):
+        for algo in (("auto",) if ns.skip_allreduce_algos else ("auto", "ll", "oneshot", "twoshot", "nvls")):
             if algo == "ll" and nbytes > (64 << 10):
                 continue
             if algo == "nvls" and not has_nvls:
@@ -170,6 +172,55 @@ for nbytes in sizes:
         del y
     if rank == 0:
         print("allgather/alltoall", nbytes, row, result["alltoall"].get(str(nbytes)), flush=True)
+    del x
+
+# ---------------------------------------------------------------- rooted ops + scan (per-rank payload = nbytes)
+result.update({"bcast": {}, "reduce": {}, "gather": {}, "scatter": {}, "scan": {}})
+root = size - 1
+for nbytes in [b for b in sizes if b >= 1 << 10][::1 if ns.quick else 2]:
+    reps = reps_for(nbytes)
+    x = torch.ones(nbytes // 4, device=dev)
+    rows = {k: {} for k in ("bcast", "reduce", "scan")}
+    us = time_graph(lambda: m.bcast(x, root, comm=comm), reps)
+    rows["bcast"]["ours"] = {"us": round(us, 2), "gbs": round(nbytes / us / 1e3, 1)}
+    us = time_graph(lambda: m.reduce(x, MPI.SUM, root, comm=comm), reps)
+    rows["reduce"]["ours"] = {"us": round(us, 2), "gbs": round(nbytes / us / 1e3, 1)}
+    us = time_graph(lambda: m.scan(x, MPI.SUM, comm=comm), reps)
+    rows["scan"]["ours"] = {"us": round(us, 2), "gbs": round(nbytes / us / 1e3, 1)}
+    if nccl is not None:
+        y = x.clone()
+        us = time_nccl(lambda: dist.broadcast(y, src=root, group=nccl), reps)
+        rows["bcast"]["nccl"] = {"us": round(us, 2), "gbs": round(nbytes / us / 1e3, 1)}
+        us = time_nccl(lambda: dist.reduce(y, dst=root, group=nccl), reps)
+        rows["reduce"]["nccl"] = {"us": round(us, 2), "gbs": round(nbytes / us / 1e3, 1)}
+        del y
+    for k in rows:
+        result[k][str(nbytes)] = rows[k]
+    if nbytes * size <= (2 << 30):
+        rows2 = {"gather": {}, "scatter": {}}
+        us = time_graph(lambda: m.gather(x, root, comm=comm), reps)
+        rows2["gather"]["ours"] = {"us": round(us, 2), "gbs": round(nbytes * (size - 1) / us / 1e3, 1)}
+        big = torch.ones(size, nbytes // 4, device=dev) if rank == root else x
+        us = time_graph(lambda: m.scatter(big, root, comm=comm), reps)
+        rows2["scatter"]["ours"] = {"us": round(us, 2), "gbs": round(nbytes * (size - 1) / us / 1e3, 1)}
+        if nccl is not None:
+            try:
+                outs = [torch.empty_like(x) for _ in range(size)] if rank == root else None
+                us = time_eager(lambda: dist.gather(x, outs, dst=root, group=nccl), max(reps, 5))
+                rows2["gather"]["nccl"] = {"us": round(us, 2), "gbs": round(nbytes * (size - 1) / us / 1e3, 1)}
+                ins = [torch.ones_like(x) for _ in range(size)] if rank == root else None
+                y = torch.empty_like(x)
+                us = time_eager(lambda: dist.scatter(y, ins, src=root, group=nccl), max(reps, 5))
+                rows2["scatter"]["nccl"] = {"us": round(us, 2), "gbs": round(nbytes * (size - 1) / us / 1e3, 1)}
+                del outs, ins, y
+            except Exception as exc:  # pragma: no cover
+                rows2["gather"]["nccl"] = {"error": str(exc)[:100]}
+        for k in rows2:
+            result[k][str(nbytes)] = rows2[k]
+        del big
+    if rank == 0:
+        print("rooted", nbytes, {k: v for k, v in rows.items()}, {k: result[k].get(str(nbytes)) for k in ("gather", "scatter")},
+              flush=True)
     del x
 
 # ---------------------------------------------------------------- p2p ring + halo

@@ -16,11 +16,12 @@
 #include <cstddef>
 #include <cstdint>
 
-#define B2_ABI_VERSION 9   // bump whenever a struct shared with Python or a C signature changes
+#define B2_ABI_VERSION 10   // bump whenever a struct shared with Python or a C signature changes
 #define B2_MAX_RANKS 16          // ranks per NVLink domain we support (8 on HGX B200)
 #define B2_MAX_BLOCKS 1024       // max CTAs per collective launch (flag rows)
 #define B2_P2P_NSLOT 8           // ring slots per directed pair
 #define B2_P2P_MAX_LANES 64      // CTAs cooperating on one p2p message
+#define B2_P2P_LL_MAX 8192       // payload bytes up to which a p2p message travels flag-in-data
 #define B2_HALO_MAX_FIELDS 8
 
 // ---- dtype / op codes (must match mpi4jax_b200/_src/native/codes.py) -------
@@ -105,6 +106,7 @@ static inline size_t b2_dtype_size(int dt) {
 //   [halo flags] 8 sides x 64 B                     fused halo exchange (arrival counters)
 //   [ll]         2 parities x P x ll_cap            flag-in-data allreduce buffers
 //   [p2p slots]  P x NSLOT x slot_bytes             eager/streaming payload ring
+//   [p2p LL]     P x NSLOT x 16 KiB                 small messages, 8-byte {word, seq} stores
 //   [halo bufs]  2 parities x 8 sides x halo_cap
 //   [halo LL]    2 parities x 8 sides x 2*halo_cap  (fused stencil+halo kernels)
 //   -- separate, growable segment --
@@ -119,6 +121,7 @@ struct B2Layout {
   size_t ll_cap;          // bytes per (parity, source) LL buffer (wire bytes = 2x payload)
   size_t p2p_slot_off;
   size_t p2p_slot_bytes;
+  size_t p2p_ll_off;      // P x NSLOT x (2 * B2_P2P_LL_MAX): flag-in-data copies of small messages
   size_t halo_buf_off;
   size_t halo_cap;        // bytes per (parity, direction)
   size_t halo_ll_off;     // flag-in-data halo buffers of the fused stencil kernels

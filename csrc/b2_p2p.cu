@@ -32,6 +32,12 @@
 // Messages larger than a slot stream through the ring and can only be matched
 // at the head of the pair's queue -- like MPI's rendezvous protocol, where the
 // blocked sender would not have reached the later send either.
+//
+// Small messages (<= B2_P2P_LL_MAX bytes) travel flag-in-data: every 4-byte word is pushed as one
+// 8-byte {word, seq + 1} store into the slot's LL area and the receiver polls the words themselves,
+// so the header needs no release fence over the payload and the message costs ONE NVLink one-way
+// latency (the halo kernels' transport, b2_halo_ll.cuh).  Matching, tags, Status and credits are
+// unchanged: the header is still written, its size field tells the receiver which format to read.
 #include <cstdio>
 #include <cstring>
 
@@ -68,6 +74,38 @@ struct B2P2PArgs {
   int opcode;
 };
 
+// ---- flag-in-data transport of small messages ---------------------------------------------------
+__device__ __forceinline__ bool p2p_is_ll(size_t nbytes) { return nbytes > 0 && nbytes <= B2_P2P_LL_MAX; }
+__device__ __forceinline__ unsigned p2p_load_word(const char* src, size_t w, size_t nbytes) {
+  const size_t b = w << 2;
+  if (b + 4 <= nbytes && (((uintptr_t)src) & 3) == 0) return *reinterpret_cast<const unsigned*>(src + b);
+  unsigned v = 0;
+  for (size_t k = 0; k < 4 && b + k < nbytes; ++k) v |= (unsigned)(unsigned char)src[b + k] << (8 * k);
+  return v;
+}
+__device__ __forceinline__ void p2p_store_word(char* dst, size_t w, size_t nbytes, unsigned v) {
+  const size_t b = w << 2;
+  if (b + 4 <= nbytes && (((uintptr_t)dst) & 3) == 0) { *reinterpret_cast<unsigned*>(dst + b) = v; return; }
+  for (size_t k = 0; k < 4 && b + k < nbytes; ++k) dst[b + k] = (char)(v >> (8 * k));
+}
+__device__ __forceinline__ void p2p_ll_put(uint2* p, unsigned v, unsigned flag) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(flag));
+}
+__device__ __forceinline__ unsigned p2p_ll_get(const B2DevComm& c, const uint2* p, unsigned flag, int opcode, int src) {
+  unsigned v, f;
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
+  while (true) {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
+    if (f == flag) return v;
+    if ((++spins & 0xfffu) == 0) {
+      unsigned long long now = b2_gtime();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > c.timeout_ns) b2_fatal(c, B2_ERR_TIMEOUT, opcode, src, flag, f, 7);
+    }
+  }
+}
+
 __device__ __forceinline__ void stripe_of(size_t fraglen, int lanes, int lane, size_t* lo,
                                           size_t* hi) {
   size_t stripe = (fraglen + lanes - 1) / lanes;
@@ -100,9 +138,17 @@ __device__ void p2p_send_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
       b2_wait_ge(c, ack, fs + 1u - B2_P2P_NSLOT, a.opcode, a.dest);
     }
     __syncthreads();
-    char* dslot = dheap + c.lay.p2p_slot_off + ((size_t)c.rank * B2_P2P_NSLOT + slot) * slot_bytes;
-    b2_copy_bytes<false>(dslot + lo, src + fragoff + lo, hi - lo);
-    __syncthreads();
+    if (p2p_is_ll(a.send_bytes)) {
+      // flag-in-data: no barrier between the payload and the header (nothing to fence)
+      uint2* ll = (uint2*)(dheap + c.lay.p2p_ll_off + ((size_t)c.rank * B2_P2P_NSLOT + slot) * (2 * B2_P2P_LL_MAX));
+      const size_t nw = (a.send_bytes + 3) >> 2;
+      for (size_t w = threadIdx.x; w < nw; w += blockDim.x)
+        p2p_ll_put(ll + w, p2p_load_word(src, w, a.send_bytes), fs + 1u);
+    } else {
+      char* dslot = dheap + c.lay.p2p_slot_off + ((size_t)c.rank * B2_P2P_NSLOT + slot) * slot_bytes;
+      b2_copy_bytes<false>(dslot + lo, src + fragoff + lo, hi - lo);
+      __syncthreads();
+    }
     if (threadIdx.x == 0) {
       unsigned* hdr = (unsigned*)(dheap + c.lay.p2p_hdr_off) +
                       (((size_t)c.rank * B2_P2P_NSLOT + slot) * B2_P2P_MAX_LANES + lane) * 4;
@@ -288,8 +334,15 @@ __device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
       }
     }
     __syncthreads();
-    const char* sslot = myheap + c.lay.p2p_slot_off + ((size_t)src * B2_P2P_NSLOT + slot) * slot_bytes;
-    b2_copy_bytes<true>(dst + fragoff + lo, sslot + lo, hi - lo);
+    if (p2p_is_ll(a.recv_bytes)) {
+      const uint2* ll = (const uint2*)(myheap + c.lay.p2p_ll_off + ((size_t)src * B2_P2P_NSLOT + slot) * (2 * B2_P2P_LL_MAX));
+      const size_t nw = (a.recv_bytes + 3) >> 2;
+      for (size_t w = threadIdx.x; w < nw; w += blockDim.x)
+        p2p_store_word(dst, w, a.recv_bytes, p2p_ll_get(c, ll + w, fs + 1u, a.opcode, src));
+    } else {
+      const char* sslot = myheap + c.lay.p2p_slot_off + ((size_t)src * B2_P2P_NSLOT + slot) * slot_bytes;
+      b2_copy_bytes<true>(dst + fragoff + lo, sslot + lo, hi - lo);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();

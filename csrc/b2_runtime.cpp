@@ -363,6 +363,7 @@ static B2Layout make_layout(int nranks, size_t slot_bytes, size_t ll_cap, size_t
   L.ll_off = take(2 * (size_t)nranks * L.ll_cap);
   L.p2p_slot_bytes = round_up(slot_bytes, 4096);
   L.p2p_slot_off = take((size_t)nranks * B2_P2P_NSLOT * L.p2p_slot_bytes);
+  L.p2p_ll_off = take((size_t)nranks * B2_P2P_NSLOT * 2 * B2_P2P_LL_MAX);
   L.halo_cap = round_up(halo_cap, 4096);
   L.halo_buf_off = take(2 * 8 * L.halo_cap);
   L.halo_ll_cap = 2 * L.halo_cap;

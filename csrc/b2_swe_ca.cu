@@ -167,7 +167,11 @@ static cudaEvent_t g_ev[4];
 
 static int ca_streams() {
   if (g_side) return 0;
-  if (cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking) != cudaSuccess) {
+  // highest priority: the frame kernels are tiny and on the critical path, their CTAs must not queue
+  // behind the thousands of CTAs of the bulk kernel running next to them
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, hi) != cudaSuccess) {
     b2_set_error("swe_ca: cudaStreamCreate failed");
     g_side = nullptr;
     return 1;

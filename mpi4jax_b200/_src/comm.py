@@ -136,6 +136,13 @@ class Status:
     """
 
     def __init__(self):
+        # every Status can be named by an integer (like a communicator): the traceable frontend passes
+        # it through compiled graphs as a plain attribute (compile_ops.py), the counterpart of the
+        # reference baking the address of the mpi4py Status object into the custom call (recv.py:100-103)
+        global _status_counter
+        _status_counter += 1
+        self._id = _status_counter
+        _status_registry[self._id] = self
         self._source = ANY_SOURCE
         self._tag = ANY_TAG
         self._count_bytes = 0
@@ -192,6 +199,8 @@ class Status:
 
 
 BYTE = object()
+_status_registry: "weakref.WeakValueDictionary[int, Status]" = weakref.WeakValueDictionary()
+_status_counter = 0
 
 _comm_registry: "weakref.WeakSet[Comm]" = weakref.WeakSet()
 _world_lock = threading.Lock()

@@ -48,6 +48,17 @@ def _c(comm_id: int) -> Comm:
                        "collected after the function using it was compiled)")
 
 
+def _st(status_id: int):
+    """Status id -> object (0 = no status requested)."""
+    if status_id == 0:
+        return None
+    st = _comm_mod._status_registry.get(status_id)
+    if st is None:
+        raise RuntimeError(f"mpi4jax_b200: Status #{status_id} was garbage collected after the function "
+                           "using it was compiled; keep a reference to it")
+    return st
+
+
 # ---------------------------------------------------------------- op definitions
 @custom_op("mpi4jax_b200::allreduce", mutates_args=())
 def _allreduce(x: torch.Tensor, op: int, comm_id: int) -> torch.Tensor:
@@ -217,28 +228,29 @@ def _(x, dest, tag, comm_id):
 
 
 @custom_op("mpi4jax_b200::recv", mutates_args=())
-def _recv(template: torch.Tensor, source: int, tag: int, comm_id: int) -> torch.Tensor:
-    return _dispatch.recv(_c(comm_id), template, source, tag, None)
+def _recv(template: torch.Tensor, source: int, tag: int, comm_id: int, status_id: int) -> torch.Tensor:
+    return _dispatch.recv(_c(comm_id), template, source, tag, _st(status_id))
 
 
 @_recv.register_fake
-def _(template, source, tag, comm_id):
+def _(template, source, tag, comm_id, status_id):
     return torch.empty_like(template, memory_format=torch.contiguous_format)
 
 
 @custom_op("mpi4jax_b200::sendrecv", mutates_args=())
 def _sendrecv(sendbuf: torch.Tensor, recvbuf: torch.Tensor, source: int, dest: int, sendtag: int,
-              recvtag: int, comm_id: int) -> torch.Tensor:
-    return _dispatch.sendrecv(_c(comm_id), sendbuf.contiguous(), recvbuf, source, dest, sendtag, recvtag, None)
+              recvtag: int, comm_id: int, status_id: int) -> torch.Tensor:
+    return _dispatch.sendrecv(_c(comm_id), sendbuf.contiguous(), recvbuf, source, dest, sendtag, recvtag,
+                              _st(status_id))
 
 
 @_sendrecv.register_fake
-def _(sendbuf, recvbuf, source, dest, sendtag, recvtag, comm_id):
+def _(sendbuf, recvbuf, source, dest, sendtag, recvtag, comm_id, status_id):
     return torch.empty_like(recvbuf, memory_format=torch.contiguous_format)
 
 
 def _sendrecv_setup(ctx, inputs, output):
-    sendbuf, _, ctx.source, ctx.dest, ctx.sendtag, ctx.recvtag, ctx.comm_id = inputs
+    sendbuf, _, ctx.source, ctx.dest, ctx.sendtag, ctx.recvtag, ctx.comm_id, _ = inputs
     ctx.send_meta = (tuple(sendbuf.shape), sendbuf.dtype, sendbuf.device)
 
 
@@ -248,8 +260,8 @@ def _sendrecv_backward(ctx, g):
     shape, dtype, device = ctx.send_meta
     template = torch.empty(shape, dtype=dtype, device=device)
     back = torch.ops.mpi4jax_b200.sendrecv(g.contiguous(), template, ctx.dest, ctx.source,
-                                           max(ctx.recvtag, 0), ctx.sendtag, ctx.comm_id)
-    return back, None, None, None, None, None, None
+                                           max(ctx.recvtag, 0), ctx.sendtag, ctx.comm_id, 0)
+    return back, None, None, None, None, None, None, None
 
 
 _sendrecv.register_autograd(_sendrecv_backward, setup_context=_sendrecv_setup)
@@ -318,10 +330,13 @@ class compiled:
         torch.ops.mpi4jax_b200.send(x, int(dest), int(tag), _register(comm))
 
     @staticmethod
-    def recv(x, source=ANY_SOURCE, *, tag=ANY_TAG, comm=None):
-        return torch.ops.mpi4jax_b200.recv(x, int(source), int(tag), _register(comm))
+    def recv(x, source=ANY_SOURCE, *, tag=ANY_TAG, comm=None, status=None):
+        """``status``: an ``MPI.Status`` filled when the compiled function runs (as under ``jax.jit`` in
+        the reference, tests/collective_ops/test_send_and_recv.py:113-153); keep it alive."""
+        return torch.ops.mpi4jax_b200.recv(x, int(source), int(tag), _register(comm),
+                                           0 if status is None else status._id)
 
     @staticmethod
-    def sendrecv(sendbuf, recvbuf, source, dest, *, sendtag=0, recvtag=ANY_TAG, comm=None):
+    def sendrecv(sendbuf, recvbuf, source, dest, *, sendtag=0, recvtag=ANY_TAG, comm=None, status=None):
         return torch.ops.mpi4jax_b200.sendrecv(sendbuf, recvbuf, int(source), int(dest), int(sendtag),
-                                               int(recvtag), _register(comm))
+                                               int(recvtag), _register(comm), 0 if status is None else status._id)

@@ -132,3 +132,24 @@ def test_compiled_gather_scatter_allgather_shapes_under_compile(device):
     assert (g.shape == (size, 4)) if rank == 0 else torch.equal(g, t)
     assert torch.equal(s, torch.arange(4, dtype=torch.float32, device=device) + 10 * rank)
     m.flush()
+
+
+def test_compiled_recv_and_sendrecv_fill_a_status(device):
+    """``status=`` on the traceable path (reference: the Status is filled under jit,
+    tests/collective_ops/test_send_and_recv.py:113-153, test_sendrecv.py:28-60)."""
+    st_a, st_b = MPI.Status(), MPI.Status()
+    nxt, prv = (rank + 1) % size, (rank - 1) % size
+
+    def f(t):
+        a = mc.sendrecv(t, t, prv, nxt, sendtag=4, recvtag=4, comm=comm, status=st_a)
+        mc.send(t * 2, nxt, tag=9, comm=comm)
+        b = mc.recv(t, prv, tag=9, comm=comm, status=st_b)
+        return a, b
+
+    t = torch.arange(6, dtype=torch.float32, device=device) + 100 * rank
+    a, b = torch.compile(f, backend="aot_eager", fullgraph=True)(t)
+    want = torch.arange(6, dtype=torch.float32, device=device) + 100 * prv
+    assert torch.equal(a, want) and torch.equal(b, want * 2)
+    for st, tag in ((st_a, 4), (st_b, 9)):
+        assert st.Get_source() == prv and st.Get_tag() == tag and st.Get_count() == 6
+    m.flush()

@@ -133,3 +133,54 @@ def test_comm_reserve(device):
     m.comm_reserve(1 << 20, comm=comm)
     x = torch.ones(1 << 18, device=device)
     assert torch.equal(m.allreduce(x, MPI.SUM, comm=comm), x * size)
+
+
+def test_strided_inputs_are_packed_by_the_collective_itself(device):
+    """Non-contiguous inputs (transposes, slices) of the data-movement collectives: on CUDA the
+    strides go to the native kernel, which gathers while it stages (no ``.contiguous()`` copy
+    kernel in front, cf. the reference's regression tests/collective_ops/test_alltoall.py:43-65)."""
+    base = torch.arange(float(size * 6 * 10), device=device).reshape(size, 6, 10) + 1000.0 * rank
+    views = {
+        "transposed": base.transpose(1, 2),                 # (size, 10, 6), inner stride 10
+        "sliced": base[:, ::2, 1:9:3],                      # (size, 3, 3)
+        "lead_stride": base.transpose(0, 1)[:size] if size <= 6 else base,     # block stride != block size
+    }
+    for name, x in views.items():
+        assert x.shape[0] == size
+        want = x.contiguous()
+        got = m.alltoall(x, comm=comm)
+        ref = m.alltoall(want, comm=comm)
+        assert torch.equal(got, ref), ("alltoall", name)
+        assert torch.equal(m.allgather(x[0], comm=comm), m.allgather(want[0], comm=comm)), ("allgather", name)
+        root = size - 1
+        g, gr = m.gather(x[0], root, comm=comm), m.gather(want[0], root, comm=comm)
+        assert torch.equal(g, gr) or rank != root, ("gather", name)
+        sc = m.scatter(x if rank == root else torch.empty_like(want[0]), root, comm=comm)
+        scr = m.scatter(want if rank == root else torch.empty_like(want[0]), root, comm=comm)
+        assert torch.equal(sc, scr), ("scatter", name)
+    for dtype in (torch.uint8, torch.bfloat16, torch.float64, torch.complex128):
+        t = (torch.arange(size * 8 * 4, device=device).reshape(size, 8, 4) % 13 + rank).to(dtype).transpose(1, 2)
+        assert torch.equal(m.alltoall(t, comm=comm), m.alltoall(t.contiguous(), comm=comm)), dtype
+
+
+@pytest.mark.parametrize("nbytes", [1 << 12, 3 << 20])
+def test_large_rooted_ops_and_scan(device, nbytes):
+    """Sizes on both sides of the switch-over to the multicast paths (bcast by multimem.st, reduce by
+    multimem.ld_reduce on the root, two-phase scan) -- closed-form results, root = last rank."""
+    n = nbytes // 4
+    base = (torch.arange(n, device=device) % 97).float()
+    x = base + rank
+    root = size - 1
+    b = m.bcast(x if rank == root else torch.empty_like(x), root, comm=comm)
+    assert torch.equal(b, base + root)
+    r = m.reduce(x, MPI.SUM, root, comm=comm)
+    assert torch.equal(r, base * size + size * (size - 1) / 2 if rank == root else x)
+    s = m.scan(x, MPI.SUM, comm=comm)
+    assert torch.equal(s, base * (rank + 1) + rank * (rank + 1) / 2)
+    s = m.scan((x % 5).to(torch.int32), MPI.MAX, comm=comm)
+    want = torch.stack([((base + q) % 5).to(torch.int32) for q in range(rank + 1)]).max(0).values
+    assert torch.equal(s, want)
+    xb = (torch.arange(n, device=device) % 7 + rank).to(torch.bfloat16)
+    rb = m.reduce(xb, MPI.SUM, 0, comm=comm)
+    if rank == 0:
+        assert torch.equal(rb.float(), (torch.arange(n, device=device) % 7).float() * size + size * (size - 1) / 2)
