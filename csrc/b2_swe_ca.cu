@@ -3,14 +3,16 @@
 //
 // One model step (the reference's shallow_water_step, examples/shallow_water.py:270-403):
 //
-//   stream s  (bulk) :  K12 bulk ------------------> friction bulk ------------+--> next step
-//                         \                            ^                        |
-//   stream s2 (frame):  A (tendencies, frame) -> X (deep halo exchange) -> D (friction, frame + ext)
+//   stream s  (bulk) :  S  the whole step on the bulk, one pass over memory (b2_swe_strip.cuh) ----+--> next step
+//                                                                                                   |
+//   stream s2 (frame):  A (tendencies, frame band) -> X (deep halo exchange) -> D (friction, frame + ext)
 //
-// The bulk kernels read no halo and write no frame cell, so the NVLink round of X is hidden
-// behind them; cross edges: friction bulk needs A (u', v' next to the frame), D needs K12 bulk.
-// Under CUDA-graph capture (mpi4jax_b200.jit) the event fork / join becomes graph edges.
-// 16 array passes per step on the bulk (12 + 4) instead of 32, one exchange instead of three.
+// S reads only the step's input arrays and writes only bulk cells of the output arrays (every
+// prognostic array is a ping-pong pair), A / X / D own the frame: no edge between the two streams
+// inside a step, two at the step boundary (S(t+1) reads what D(t) wrote next to the bulk, A(t+1)
+// what S(t) wrote next to the frame).  The NVLink round of X is hidden behind S.  Under CUDA-graph
+// capture (mpi4jax_b200.jit) the event fork / join becomes graph edges.
+// 12 array passes per step instead of 32, one exchange instead of three, 4 launches instead of 7.
 #include <cstdio>
 #include <cstdlib>
 
@@ -18,6 +20,7 @@
 #include "b2_halo_ll.cuh"
 #include "b2_runtime.h"
 #include "b2_swe_ca_body.cuh"
+#include "b2_swe_strip.cuh"
 
 extern "C" void b2_set_error(const char* fmt, ...);
 extern "C" void b2_count_launch(B2Comm* c);
@@ -26,25 +29,42 @@ extern "C" int b2_swe_multistep(B2Comm* c, const B2SweParams* p0, const B2SweSta
 
 #define CA_THREADS 256
 
+// Optional device-side timeline (MPI4JAX_B200_SWE_TIMELINE=1, scripts/swe_timeline.py): every CTA folds
+// its entry / exit %globaltimer into the [first start, last end] pair of its kernel's slot.  Unlike a
+// profiler, which serialises the launches, this shows how the two streams actually overlap inside a
+// CUDA-graph replay.  Null pointer = off (the default): one predictable branch per CTA.
+struct CAStamp {
+  unsigned long long* slot;      // {min start, max end} or null
+};
+__device__ __forceinline__ void ca_stamp_begin(const CAStamp& s) {
+  if (s.slot != nullptr && threadIdx.x == 0) atomicMin(s.slot, b2_gtime());
+}
+__device__ __forceinline__ void ca_stamp_end(const CAStamp& s) {
+  if (s.slot != nullptr && threadIdx.x == 0) atomicMax(s.slot + 1, b2_gtime());
+}
+
 // ---- frame kernels (one thread per cell; a few thousand cells) ------------------------------------
-__global__ void __launch_bounds__(CA_THREADS) swe_ca_tend_frame(const CACtx c, const CAFrame f) {
+__global__ void __launch_bounds__(CA_THREADS) swe_ca_tend_frame(const CACtx c, const CAFrame f, const CAStamp ts) {
+  ca_stamp_begin(ts);
   int j, i;
-  if (!ca_frame_cell(c.p, f, c.x.cb1, (long long)blockIdx.x * CA_THREADS + threadIdx.x, j, i)) return;
-  swe_ca_tend_cell(c, j, i);
+  if (ca_frame_cell(c.p, f, (long long)blockIdx.x * CA_THREADS + threadIdx.x, j, i)) swe_ca_tend_cell(c, j, i);
+  ca_stamp_end(ts);
 }
 
 // friction on the frame cells (u', v' -> ua_out, va_out) and u'' / v'' of the neighbours' cells
 __global__ void __launch_bounds__(CA_THREADS) swe_ca_fric_frame(const CACtx c, const CAFrame f,
                                                                 float* __restrict__ ua_out,
-                                                                float* __restrict__ va_out) {
+                                                                float* __restrict__ va_out, const CAStamp ts) {
+  ca_stamp_begin(ts);
   const long long t = (long long)blockIdx.x * CA_THREADS + threadIdx.x;
   int j, i;
   if (t < f.total) {
-    ca_frame_cell(c.p, f, c.x.cb1, t, j, i);
+    ca_frame_cell(c.p, f, t, j, i);
     swe_ca_fric_cell(c, ua_out, va_out, j, i);
   } else if (ca_ext_cell(c.p, t - f.total, j, i)) {
     swe_ca_fric_ext_cell(c, ua_out, va_out, j, i);
   }
+  ca_stamp_end(ts);
 }
 
 // after (re)initialising the state: no friction step has happened yet, so the "fresh" values of
@@ -75,28 +95,24 @@ __global__ void __launch_bounds__(CA_THREADS) swe_ca_init_ext(const B2SweParams 
   }
 }
 
-// ---- bulk kernels: the vectorised bodies of b2_swe_k12_body.cuh on whole groups -------------------
-template <int OCC>
-__global__ void __launch_bounds__(SWE_THREADS, OCC)
-swe_ca_bulk_k12(const B2SweParams p, const int cb1, const float* __restrict__ h, float* __restrict__ h_new,
-                const float* __restrict__ u, float* __restrict__ u_new, const float* __restrict__ v,
-                float* __restrict__ v_new, float* __restrict__ dh, float* __restrict__ du,
-                float* __restrict__ dv) {
-  const long long t = (long long)blockIdx.x * SWE_THREADS + threadIdx.x;
-  if (t >= ca_bulk_tasks(p, cb1)) return;
-  int j, i0;
-  ca_bulk_task(p, cb1, t, j, i0);
-  swe_k12_body(p, h, h_new, u, u_new, v, v_new, dh, du, dv, j, i0);
-}
-
-__global__ void __launch_bounds__(SWE_THREADS, 4)
-swe_ca_bulk_fric(const B2SweParams p, const int cb1, const float* __restrict__ u, float* __restrict__ u_new,
-                 const float* __restrict__ v, float* __restrict__ v_new) {
-  const long long t = (long long)blockIdx.x * SWE_THREADS + threadIdx.x;
-  if (t >= ca_bulk_tasks(p, cb1)) return;
-  int j, i0;
-  ca_bulk_task(p, cb1, t, j, i0);
-  swe_k345_body(p, u, u_new, v, v_new, j, i0);
+// ---- bulk kernel: the whole step in one pass (phases and geometry: b2_swe_strip.cuh) ---------------
+// every phase ends with a barrier: the next one reads what other threads just wrote to the rings
+struct StripSync {
+  StripThr t;
+  template <class F>
+  __device__ __forceinline__ void operator()(F&& f) const {
+    f(t);
+    __syncthreads();
+  }
+};
+__global__ void __launch_bounds__(STRIP_NT) swe_ca_bulk_step(const StripArgs a, const CAStamp ts) {
+  ca_stamp_begin(ts);
+  __shared__ StripSmem sm;
+  const StripGeo g = strip_geo(a.p, a.cb1, (int)blockIdx.x);
+  StripSync each;
+  each.t = strip_thread(a, g, (int)threadIdx.x);
+  strip_cta(a, sm, g, each);
+  ca_stamp_end(ts);
 }
 
 // ---- X: three layers of (h', u', v') to all eight neighbours, flag-in-data (b2_halo_ll.cuh) -----
@@ -105,7 +121,8 @@ swe_ca_bulk_fric(const B2SweParams p, const int cb1, const float* __restrict__ u
 struct CAExt3 { float* a[CA_NF]; };
 
 __global__ void __launch_bounds__(CA_THREADS) b2_k_halo_ca(const B2DevComm c, const B2HaloDesc d,
-                                                           const CAExt3 ext, const int epitch) {
+                                                           const CAExt3 ext, const int epitch, const CAStamp ts) {
+  ca_stamp_begin(ts);
   __shared__ unsigned s_rx[FS_NSIDES], s_tx[FS_NSIDES];
   __shared__ int s_cnt[FS_NSIDES + 1];
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
@@ -159,11 +176,12 @@ __global__ void __launch_bounds__(CA_THREADS) b2_k_halo_ca(const B2DevComm c, co
       __threadfence();
     }
   }
+  ca_stamp_end(ts);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
 static cudaStream_t g_side = nullptr;
-static cudaEvent_t g_ev[4];
+static cudaEvent_t g_ev[3];
 
 static int ca_streams() {
   if (g_side) return 0;
@@ -176,7 +194,7 @@ static int ca_streams() {
     g_side = nullptr;
     return 1;
   }
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < 3; ++k)
     if (cudaEventCreateWithFlags(&g_ev[k], cudaEventDisableTiming) != cudaSuccess) {
       b2_set_error("swe_ca: cudaEventCreate failed");
       return 1;
@@ -213,8 +231,17 @@ static int ca_check(B2Comm* c, const B2SweParams& p, const B2SweCA& x) {
   return 0;
 }
 
+// timeline buffer: [step][kernel 0 = A, 1 = S (bulk), 2 = X, 3 unused, 4 = D][start, end]
+static unsigned long long* g_stamps = nullptr;
+static int g_stamp_steps = 0;
+static CAStamp ca_slot(int step, int kernel) {
+  CAStamp s;
+  s.slot = (g_stamps != nullptr && step >= 0 && step < g_stamp_steps) ? g_stamps + ((size_t)step * 5 + kernel) * 2 : nullptr;
+  return s;
+}
+
 static int ca_exchange(B2Comm* c, const B2HaloDesc& topo, const B2SweParams& p, const B2SweCA& x, float* f0,
-                       float* f1, float* f2, cudaStream_t s) {
+                       float* f1, float* f2, cudaStream_t s, CAStamp ts = CAStamp{nullptr}) {
   B2HaloDesc d = topo;
   d.ny = p.ny; d.nx = p.nx; d.pitch = p.pitch;
   d.nfields = CA_NF;
@@ -235,11 +262,18 @@ static int ca_exchange(B2Comm* c, const B2HaloDesc& topo, const B2SweParams& p, 
   unsigned ctas = ca_blocks(total, CA_THREADS);          // pure latency: about one element per thread
   if (ctas < 8) ctas = 8;
   if (ctas > 120) ctas = 120;                            // all co-resident next to the bulk kernel's CTAs
-  b2_k_halo_ca<<<ctas, CA_THREADS, 0, s>>>(c->dev, d, ext, x.epitch);
+  b2_k_halo_ca<<<ctas, CA_THREADS, 0, s>>>(c->dev, d, ext, x.epitch, ts);
   return ca_done(c, "halo_ca");
 }
 
 extern "C" {
+
+// Debug timeline: `buf` holds nsteps * 5 * 2 u64 (device memory, start slots preset to ~0, end slots to 0);
+// pass null to switch it off again.  Applies to multistep calls (and graphs captured) afterwards.
+void b2_swe_ca_timeline(unsigned long long* buf, int nsteps) {
+  g_stamps = buf;
+  g_stamp_steps = buf ? nsteps : 0;
+}
 
 // Fill the ext arrays from a state whose main arrays are complete (after reset / load_state):
 // deep exchange of (h, u, v), then fresh := exchanged and the ring mirror.  Collective.
@@ -258,7 +292,7 @@ int b2_swe_ca_init(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const
 
 int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const B2SweCA* x0,
                         const B2HaloDesc* topo, int nsteps, int first_step, cudaStream_t s) {
-  // blocks too small for the bulk / frame split, or no friction step to bring u, v back home
+  // blocks too small for the bulk / frame split, or no friction step: the stand-alone kernels
   if (!swe_ca_supported(*p0) || !(p0->viscosity > 0.f) || !st->u1 || !st->v1)
     return b2_swe_multistep(c, p0, st, topo, nsteps, first_step, s);
   B2SweParams p = *p0;
@@ -267,18 +301,21 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
   if (int rc = ca_check(c, p, x)) return rc;
   if (int rc = ca_streams()) return rc;
   const cudaStream_t s2 = g_side;
-  const cudaEvent_t e0 = g_ev[0], eA = g_ev[1], eB = g_ev[2], eD = g_ev[3];
-  float* h = st->h0;
-  float* hn = st->h1;
-  const CAFrame f = ca_frame(p, x.cb1);
-  const unsigned bulk_blocks = ca_blocks(ca_bulk_tasks(p, x.cb1), SWE_THREADS);
-  const unsigned frame_blocks = ca_blocks(f.total, CA_THREADS);
-  const unsigned fric_blocks = ca_blocks(f.total + ca_ext_total(p), CA_THREADS);
-  static int k12_occ = 0;       // resident CTAs per SM the flux+tendency kernel is compiled for (2: 92 regs; 3: 84)
-  if (k12_occ == 0) {
-    const char* e = getenv("MPI4JAX_B200_SWE_K12_OCC");
-    k12_occ = (e && e[0] == '2') ? 2 : 3;
-  }
+  const cudaEvent_t e0 = g_ev[0], eS = g_ev[1], eD = g_ev[2];
+  // ping-pong pairs; the flux arrays of the stand-alone path are free here and serve as partners of
+  // the tendencies and as the frame band's u', v' store
+  float* H[2] = {st->h0, st->h1};
+  float* U[2] = {st->u, st->u1};
+  float* V[2] = {st->v, st->v1};
+  float* DH[2] = {st->dh, st->q};
+  float* DU[2] = {st->du, st->ke};
+  float* DV[2] = {st->dv, st->fe2};
+  float* const upf = st->fe;
+  float* const vpf = st->fn;
+  const CAFrame fa = ca_frame(p, 5, x.cb1 - 2), fd = ca_frame(p, 3, x.cb1);
+  const unsigned bulk_blocks = (unsigned)(strip_nstrips(p, x.cb1) * strip_nchunks(p));
+  const unsigned tend_blocks = ca_blocks(fa.total, CA_THREADS);
+  const unsigned fric_blocks = ca_blocks(fd.total + ca_ext_total(p), CA_THREADS);
   int rc = 0;
 #define CA_RT(call)                                                              \
   if (rc == 0) {                                                                 \
@@ -288,47 +325,46 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
       rc = 1000 + (int)e_;                                                       \
     }                                                                            \
   }
+  CA_RT(cudaEventRecord(e0, s));
+  CA_RT(cudaStreamWaitEvent(s2, e0, 0));
+  int cur = 0;
   for (int it = 0; it < nsteps && rc == 0; ++it) {
+    const int nxt = cur ^ 1;
     p.first_step = (first_step && it == 0) ? 1 : 0;
+    // ---- bulk stream: needs D of the previous step (u'', v'' of the frame, the arrays' halos)
+    if (it > 0) CA_RT(cudaStreamWaitEvent(s, eD, 0));
+    if (rc) break;
+    StripArgs sa;
+    sa.p = p; sa.cb1 = x.cb1;
+    sa.h = H[cur]; sa.u = U[cur]; sa.v = V[cur]; sa.dh = DH[cur]; sa.du = DU[cur]; sa.dv = DV[cur];
+    sa.h_o = H[nxt]; sa.u_o = U[nxt]; sa.v_o = V[nxt]; sa.dh_o = DH[nxt]; sa.du_o = DU[nxt]; sa.dv_o = DV[nxt];
+    swe_ca_bulk_step<<<bulk_blocks, STRIP_NT, 0, s>>>(sa, ca_slot(it, 1));
+    if ((rc = ca_done(c, "swe_ca_bulk_step"))) break;
+    // ---- frame stream: needs the bulk kernel of the previous step (u'', v'', h next to the frame)
+    if (it > 0) CA_RT(cudaStreamWaitEvent(s2, eS, 0));
+    CA_RT(cudaEventRecord(eS, s));
+    if (rc) break;
     CACtx ctx;
     ctx.p = p; ctx.x = x;
-    ctx.h = h; ctx.ua = st->u; ctx.va = st->v;
-    ctx.hn = hn; ctx.ub = st->u1; ctx.vb = st->v1;
-    ctx.dh = st->dh; ctx.du = st->du; ctx.dv = st->dv;
-    CA_RT(cudaEventRecord(e0, s));
-    CA_RT(cudaStreamWaitEvent(s2, e0, 0));
-    if (rc) break;
-    // frame: tendencies
-    swe_ca_tend_frame<<<frame_blocks, CA_THREADS, 0, s2>>>(ctx, f);
+    ctx.h = H[cur]; ctx.ua = U[cur]; ctx.va = V[cur];
+    ctx.dh = DH[cur]; ctx.du = DU[cur]; ctx.dv = DV[cur];
+    ctx.hn = H[nxt]; ctx.dho = DH[nxt]; ctx.duo = DU[nxt]; ctx.dvo = DV[nxt];
+    ctx.upf = upf; ctx.vpf = vpf;
+    swe_ca_tend_frame<<<tend_blocks, CA_THREADS, 0, s2>>>(ctx, fa, ca_slot(it, 0));
     if ((rc = ca_done(c, "swe_ca_tend_frame"))) break;
-    CA_RT(cudaEventRecord(eA, s2));
-    // bulk: tendencies
-    if (k12_occ == 3)
-      swe_ca_bulk_k12<3><<<bulk_blocks, SWE_THREADS, 0, s>>>(p, x.cb1, h, hn, st->u, st->u1, st->v, st->v1, st->dh,
-                                                             st->du, st->dv);
-    else
-      swe_ca_bulk_k12<2><<<bulk_blocks, SWE_THREADS, 0, s>>>(p, x.cb1, h, hn, st->u, st->u1, st->v, st->v1, st->dh,
-                                                             st->du, st->dv);
-    if ((rc = ca_done(c, "swe_ca_bulk_k12"))) break;
-    CA_RT(cudaEventRecord(eB, s));
-    // frame: the step's only exchange
-    if ((rc = ca_exchange(c, *topo, p, x, hn, st->u1, st->v1, s2))) break;
-    // bulk: friction (reads u', v' two cells into the frame)
-    CA_RT(cudaStreamWaitEvent(s, eA, 0));
-    if (rc) break;
-    swe_ca_bulk_fric<<<bulk_blocks, SWE_THREADS, 0, s>>>(p, x.cb1, st->u1, st->u, st->v1, st->v);
-    if ((rc = ca_done(c, "swe_ca_bulk_fric"))) break;
-    // frame: friction (reads u', v' up to five cells in: needs the bulk tendencies)
-    CA_RT(cudaStreamWaitEvent(s2, eB, 0));
-    if (rc) break;
-    swe_ca_fric_frame<<<fric_blocks, CA_THREADS, 0, s2>>>(ctx, f, st->u, st->v);
+    if ((rc = ca_exchange(c, *topo, p, x, H[nxt], upf, vpf, s2, ca_slot(it, 2)))) break;
+    swe_ca_fric_frame<<<fric_blocks, CA_THREADS, 0, s2>>>(ctx, fd, U[nxt], V[nxt], ca_slot(it, 4));
     if ((rc = ca_done(c, "swe_ca_fric_frame"))) break;
     CA_RT(cudaEventRecord(eD, s2));
-    CA_RT(cudaStreamWaitEvent(s, eD, 0));
-    float* t = h; h = hn; hn = t;
+    cur = nxt;
   }
-  if (rc == 0 && h != st->h0)
-    CA_RT(cudaMemcpyAsync(st->h0, h, (size_t)p.ny * p.pitch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CA_RT(cudaStreamWaitEvent(s, eD, 0));           // join (also required to end a stream capture)
+  if (rc == 0 && cur != 0) {
+    // odd step count: the state goes back to its home buffers
+    const size_t bytes = (size_t)p.ny * p.pitch * sizeof(float);
+    float* const* pairs[6] = {H, U, V, DH, DU, DV};
+    for (int k = 0; k < 6; ++k) CA_RT(cudaMemcpyAsync(pairs[k][0], pairs[k][1], bytes, cudaMemcpyDeviceToDevice, s));
+  }
 #undef CA_RT
   return rc;
 }

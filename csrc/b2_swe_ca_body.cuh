@@ -15,8 +15,9 @@
 //   exchange X       3 layers of (h', u', v') to all eight neighbours (b2_swe_ca.cu).
 //   frame kernel D   friction (u' -> u'', v' -> v'') on the frame, and the neighbours' u'', v''
 //                    one / two cells beyond the edge, which next step's halo fluxes need.
-//   bulk kernels     K12 and the fused friction kernel (b2_swe_k12_body.cuh) on everything else;
-//                    they touch no halo, so they run concurrently with A -> X -> D.
+//   bulk kernel      the whole step in one pass over memory on everything else (b2_swe_strip.cuh):
+//                    its dependency cone stays inside the step's input arrays, so it needs nothing
+//                    from X and runs concurrently with A -> X -> D.
 //
 // Views.  The reference's discrete system is decomposition dependent: a rank computes its
 // fluxes from u, v whose HALO is stale by the friction update (the halo of u, v is exchanged
@@ -34,7 +35,7 @@
 // neighbours' cells, layers 1..2 / 1).  Only their outer cells are ever touched.
 #pragma once
 
-#include "b2_swe_k12_body.cuh"
+#include "b2_swe_body.cuh"
 
 #define CA_L 3        // halo layers exchanged per step (layer 1 = the main arrays' halo cell)
 #define CA_NF 3       // fields per exchange: h', u', v'
@@ -43,16 +44,22 @@
 struct CACtx {
   B2SweParams p;
   B2SweCA x;
-  const float *h;           // h of this step (halo fresh)
-  const float *ua, *va;     // u'', v'' of the previous step (interior; wall rows constant)
-  float *hn, *ub, *vb;      // h', u', v' (tendency phase output)
-  float *dh, *du, *dv;
+  const float *h;                 // h of this step (halo fresh)
+  const float *ua, *va;           // u'', v'' of the previous step (interior; wall rows constant)
+  const float *dh, *du, *dv;      // tendencies of the previous step
+  float *hn;                      // h' (ping-pong partner of h)
+  float *dho, *duo, *dvo;         // new tendencies (ping-pong partners)
+  float *upf, *vpf;               // u', v' of the frame band (cells within 5 of the edge) and, after X, their halo
 };
 
 __host__ __device__ inline bool swe_ca_supported(const B2SweParams& p) {
-  return p.ny >= 12 && p.nx >= 16;
+  return p.ny >= 16 && p.nx >= 24;
 }
-__host__ __device__ inline int swe_ca_cb1(const B2SweParams& p) { return ((p.nx - 4) >> 2) << 2; }
+__host__ __device__ inline int swe_ca_cb1(const B2SweParams& p) { return p.nx - 4; }
+// frame cells proper: within three of the block edge (plus the columns the bulk's alignment leaves over)
+__host__ __device__ __forceinline__ bool ca_is_frame(const B2SweParams& p, int cb1, int j, int i) {
+  return j <= 3 || j >= p.ny - 4 || i <= 3 || i >= cb1;
+}
 
 __host__ __device__ __forceinline__ int ca_rj(const B2SweParams& p, int j) { return j < 1 ? -1 : (j > p.ny - 2 ? 1 : 0); }
 __host__ __device__ __forceinline__ int ca_ri(const B2SweParams& p, int i) { return i < 1 ? -1 : (i > p.nx - 2 ? 1 : 0); }
@@ -133,6 +140,9 @@ __device__ __forceinline__ float ca_ke(const CACtx& c, int j0, int i) {
 }
 
 // ---- frame kernel A: flux + tendency update of one of this rank's cells ------------------------
+// Frame cells get everything; the two cells beyond them (distance 4, 5: bulk cells, whose h', dh ..
+// the bulk kernel writes) only need their u', v' here, because kernel D's friction stencil on the
+// frame reaches that far and must not wait for the bulk kernel.
 __device__ __forceinline__ void swe_ca_tend_cell(const CACtx& c, int j, int i) {
   const B2SweParams& p = c.p;
   const size_t off = ca_m(p, j, i);
@@ -148,20 +158,24 @@ __device__ __forceinline__ void swe_ca_tend_cell(const CACtx& c, int j, int i) {
   in.dv_o = p.first_step ? 0.f : c.dv[off];
   SweK2Out o = swe_k2_cell(p, in);
   if (p.north_wall && j == p.ny - 2) o.v = 0.f;       // "v" wall rule, after the update
-  c.hn[off] = o.h; c.ub[off] = o.u; c.vb[off] = o.v;
-  c.dh[off] = o.dh; c.du[off] = o.du; c.dv[off] = o.dv;
+  c.upf[off] = o.u; c.vpf[off] = o.v;
+  if (ca_is_frame(p, c.x.cb1, j, i)) {
+    c.hn[off] = o.h;
+    c.dho[off] = o.dh; c.duo[off] = o.du; c.dvo[off] = o.dv;
+  }
 }
 
 // ---- frame kernel D: friction ------------------------------------------------------------------
-// u', v' anywhere within three cells of the block (mine: main arrays; beyond: the exchanged copy)
+// u', v' of the frame band and of the cells up to three beyond the block (mine: upf / vpf; beyond: the
+// exchanged copy)
 __device__ __forceinline__ float ca_up(const CACtx& c, int j, int i) {
   const bool main = ca_mine(c.p, j, i) || ca_wall_row(c.p, j);
-  const float* ptr = main ? c.ub + ca_m_safe(c.p, j, i) : c.x.upx + ca_e(c.x, j, i);
+  const float* ptr = main ? c.upf + ca_m_safe(c.p, j, i) : c.x.upx + ca_e(c.x, j, i);
   return *ptr;
 }
 __device__ __forceinline__ float ca_vp(const CACtx& c, int j, int i) {
   const bool main = ca_mine(c.p, j, i) || ca_wall_row(c.p, j);
-  const float* ptr = main ? c.vb + ca_m_safe(c.p, j, i) : c.x.vpx + ca_e(c.x, j, i);
+  const float* ptr = main ? c.vpf + ca_m_safe(c.p, j, i) : c.x.vpx + ca_e(c.x, j, i);
   return *ptr;
 }
 // u'' of cell (j, i) (swe_k34_body's update; the wall rules are functions of the row only, and a
@@ -194,8 +208,8 @@ __device__ __forceinline__ void swe_ca_fric_cell(const CACtx& c, float* __restri
   va_out[off] = ca_vpp(c, j, i, upp);
   if (j == 1 || j == p.ny - 2 || i == 1 || i == p.nx - 2) {
     const size_t e = ca_e(c.x, j, i);
-    c.x.upx[e] = c.ub[off];
-    c.x.vpx[e] = c.vb[off];
+    c.x.upx[e] = c.upf[off];
+    c.x.vpx[e] = c.vpf[off];
   }
 }
 // a neighbour's cell, one or two layers beyond the edge: its u'' (and v'' on layer 1).  Layer 1 is
@@ -215,31 +229,35 @@ __device__ __forceinline__ void swe_ca_fric_ext_cell(const CACtx& c, float* __re
 }
 
 // ---- task enumeration ----------------------------------------------------------------------------
-// Bulk = rows [4, ny-5] x columns [4, cb1): whole float4 groups, no cell within 3 of the edge.
-// Frame = every other interior cell.
+// Bulk (b2_swe_strip.cuh) = rows [4, ny-5] x columns [4, cb1); frame = every other interior cell.
+// A band of width w: rows [1, w] and [ny-1-w, ny-2] completely, of the rows in between the columns
+// [1, w] and [ce, nx-2].  Kernel D walks the frame (w = 3, ce = cb1), kernel A the frame plus the two
+// cells beyond it (w = 5, ce = cb1 - 2).
 struct CAFrame {
-  int nfull;          // cells in the six full rows
-  int per;            // frame cells per middle row
+  int w, ce;
+  int nfull;          // cells in the 2w full rows
+  int per;            // band cells per middle row
   long long total;
 };
-__host__ __device__ inline CAFrame ca_frame(const B2SweParams& p, int cb1) {
+__host__ __device__ inline CAFrame ca_frame(const B2SweParams& p, int w, int ce) {
   CAFrame f;
-  f.nfull = 6 * (p.nx - 2);
-  f.per = 3 + (p.nx - 1 - cb1);
-  f.total = (long long)f.nfull + (long long)(p.ny - 8) * f.per;
+  f.w = w; f.ce = ce;
+  f.nfull = 2 * w * (p.nx - 2);
+  f.per = w + (p.nx - 1 - ce);
+  f.total = (long long)f.nfull + (long long)(p.ny - 2 - 2 * w) * f.per;
   return f;
 }
-__host__ __device__ inline bool ca_frame_cell(const B2SweParams& p, const CAFrame& f, int cb1, long long idx, int& j, int& i) {
+__host__ __device__ inline bool ca_frame_cell(const B2SweParams& p, const CAFrame& f, long long idx, int& j, int& i) {
   if (idx >= f.total) return false;
   if (idx < f.nfull) {
     const int r = (int)(idx / (p.nx - 2));
     i = 1 + (int)(idx % (p.nx - 2));
-    j = r < 3 ? 1 + r : (p.ny - 4) + (r - 3);
+    j = r < f.w ? 1 + r : (p.ny - 1 - f.w) + (r - f.w);
   } else {
     const long long t = idx - f.nfull;
     const int s = (int)(t % f.per);
-    j = 4 + (int)(t / f.per);
-    i = s < 3 ? 1 + s : cb1 + (s - 3);
+    j = f.w + 1 + (int)(t / f.per);
+    i = s < f.w ? 1 + s : f.ce + (s - f.w);
   }
   return true;
 }
@@ -263,15 +281,6 @@ __host__ __device__ inline bool ca_ext_cell(const B2SweParams& p, long long idx,
   }
   return !ca_wall_row(p, j);
 }
-__host__ __device__ inline long long ca_bulk_tasks(const B2SweParams& p, int cb1) {
-  return (long long)(p.ny - 8) * ((cb1 >> 2) - 1);
-}
-__host__ __device__ inline void ca_bulk_task(const B2SweParams& p, int cb1, long long idx, int& j, int& i0) {
-  const int ng = (cb1 >> 2) - 1;
-  j = 4 + (int)(idx / ng);
-  i0 = (1 + (int)(idx % ng)) << 2;
-}
-
 // ---- exchange geometry -----------------------------------------------------------------------------
 // Element e of the message that LANDS on receiver side `side` (FS_W = it comes from the west
 // neighbour, ...): field f, the sender's cell (js, is), the receiver's cell (jr, ir) and the layer

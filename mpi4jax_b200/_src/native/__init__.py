@@ -192,6 +192,7 @@ _SIGNATURES = {
         [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2SweCA), POINTER(B2HaloDesc), c_int, c_int,
          c_void_p],
     ),
+    "b2_swe_ca_timeline": (None, [c_void_p, c_int]),
     "b2_swe_ca_init": (
         c_int,
         [c_void_p, POINTER(B2SweParams), POINTER(B2SweState), POINTER(B2SweCA), POINTER(B2HaloDesc), c_void_p],

@@ -29,7 +29,7 @@ def _free_port() -> int:
 
 def launch(nprocs: int, argv: list, *, cpu: bool = False, timeout: float | None = None,
            env_extra: dict | None = None, capture: bool = False, nnodes: int = 1, node_rank: int = 0,
-           master_addr: str = "127.0.0.1", master_port: int | None = None):
+           master_addr: str = "127.0.0.1", master_port: int | None = None, output_dir: str | None = None):
     """Start ``nprocs`` local ranks running ``python <argv...>``; returns (exit_code, outputs).
 
     Multi-node jobs run this launcher once per node with the same ``nnodes`` / ``master_addr`` /
@@ -52,6 +52,9 @@ def launch(nprocs: int, argv: list, *, cpu: bool = False, timeout: float | None 
         if env_extra:
             env.update(env_extra)
         kw = dict(stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) if capture else {}
+        if output_dir is not None:          # one log per rank (mpirun --output-filename)
+            os.makedirs(output_dir, exist_ok=True)
+            kw = dict(stdout=open(os.path.join(output_dir, f"rank{rank}.log"), "w"), stderr=subprocess.STDOUT)
         procs.append(subprocess.Popen([sys.executable, *argv], env=env, start_new_session=True, **kw))
     deadline = None if timeout is None else time.time() + timeout
     code = 0
@@ -108,6 +111,7 @@ def main(argv=None) -> int:
     ap.add_argument("--node-rank", type=int, default=0, help="index of this node, 0 .. nnodes-1")
     ap.add_argument("--master-addr", default="127.0.0.1", help="address of node 0 (rendezvous)")
     ap.add_argument("--master-port", type=int, default=None, help="rendezvous port (required for nnodes > 1)")
+    ap.add_argument("--output-dir", default=None, help="write every rank's stdout + stderr to <dir>/rank<r>.log")
     ap.add_argument("-m", dest="module", default=None, help="run a module (python -m ...) in every rank")
     ap.add_argument("rest", nargs=argparse.REMAINDER)
     ns = ap.parse_args(argv)
@@ -116,7 +120,7 @@ def main(argv=None) -> int:
     if not cmd:
         ap.error("nothing to run")
     code, _ = launch(ns.nprocs, cmd, cpu=ns.cpu, timeout=ns.timeout, nnodes=ns.nnodes, node_rank=ns.node_rank,
-                     master_addr=ns.master_addr, master_port=ns.master_port)
+                     master_addr=ns.master_addr, master_port=ns.master_port, output_dir=ns.output_dir)
     return code
 
 

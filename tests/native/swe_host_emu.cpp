@@ -19,6 +19,7 @@ struct FakeIdx { unsigned x; };
 static FakeIdx blockIdx, threadIdx;
 
 #include "b2_swe_ca_body.cuh"
+#include "b2_swe_strip.cuh"
 
 static void masks(const B2SweParams& p, int i0, bool m[4]) {
   for (int k = 0; k < 4; ++k) m[k] = (i0 + k >= 1) && (i0 + k <= p.nx - 2);
@@ -72,78 +73,86 @@ void emu_k34(const B2SweParams* p, const float* u, float* u_new, const float* v,
     }
 }
 
-// ---- communication-avoiding step (csrc/b2_swe_ca_body.cuh): the kernels of b2_swe_ca.cu as loops ----
-// `reverse` walks the tasks backwards: a kernel whose threads only read what no thread of the same
-// launch writes gives the same bits in any order.
-static CACtx make_ctx(const B2SweParams* p, const B2SweCA* x, const float* h, const float* ua, const float* va,
-                      float* hn, float* ub, float* vb, float* dh, float* du, float* dv) {
+// ---- communication-avoiding step (csrc/b2_swe_ca_body.cuh, b2_swe_strip.cuh): the kernels of
+// b2_swe_ca.cu as loops.  `reverse` walks the tasks backwards: a kernel whose threads only read what no
+// thread of the same launch (or phase) writes gives the same bits in any order.
+struct EmuStep {      // the arrays of one rank for one step (B2SweState roles of b2_swe_multistep_ca)
+  const float *h, *u, *v, *dh, *du, *dv;
+  float *h_o, *u_o, *v_o, *dh_o, *du_o, *dv_o, *upf, *vpf;
+};
+
+static CACtx make_ctx(const B2SweParams* p, const B2SweCA* x, const EmuStep* e) {
   CACtx c;
   c.p = *p; c.x = *x; c.x.cb1 = swe_ca_cb1(*p);
-  c.h = h; c.ua = ua; c.va = va; c.hn = hn; c.ub = ub; c.vb = vb; c.dh = dh; c.du = du; c.dv = dv;
+  c.h = e->h; c.ua = e->u; c.va = e->v; c.dh = e->dh; c.du = e->du; c.dv = e->dv;
+  c.hn = e->h_o; c.dho = e->dh_o; c.duo = e->du_o; c.dvo = e->dv_o;
+  c.upf = e->upf; c.vpf = e->vpf;
   return c;
 }
 
 int emu_ca_supported(const B2SweParams* p) { return swe_ca_supported(*p) ? 1 : 0; }
 int emu_ca_cb1(const B2SweParams* p) { return swe_ca_cb1(*p); }
 
-void emu_ca_tend_frame(const B2SweParams* p, const B2SweCA* x, const float* h, const float* ua, const float* va,
-                       float* hn, float* ub, float* vb, float* dh, float* du, float* dv, int reverse) {
-  const CACtx c = make_ctx(p, x, h, ua, va, hn, ub, vb, dh, du, dv);
-  const CAFrame f = ca_frame(c.p, c.x.cb1);
+void emu_ca_tend_frame(const B2SweParams* p, const B2SweCA* x, const EmuStep* e, int reverse) {
+  const CACtx c = make_ctx(p, x, e);
+  const CAFrame f = ca_frame(c.p, 5, c.x.cb1 - 2);
   for (long long k = 0; k < f.total; ++k) {
     int j, i;
-    if (ca_frame_cell(c.p, f, c.x.cb1, reverse ? f.total - 1 - k : k, j, i)) swe_ca_tend_cell(c, j, i);
+    if (ca_frame_cell(c.p, f, reverse ? f.total - 1 - k : k, j, i)) swe_ca_tend_cell(c, j, i);
   }
 }
 
-void emu_ca_fric_frame(const B2SweParams* p, const B2SweCA* x, float* ub, float* vb, float* ua_out, float* va_out,
-                       int reverse) {
-  const CACtx c = make_ctx(p, x, nullptr, nullptr, nullptr, nullptr, ub, vb, nullptr, nullptr, nullptr);
-  const CAFrame f = ca_frame(c.p, c.x.cb1);
+void emu_ca_fric_frame(const B2SweParams* p, const B2SweCA* x, const EmuStep* e, int reverse) {
+  const CACtx c = make_ctx(p, x, e);
+  const CAFrame f = ca_frame(c.p, 3, c.x.cb1);
   const long long n = f.total + ca_ext_total(c.p);
   for (long long k = 0; k < n; ++k) {
     const long long t = reverse ? n - 1 - k : k;
     int j, i;
     if (t < f.total) {
-      ca_frame_cell(c.p, f, c.x.cb1, t, j, i);
-      swe_ca_fric_cell(c, ua_out, va_out, j, i);
+      ca_frame_cell(c.p, f, t, j, i);
+      swe_ca_fric_cell(c, e->u_o, e->v_o, j, i);
     } else if (ca_ext_cell(c.p, t - f.total, j, i)) {
-      swe_ca_fric_ext_cell(c, ua_out, va_out, j, i);
+      swe_ca_fric_ext_cell(c, e->u_o, e->v_o, j, i);
     }
   }
 }
 
-void emu_ca_bulk_k12(const B2SweParams* p, const float* h, float* h_new, const float* u, float* u_new,
-                     const float* v, float* v_new, float* dh, float* du, float* dv) {
-  const int cb1 = swe_ca_cb1(*p);
-  for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
-    int j, i0;
-    ca_bulk_task(*p, cb1, t, j, i0);
-    swe_k12_body(*p, h, h_new, u, u_new, v, v_new, dh, du, dv, j, i0);
+// swe_ca_bulk_step: CTAs one after the other, every phase as a loop over the CTA's threads
+// (`reverse`: CTAs and threads backwards -- a phase only reads what earlier phases wrote)
+void emu_ca_bulk_step(const B2SweParams* p, const EmuStep* e, int reverse) {
+  StripArgs a;
+  a.p = *p; a.cb1 = swe_ca_cb1(*p);
+  a.h = e->h; a.u = e->u; a.v = e->v; a.dh = e->dh; a.du = e->du; a.dv = e->dv;
+  a.h_o = e->h_o; a.u_o = e->u_o; a.v_o = e->v_o; a.dh_o = e->dh_o; a.du_o = e->du_o; a.dv_o = e->dv_o;
+  const int nb = strip_nstrips(a.p, a.cb1) * strip_nchunks(a.p);
+  static StripSmem sm;
+  for (int bb = 0; bb < nb; ++bb) {
+    const int b = reverse ? nb - 1 - bb : bb;
+    const StripGeo g = strip_geo(a.p, a.cb1, b);
+    for (int k = 0; k < (int)(sizeof(sm) / sizeof(float)); ++k) ((float*)&sm)[k] = NAN;     // stale smem of another CTA
+    strip_cta(a, sm, g, [&](auto&& phase) {
+      for (int tt = 0; tt < STRIP_NT; ++tt) phase(strip_thread(a, g, reverse ? STRIP_NT - 1 - tt : tt));
+    });
   }
 }
 
-void emu_ca_bulk_fric(const B2SweParams* p, const float* u, float* u_new, const float* v, float* v_new) {
-  const int cb1 = swe_ca_cb1(*p);
-  for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
-    int j, i0;
-    ca_bulk_task(*p, cb1, t, j, i0);
-    swe_k345_body(*p, u, u_new, v, v_new, j, i0);
-  }
-}
-
-// which interior cells do the bulk and frame enumerations cover?  marks[j * nx + i]: +1 frame, +16 bulk
+// which interior cells do the bulk kernel and the frame kernels WRITE?  marks[j * nx + i]: +1 frame
+// (kernel D's cells = kernel A's full updates), +16 bulk, +256 kernel A's u' / v' band
 void emu_ca_marks(const B2SweParams* p, int* marks) {
   const int cb1 = swe_ca_cb1(*p);
-  const CAFrame f = ca_frame(*p, cb1);
-  for (long long t = 0; t < f.total; ++t) {
-    int j, i;
-    if (ca_frame_cell(*p, f, cb1, t, j, i)) marks[j * p->nx + i] += 1;
-  }
-  for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
-    int j, i0;
-    ca_bulk_task(*p, cb1, t, j, i0);
-    for (int k = 0; k < 4; ++k) marks[j * p->nx + i0 + k] += 16;
+  const CAFrame fd = ca_frame(*p, 3, cb1), fa = ca_frame(*p, 5, cb1 - 2);
+  int j, i;
+  for (long long t = 0; t < fd.total; ++t)
+    if (ca_frame_cell(*p, fd, t, j, i)) marks[j * p->nx + i] += 1;
+  for (long long t = 0; t < fa.total; ++t)
+    if (ca_frame_cell(*p, fa, t, j, i)) marks[j * p->nx + i] += 256;
+  const int nb = strip_nstrips(*p, cb1) * strip_nchunks(*p);
+  for (int b = 0; b < nb; ++b) {
+    const StripGeo g = strip_geo(*p, cb1, b);
+    for (int jj = g.j0; jj < g.j1; ++jj)
+      for (int tid = 4; tid <= STRIP_NT - 4; ++tid)
+        if (g.i0 - 4 + tid < cb1) marks[jj * p->nx + g.i0 - 4 + tid] += 16;
   }
 }
 

@@ -222,9 +222,16 @@ def _ca_ext(blk, epitch):
                  uppx=blk["uppx"].ctypes.data, vppx=blk["vppx"].ctypes.data, epitch=epitch, cb1=0)
 
 
+class EmuStep(ctypes.Structure):      # EmuStep (tests/native/swe_host_emu.cpp): one rank's arrays for one step
+    _fields_ = [(n, ctypes.c_void_p) for n in ("h", "u", "v", "dh", "du", "dv", "h_o", "u_o", "v_o", "dh_o", "du_o",
+                                                "dv_o", "upf", "vpf")]
+
+
 def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0):
-    """The launch sequence of b2_swe_multistep_ca on a process grid (messages are read before any
-    rank scatters: all sends of a step come from h', u', v' frame cells, which no message writes)."""
+    """The launch sequence of b2_swe_multistep_ca on a process grid: per step the bulk kernel (whole
+    step, one pass), frame kernel A, the deep exchange, frame kernel D; every prognostic array is a
+    ping-pong pair.  (Messages are read before any rank scatters: all sends of a step come from h',
+    u', v' frame cells, which no message writes.)"""
     from ._halo_sim import new_exchange
 
     ranks, ny, nx, pitch = _blocks(model, PY, PX)
@@ -235,42 +242,50 @@ def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0):
         r["h1"][:], r["u1"][:], r["v1"][:] = r["h"], r["u"], r["v"]
         for n in ("hx", "upx", "vpx", "uppx", "vppx"):
             r[n] = np.full((ny + 4, epitch), np.nan, np.float32)     # NaN = never delivered / computed
+        for n in ("dh1", "du1", "dv1", "upf", "vpf"):
+            r[n] = np.full((ny, pitch), np.nan, np.float32)
     B = ctypes.byref
     _ca_exchange(emu, ranks, ("h", "u", "v"), ny, nx, pitch, epitch, PY, PX)       # b2_swe_ca_init
     for i, r in enumerate(ranks):
         p = _params(model, r, ny, nx, pitch, i // PX, PY, True)
         x = _ca_ext(r, epitch)
         emu.emu_ca_init_ext(B(p), B(x), _ptr(r["u"]), _ptr(r["v"]))
-    hk, hnk = "h", "h1"
+    pairs = dict(h=("h", "h1"), u=("u", "u1"), v=("v", "v1"), dh=("dh", "dh1"), du=("du", "du1"), dv=("dv", "dv1"))
+    cur = 0
     for it in range(nsteps):
+        nxt = cur ^ 1
         ps = [_params(model, r, ny, nx, pitch, i // PX, PY, it == 0) for i, r in enumerate(ranks)]
         xs = [_ca_ext(r, epitch) for r in ranks]
-        for r, p, x in zip(ranks, ps, xs):
-            emu.emu_ca_tend_frame(B(p), B(x), _ptr(r[hk]), _ptr(r["u"]), _ptr(r["v"]), _ptr(r[hnk]), _ptr(r["u1"]),
-                                  _ptr(r["v1"]), _ptr(r["dh"]), _ptr(r["du"]), _ptr(r["dv"]), reverse)
-            emu.emu_ca_bulk_k12(B(p), _ptr(r[hk]), _ptr(r[hnk]), _ptr(r["u"]), _ptr(r["u1"]), _ptr(r["v"]),
-                                _ptr(r["v1"]), _ptr(r["dh"]), _ptr(r["du"]), _ptr(r["dv"]))
-        _ca_exchange(emu, ranks, (hnk, "u1", "v1"), ny, nx, pitch, epitch, PY, PX)
-        for r, p, x in zip(ranks, ps, xs):
-            emu.emu_ca_bulk_fric(B(p), _ptr(r["u1"]), _ptr(r["u"]), _ptr(r["v1"]), _ptr(r["v"]))
-            emu.emu_ca_fric_frame(B(p), B(x), _ptr(r["u1"]), _ptr(r["v1"]), _ptr(r["u"]), _ptr(r["v"]), reverse)
-        hk, hnk = hnk, hk
-    return [dict(h=r[hk][:, :nx], u=r["u"][:, :nx], v=r["v"][:, :nx], dh=r["dh"][:, :nx], du=r["du"][:, :nx],
-                 dv=r["dv"][:, :nx]) for r in ranks]
+        es = [EmuStep(**{k: r[pairs[k][cur]].ctypes.data for k in pairs},
+                      **{k + "_o": r[pairs[k][nxt]].ctypes.data for k in pairs},
+                      upf=r["upf"].ctypes.data, vpf=r["vpf"].ctypes.data) for r in ranks]
+        for p, x, e in zip(ps, xs, es):
+            emu.emu_ca_bulk_step(B(p), B(e), reverse)
+            emu.emu_ca_tend_frame(B(p), B(x), B(e), reverse)
+        _ca_exchange(emu, ranks, (pairs["h"][nxt], "upf", "vpf"), ny, nx, pitch, epitch, PY, PX)
+        for p, x, e in zip(ps, xs, es):
+            emu.emu_ca_fric_frame(B(p), B(x), B(e), reverse)
+        cur = nxt
+    return [{k: r[pairs[k][cur]][:, :nx] for k in pairs} for r in ranks]
 
 
-@pytest.mark.parametrize("shape", [(12, 16), (26, 50), (13, 21), (40, 19), (31, 64)])
+@pytest.mark.parametrize("shape", [(16, 24), (26, 50), (17, 29), (140, 33), (31, 300), (200, 530)])
 def test_ca_bulk_and_frame_partition_the_interior(emu, shape):
     ny, nx = shape
     p, *_ = _setup(ny, nx, False, 0, 0)
     assert emu.emu_ca_supported(ctypes.byref(p)) == 1
     marks = np.zeros((ny, nx), np.int32)
     emu.emu_ca_marks(ctypes.byref(p), marks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
-    assert (marks[1:-1, 1:-1] != 0).all() and set(np.unique(marks[1:-1, 1:-1])) <= {1, 16}   # exactly one owner
+    owner = marks & 0xff                     # 1 = frame kernels, 16 = bulk kernel (several CTAs)
+    assert set(np.unique(owner[1:-1, 1:-1])) <= {1, 16}          # every interior cell written exactly once
     assert marks[0].sum() == marks[-1].sum() == marks[:, 0].sum() == marks[:, -1].sum() == 0
-    bulk = marks == 16
-    jj, ii = np.nonzero(bulk)
-    assert jj.min() >= 4 and jj.max() <= ny - 5 and ii.min() >= 4 and ii.max() <= nx - 5     # >= 3 cells from the edge
+    jj, ii = np.nonzero(owner == 16)
+    assert jj.min() == 4 and jj.max() == ny - 5 and ii.min() == 4 and ii.max() == nx - 5     # exactly 3 frame cells
+    band = (marks & 256) != 0                # kernel A also computes u', v' two cells into the bulk
+    want = np.zeros_like(band)
+    want[1:-1, 1:-1] = True
+    want[6:ny - 6, 6:nx - 6] = False
+    assert np.array_equal(band, want)
 
 
 @pytest.mark.parametrize("grid", [(1, 1), (2, 1), (1, 2), (2, 2), (3, 2), (2, 4)])
@@ -293,3 +308,17 @@ def test_emulated_ca_pipeline_is_bit_identical_to_the_standalone_pipeline(emu, g
             # the main arrays' halos as well (h fresh; u, v stale by the friction step)
             if name in ("h", "u", "v"):
                 assert np.array_equal(ra[name], rb[name]), (grid, name, "halo")
+
+
+def test_emulated_ca_pipeline_with_several_strips_and_chunks(emu):
+    """A block larger than one CTA of the bulk kernel in both directions (3 column strips of 249, 3 row
+    chunks of 128): the strip / chunk seams and the ring warm-up rows, still bit for bit."""
+    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
+
+    model = ShallowWaterModel(ShallowWaterConfig(nx=530, ny=300), device="cpu", backend="ops")
+    a = _emulate(emu, model, 1, 1, 3)
+    b = _emulate_ca(emu, model, 1, 1, 3)
+    c = _emulate_ca(emu, model, 1, 1, 3, reverse=1)
+    for name in a[0]:
+        assert np.array_equal(a[0][name][1:-1, 1:-1], b[0][name][1:-1, 1:-1]), name
+        assert np.array_equal(b[0][name][1:-1, 1:-1], c[0][name][1:-1, 1:-1]), (name, "task order")
