@@ -43,26 +43,46 @@ __device__ __forceinline__ void ca_stamp_end(const CAStamp& s) {
   if (s.slot != nullptr && threadIdx.x == 0) atomicMax(s.slot + 1, b2_gtime());
 }
 
-// ---- frame kernels (one thread per cell; a few thousand cells) ------------------------------------
-__global__ void __launch_bounds__(CA_THREADS) swe_ca_tend_frame(const CACtx c, const CAFrame f, const CAStamp ts) {
+// ---- frame kernels -------------------------------------------------------------------------------
+// The frame is a few thousand cells and sits on the step's critical path: latency, not throughput.
+// A thread per cell would evaluate 14 flux quantities (kernel A) or 3 friction stencils (kernel D) one
+// after the other -- ~4000 dependent-issue instructions, measured 18 us.  Instead a CTA takes 32 cells
+// and one WARP per quantity: warp w evaluates quantity w for the 32 cells (no divergence inside a
+// warp), the values meet in shared memory, warp 0 finishes the cells.
+#define CA_CELLS 32
+__global__ void __launch_bounds__(CA_CELLS * CA_NSLOT) swe_ca_tend_frame(const CACtx c, const CAFrame f, const CAStamp ts) {
   ca_stamp_begin(ts);
+  __shared__ float fl[CA_NSLOT][CA_CELLS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int j, i;
-  if (ca_frame_cell(c.p, f, (long long)blockIdx.x * CA_THREADS + threadIdx.x, j, i)) swe_ca_tend_cell(c, j, i);
+  const bool ok = ca_frame_cell(c.p, f, (long long)blockIdx.x * CA_CELLS + lane, j, i);
+  if (ok) fl[w][lane] = ca_flux_slot(c, j, i, w);
+  __syncthreads();
+  if (ok && w == 0) {
+    float v[CA_NSLOT];
+#pragma unroll
+    for (int s = 0; s < CA_NSLOT; ++s) v[s] = fl[s][lane];
+    swe_ca_tend_finish(c, j, i, v);
+  }
   ca_stamp_end(ts);
 }
 
 // friction on the frame cells (u', v' -> ua_out, va_out) and u'' / v'' of the neighbours' cells
-__global__ void __launch_bounds__(CA_THREADS) swe_ca_fric_frame(const CACtx c, const CAFrame f,
-                                                                float* __restrict__ ua_out,
-                                                                float* __restrict__ va_out, const CAStamp ts) {
+__global__ void __launch_bounds__(CA_CELLS * 3) swe_ca_fric_frame(const CACtx c, const CAFrame f,
+                                                                  float* __restrict__ ua_out,
+                                                                  float* __restrict__ va_out, const CAStamp ts) {
   ca_stamp_begin(ts);
-  const long long t = (long long)blockIdx.x * CA_THREADS + threadIdx.x;
+  __shared__ float up[3][CA_CELLS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int j, i;
-  if (t < f.total) {
-    ca_frame_cell(c.p, f, t, j, i);
-    swe_ca_fric_cell(c, ua_out, va_out, j, i);
-  } else if (ca_ext_cell(c.p, t - f.total, j, i)) {
-    swe_ca_fric_ext_cell(c, ua_out, va_out, j, i);
+  bool ext;
+  const bool ok = ca_fric_task(c.p, f, (long long)blockIdx.x * CA_CELLS + lane, j, i, ext);
+  if (ok && (w == 0 || ca_needs_vpp(c.p, j, i))) up[w][lane] = ca_upp_slot(c, j, i, w);
+  __syncthreads();
+  if (ok && w == 0) {
+    const float v[3] = {up[0][lane], up[1][lane], up[2][lane]};
+    if (ext) swe_ca_fric_ext_finish(c, ua_out, va_out, j, i, v);
+    else swe_ca_fric_finish(c, ua_out, va_out, j, i, v);
   }
   ca_stamp_end(ts);
 }
@@ -96,19 +116,21 @@ __global__ void __launch_bounds__(CA_THREADS) swe_ca_init_ext(const B2SweParams 
 }
 
 // ---- bulk kernel: the whole step in one pass (phases and geometry: b2_swe_strip.cuh) ---------------
-// every phase ends with a barrier: the next one reads what other threads just wrote to the rings
+// an iteration ends with a barrier: the next one reads what other threads just wrote to the rings
 struct StripSync {
   StripThr t;
   template <class F>
-  __device__ __forceinline__ void operator()(F&& f) const {
+  __device__ __forceinline__ void operator()(F&& f) {
     f(t);
     __syncthreads();
   }
 };
-__global__ void __launch_bounds__(STRIP_NT) swe_ca_bulk_step(const StripArgs a, const CAStamp ts) {
+template <int NT>
+__global__ void __launch_bounds__(NT) swe_ca_bulk_step(const StripArgs a, const CAStamp ts) {
   ca_stamp_begin(ts);
-  __shared__ StripSmem sm;
-  const StripGeo g = strip_geo(a.p, a.cb1, (int)blockIdx.x);
+  extern __shared__ __align__(16) unsigned char strip_smem_raw[];       // 52 rows x NT floats: above the 48 KB static limit at NT = 256
+  StripSmem<NT>& sm = *reinterpret_cast<StripSmem<NT>*>(strip_smem_raw);
+  const StripGeo g = strip_geo(a, (int)blockIdx.x);
   StripSync each;
   each.t = strip_thread(a, g, (int)threadIdx.x);
   strip_cta(a, sm, g, each);
@@ -192,6 +214,13 @@ static int ca_streams() {
   if (cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, hi) != cudaSuccess) {
     b2_set_error("swe_ca: cudaStreamCreate failed");
     g_side = nullptr;
+    return 1;
+  }
+  if (cudaFuncSetAttribute(swe_ca_bulk_step<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(StripSmem<256>)) != cudaSuccess ||
+      cudaFuncSetAttribute(swe_ca_bulk_step<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(StripSmem<128>)) != cudaSuccess) {
+    b2_set_error("swe_ca: cudaFuncSetAttribute(shared memory) failed");
     return 1;
   }
   for (int k = 0; k < 3; ++k)
@@ -284,6 +313,7 @@ int b2_swe_ca_init(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const
   if (!swe_ca_supported(p)) return 0;
   x.cb1 = swe_ca_cb1(p);
   if (int rc = ca_check(c, p, x)) return rc;
+  if (int rc = ca_streams()) return rc;       // (here, never inside a stream capture: reset / load_state are eager)
   if (int rc = ca_exchange(c, *topo, p, x, st->h0, st->u, st->v, s)) return rc;
   const long long tasks = ca_ext_total(p) + 2LL * (p.nx - 2) + 2LL * (p.ny - 2);
   swe_ca_init_ext<<<ca_blocks(tasks, CA_THREADS), CA_THREADS, 0, s>>>(p, x, st->u, st->v);
@@ -313,9 +343,8 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
   float* const upf = st->fe;
   float* const vpf = st->fn;
   const CAFrame fa = ca_frame(p, 5, x.cb1 - 2), fd = ca_frame(p, 3, x.cb1);
-  const unsigned bulk_blocks = (unsigned)(strip_nstrips(p, x.cb1) * strip_nchunks(p));
-  const unsigned tend_blocks = ca_blocks(fa.total, CA_THREADS);
-  const unsigned fric_blocks = ca_blocks(fd.total + ca_ext_total(p), CA_THREADS);
+  const unsigned tend_blocks = ca_blocks(fa.total, CA_CELLS);
+  const unsigned fric_blocks = ca_blocks(fd.total + ca_ext_total(p), CA_CELLS);
   int rc = 0;
 #define CA_RT(call)                                                              \
   if (rc == 0) {                                                                 \
@@ -336,9 +365,12 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
     if (rc) break;
     StripArgs sa;
     sa.p = p; sa.cb1 = x.cb1;
+    strip_shape(sa, c->sm_count);
+    const unsigned bulk_blocks = (unsigned)(strip_nstrips(sa) * strip_nchunks(sa));
     sa.h = H[cur]; sa.u = U[cur]; sa.v = V[cur]; sa.dh = DH[cur]; sa.du = DU[cur]; sa.dv = DV[cur];
     sa.h_o = H[nxt]; sa.u_o = U[nxt]; sa.v_o = V[nxt]; sa.dh_o = DH[nxt]; sa.du_o = DU[nxt]; sa.dv_o = DV[nxt];
-    swe_ca_bulk_step<<<bulk_blocks, STRIP_NT, 0, s>>>(sa, ca_slot(it, 1));
+    if (sa.nt == 256) swe_ca_bulk_step<256><<<bulk_blocks, 256, sizeof(StripSmem<256>), s>>>(sa, ca_slot(it, 1));
+    else swe_ca_bulk_step<128><<<bulk_blocks, 128, sizeof(StripSmem<128>), s>>>(sa, ca_slot(it, 1));
     if ((rc = ca_done(c, "swe_ca_bulk_step"))) break;
     // ---- frame stream: needs the bulk kernel of the previous step (u'', v'', h next to the frame)
     if (it > 0) CA_RT(cudaStreamWaitEvent(s2, eS, 0));
@@ -350,10 +382,10 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
     ctx.dh = DH[cur]; ctx.du = DU[cur]; ctx.dv = DV[cur];
     ctx.hn = H[nxt]; ctx.dho = DH[nxt]; ctx.duo = DU[nxt]; ctx.dvo = DV[nxt];
     ctx.upf = upf; ctx.vpf = vpf;
-    swe_ca_tend_frame<<<tend_blocks, CA_THREADS, 0, s2>>>(ctx, fa, ca_slot(it, 0));
+    swe_ca_tend_frame<<<tend_blocks, CA_CELLS * CA_NSLOT, 0, s2>>>(ctx, fa, ca_slot(it, 0));
     if ((rc = ca_done(c, "swe_ca_tend_frame"))) break;
     if ((rc = ca_exchange(c, *topo, p, x, H[nxt], upf, vpf, s2, ca_slot(it, 2)))) break;
-    swe_ca_fric_frame<<<fric_blocks, CA_THREADS, 0, s2>>>(ctx, fd, U[nxt], V[nxt], ca_slot(it, 4));
+    swe_ca_fric_frame<<<fric_blocks, CA_CELLS * 3, 0, s2>>>(ctx, fd, U[nxt], V[nxt], ca_slot(it, 4));
     if ((rc = ca_done(c, "swe_ca_fric_frame"))) break;
     CA_RT(cudaEventRecord(eD, s2));
     cur = nxt;

@@ -143,14 +143,35 @@ __device__ __forceinline__ float ca_ke(const CACtx& c, int j0, int i) {
 // Frame cells get everything; the two cells beyond them (distance 4, 5: bulk cells, whose h', dh ..
 // the bulk kernel writes) only need their u', v' here, because kernel D's friction stencil on the
 // frame reaches that far and must not wait for the bulk kernel.
-__device__ __forceinline__ void swe_ca_tend_cell(const CACtx& c, int j, int i) {
+// The 14 flux values of a cell's tendency stencil, as (kind, dj, di); a warp of kernel A evaluates ONE
+// slot for 32 cells, so the cell's latency is one flux evaluation, not fourteen in a row.
+#define CA_NSLOT 14
+__device__ __forceinline__ float ca_flux_slot(const CACtx& c, int j, int i, int slot) {
+  switch (slot) {
+    case 0: return ca_fe(c, j, i);
+    case 1: return ca_fe(c, j, i - 1);
+    case 2: return ca_fe(c, j + 1, i);
+    case 3: return ca_fe(c, j + 1, i - 1);
+    case 4: return ca_fn(c, j, i);
+    case 5: return ca_fn(c, j, i + 1);
+    case 6: return ca_fn(c, j - 1, i);
+    case 7: return ca_fn(c, j - 1, i + 1);
+    case 8: return ca_q(c, j, i);
+    case 9: return ca_q(c, j, i - 1);
+    case 10: return ca_q(c, j - 1, i);
+    case 11: return ca_ke(c, j, i);
+    case 12: return ca_ke(c, j, i + 1);
+    default: return ca_ke(c, j + 1, i);
+  }
+}
+__device__ __forceinline__ void swe_ca_tend_finish(const CACtx& c, int j, int i, const float* fl) {
   const B2SweParams& p = c.p;
   const size_t off = ca_m(p, j, i);
   SweK2In in;
-  in.fe_c = ca_fe(c, j, i); in.fe_w = ca_fe(c, j, i - 1); in.fen_c = ca_fe(c, j + 1, i); in.fen_w = ca_fe(c, j + 1, i - 1);
-  in.fn_c = ca_fn(c, j, i); in.fn_e = ca_fn(c, j, i + 1); in.fns_c = ca_fn(c, j - 1, i); in.fns_e = ca_fn(c, j - 1, i + 1);
-  in.q_c = ca_q(c, j, i); in.q_w = ca_q(c, j, i - 1); in.qs_c = ca_q(c, j - 1, i);
-  in.ke_c = ca_ke(c, j, i); in.ke_e = ca_ke(c, j, i + 1); in.ken_c = ca_ke(c, j + 1, i);
+  in.fe_c = fl[0]; in.fe_w = fl[1]; in.fen_c = fl[2]; in.fen_w = fl[3];
+  in.fn_c = fl[4]; in.fn_e = fl[5]; in.fns_c = fl[6]; in.fns_e = fl[7];
+  in.q_c = fl[8]; in.q_w = fl[9]; in.qs_c = fl[10];
+  in.ke_c = fl[11]; in.ke_e = fl[12]; in.ken_c = fl[13];
   in.h_c = c.h[off]; in.h_e = ca_h(c, j, i + 1); in.h_n = ca_h(c, j + 1, i);
   in.u_o = c.ua[off]; in.v_o = c.va[off];
   in.dh_o = p.first_step ? 0.f : c.dh[off];
@@ -163,6 +184,11 @@ __device__ __forceinline__ void swe_ca_tend_cell(const CACtx& c, int j, int i) {
     c.hn[off] = o.h;
     c.dho[off] = o.dh; c.duo[off] = o.du; c.dvo[off] = o.dv;
   }
+}
+__device__ __forceinline__ void swe_ca_tend_cell(const CACtx& c, int j, int i) {
+  float fl[CA_NSLOT];
+  for (int s = 0; s < CA_NSLOT; ++s) fl[s] = ca_flux_slot(c, j, i, s);
+  swe_ca_tend_finish(c, j, i, fl);
 }
 
 // ---- frame kernel D: friction ------------------------------------------------------------------
@@ -185,27 +211,36 @@ __device__ __forceinline__ float ca_upp(const CACtx& c, int j, int i) {
   return swe_friction_u(p, ca_up(c, j, i), ca_up(c, j, i + 1), ca_up(c, j, i - 1), ca_up(c, j + 1, i),
                         ca_up(c, j - 1, i), p.north_wall && j == p.ny - 2, p.south_wall && j == 1);
 }
-// v'' of cell (j, i) given its own u'' (swe_k34_body's fluxes + swe_k5_body's update)
-__device__ __forceinline__ float ca_vpp(const CACtx& c, int j, int i, float upp_c) {
+// v'' of cell (j, i) given u'' of the cell, of its west and of its south neighbour (swe_k34_body's
+// fluxes + swe_k5_body's update)
+__device__ __forceinline__ float ca_vpp(const CACtx& c, int j, int i, float upp_c, float upp_w, float upp_s) {
   const B2SweParams& p = c.p;
   const float v_c = ca_vp(c, j, i);
   const float fe2_c = swe_visc_flux(p.c_nux, ca_vp(c, j, i + 1), upp_c);
-  const float fe2_w = swe_visc_flux(p.c_nux, v_c, ca_upp(c, j, i - 1));
+  const float fe2_w = swe_visc_flux(p.c_nux, v_c, upp_w);
   const float fn2_c = swe_visc_flux(p.c_nuy, ca_vp(c, j + 1, i), upp_c);
-  const float fn2_s = swe_visc_flux(p.c_nuy, v_c, ca_upp(c, j - 1, i));      // south wall: clamped loads, discarded
+  const float fn2_s = swe_visc_flux(p.c_nuy, v_c, upp_s);                     // south wall: clamped loads, discarded
   return swe_apply_div(p, v_c, fe2_c, fe2_w, (p.north_wall && j == p.ny - 2) ? 0.f : fn2_c,
                        (p.south_wall && j == 1) ? 0.f : fn2_s);
+}
+// the three u'' values a cell's friction needs: slot 0 = the cell, 1 = west, 2 = south (a warp of
+// kernel D evaluates one slot for 32 cells)
+__device__ __forceinline__ float ca_upp_slot(const CACtx& c, int j, int i, int slot) {
+  return slot == 0 ? ca_upp(c, j, i) : slot == 1 ? ca_upp(c, j, i - 1) : ca_upp(c, j - 1, i);
+}
+// cells beyond the first halo layer only need their own u'' (their v'' is never used)
+__device__ __forceinline__ bool ca_needs_vpp(const B2SweParams& p, int j, int i) {
+  return j >= 0 && j <= p.ny - 1 && i >= 0 && i <= p.nx - 1;
 }
 
 // one of this rank's frame cells: u'' -> ua, v'' -> va; ring cells also mirror u', v' into the
 // stale store (what the neighbours see in their halo until the next exchange)
-__device__ __forceinline__ void swe_ca_fric_cell(const CACtx& c, float* __restrict__ ua_out,
-                                                 float* __restrict__ va_out, int j, int i) {
+__device__ __forceinline__ void swe_ca_fric_finish(const CACtx& c, float* __restrict__ ua_out,
+                                                   float* __restrict__ va_out, int j, int i, const float* upp) {
   const B2SweParams& p = c.p;
   const size_t off = ca_m(p, j, i);
-  const float upp = ca_upp(c, j, i);
-  ua_out[off] = upp;
-  va_out[off] = ca_vpp(c, j, i, upp);
+  ua_out[off] = upp[0];
+  va_out[off] = ca_vpp(c, j, i, upp[0], upp[1], upp[2]);
   if (j == 1 || j == p.ny - 2 || i == 1 || i == p.nx - 2) {
     const size_t e = ca_e(c.x, j, i);
     c.x.upx[e] = c.upf[off];
@@ -215,19 +250,17 @@ __device__ __forceinline__ void swe_ca_fric_cell(const CACtx& c, float* __restri
 // a neighbour's cell, one or two layers beyond the edge: its u'' (and v'' on layer 1).  Layer 1 is
 // also the main arrays' halo: u, v get the exchanged u', v' there -- stale by this friction step,
 // which is what the reference's in-place update leaves in the halo.
-__device__ __forceinline__ void swe_ca_fric_ext_cell(const CACtx& c, float* __restrict__ ua_out,
-                                                     float* __restrict__ va_out, int j, int i) {
+__device__ __forceinline__ void swe_ca_fric_ext_finish(const CACtx& c, float* __restrict__ ua_out,
+                                                       float* __restrict__ va_out, int j, int i, const float* upp) {
   const B2SweParams& p = c.p;
-  const float upp = ca_upp(c, j, i);
   const size_t e = ca_e(c.x, j, i);
-  c.x.uppx[e] = upp;
-  if (j >= 0 && j <= p.ny - 1 && i >= 0 && i <= p.nx - 1) {
-    c.x.vppx[e] = ca_vpp(c, j, i, upp);
+  c.x.uppx[e] = upp[0];
+  if (ca_needs_vpp(p, j, i)) {
+    c.x.vppx[e] = ca_vpp(c, j, i, upp[0], upp[1], upp[2]);
     ua_out[ca_m(p, j, i)] = c.x.upx[e];
     va_out[ca_m(p, j, i)] = c.x.vpx[e];
   }
 }
-
 // ---- task enumeration ----------------------------------------------------------------------------
 // Bulk (b2_swe_strip.cuh) = rows [4, ny-5] x columns [4, cb1); frame = every other interior cell.
 // A band of width w: rows [1, w] and [ny-1-w, ny-2] completely, of the rows in between the columns
@@ -281,6 +314,24 @@ __host__ __device__ inline bool ca_ext_cell(const B2SweParams& p, long long idx,
   }
   return !ca_wall_row(p, j);
 }
+// task t of kernel D -> cell; frame cells first, then the two layers beyond the edge
+__device__ __forceinline__ bool ca_fric_task(const B2SweParams& p, const CAFrame& f, long long t, int& j, int& i,
+                                             bool& ext) {
+  ext = t >= f.total;
+  if (!ext) return ca_frame_cell(p, f, t, j, i);
+  return ca_ext_cell(p, t - f.total, j, i);
+}
+__device__ __forceinline__ void swe_ca_fric_task(const CACtx& c, const CAFrame& f, float* __restrict__ ua_out,
+                                                 float* __restrict__ va_out, long long t) {
+  int j, i;
+  bool ext;
+  if (!ca_fric_task(c.p, f, t, j, i, ext)) return;
+  float upp[3] = {ca_upp_slot(c, j, i, 0), 0.f, 0.f};
+  if (ca_needs_vpp(c.p, j, i)) { upp[1] = ca_upp_slot(c, j, i, 1); upp[2] = ca_upp_slot(c, j, i, 2); }
+  if (ext) swe_ca_fric_ext_finish(c, ua_out, va_out, j, i, upp);
+  else swe_ca_fric_finish(c, ua_out, va_out, j, i, upp);
+}
+
 // ---- exchange geometry -----------------------------------------------------------------------------
 // Element e of the message that LANDS on receiver side `side` (FS_W = it comes from the west
 // neighbour, ...): field f, the sender's cell (js, is), the receiver's cell (jr, ir) and the layer

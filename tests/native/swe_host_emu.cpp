@@ -25,6 +25,37 @@ static void masks(const B2SweParams& p, int i0, bool m[4]) {
   for (int k = 0; k < 4; ++k) m[k] = (i0 + k >= 1) && (i0 + k <= p.nx - 2);
 }
 
+struct EmuStep {      // the arrays of one rank for one step (B2SweState roles of b2_swe_multistep_ca)
+  const float *h, *u, *v, *dh, *du, *dv;
+  float *h_o, *u_o, *v_o, *dh_o, *du_o, *dv_o, *upf, *vpf;
+};
+
+template <int NT>
+static void emu_bulk(const StripArgs& a, int reverse) {
+  const int nb = strip_nstrips(a) * strip_nchunks(a);
+  static StripSmem<NT> sm;
+  for (int bb = 0; bb < nb; ++bb) {
+    const int b = reverse ? nb - 1 - bb : bb;
+    const StripGeo g = strip_geo(a, b);
+    for (int k = 0; k < (int)(sizeof(sm) / sizeof(float)); ++k) ((float*)&sm)[k] = NAN;     // stale smem of another CTA
+    static StripThr thr[NT];                      // per-thread state (prefetch registers) lives across iterations
+    for (int tt = 0; tt < NT; ++tt) thr[tt] = strip_thread(a, g, tt);
+    strip_cta(a, sm, g, [&](auto&& phase) {
+      for (int tt = 0; tt < NT; ++tt) phase(thr[reverse ? NT - 1 - tt : tt]);
+    });
+  }
+}
+static StripArgs strip_args(const B2SweParams* p, const EmuStep* e, int nt, int ry) {
+  StripArgs a;
+  a.p = *p; a.cb1 = swe_ca_cb1(*p);
+  a.h = e ? e->h : nullptr; a.u = e ? e->u : nullptr; a.v = e ? e->v : nullptr;
+  a.dh = e ? e->dh : nullptr; a.du = e ? e->du : nullptr; a.dv = e ? e->dv : nullptr;
+  a.h_o = e ? e->h_o : nullptr; a.u_o = e ? e->u_o : nullptr; a.v_o = e ? e->v_o : nullptr;
+  a.dh_o = e ? e->dh_o : nullptr; a.du_o = e ? e->du_o : nullptr; a.dv_o = e ? e->dv_o : nullptr;
+  if (nt > 0) { a.nt = nt; a.ry = ry; }
+  else strip_shape(a, 148);
+  return a;
+}
 extern "C" {
 
 // K1 on every interior row / group (what swe_k1_fluxes does)
@@ -76,11 +107,6 @@ void emu_k34(const B2SweParams* p, const float* u, float* u_new, const float* v,
 // ---- communication-avoiding step (csrc/b2_swe_ca_body.cuh, b2_swe_strip.cuh): the kernels of
 // b2_swe_ca.cu as loops.  `reverse` walks the tasks backwards: a kernel whose threads only read what no
 // thread of the same launch (or phase) writes gives the same bits in any order.
-struct EmuStep {      // the arrays of one rank for one step (B2SweState roles of b2_swe_multistep_ca)
-  const float *h, *u, *v, *dh, *du, *dv;
-  float *h_o, *u_o, *v_o, *dh_o, *du_o, *dv_o, *upf, *vpf;
-};
-
 static CACtx make_ctx(const B2SweParams* p, const B2SweCA* x, const EmuStep* e) {
   CACtx c;
   c.p = *p; c.x = *x; c.x.cb1 = swe_ca_cb1(*p);
@@ -106,40 +132,24 @@ void emu_ca_fric_frame(const B2SweParams* p, const B2SweCA* x, const EmuStep* e,
   const CACtx c = make_ctx(p, x, e);
   const CAFrame f = ca_frame(c.p, 3, c.x.cb1);
   const long long n = f.total + ca_ext_total(c.p);
-  for (long long k = 0; k < n; ++k) {
-    const long long t = reverse ? n - 1 - k : k;
-    int j, i;
-    if (t < f.total) {
-      ca_frame_cell(c.p, f, t, j, i);
-      swe_ca_fric_cell(c, e->u_o, e->v_o, j, i);
-    } else if (ca_ext_cell(c.p, t - f.total, j, i)) {
-      swe_ca_fric_ext_cell(c, e->u_o, e->v_o, j, i);
-    }
-  }
+  for (long long k = 0; k < n; ++k) swe_ca_fric_task(c, f, e->u_o, e->v_o, reverse ? n - 1 - k : k);
 }
 
 // swe_ca_bulk_step: CTAs one after the other, every phase as a loop over the CTA's threads
 // (`reverse`: CTAs and threads backwards -- a phase only reads what earlier phases wrote)
-void emu_ca_bulk_step(const B2SweParams* p, const EmuStep* e, int reverse) {
-  StripArgs a;
-  a.p = *p; a.cb1 = swe_ca_cb1(*p);
-  a.h = e->h; a.u = e->u; a.v = e->v; a.dh = e->dh; a.du = e->du; a.dv = e->dv;
-  a.h_o = e->h_o; a.u_o = e->u_o; a.v_o = e->v_o; a.dh_o = e->dh_o; a.du_o = e->du_o; a.dv_o = e->dv_o;
-  const int nb = strip_nstrips(a.p, a.cb1) * strip_nchunks(a.p);
-  static StripSmem sm;
-  for (int bb = 0; bb < nb; ++bb) {
-    const int b = reverse ? nb - 1 - bb : bb;
-    const StripGeo g = strip_geo(a.p, a.cb1, b);
-    for (int k = 0; k < (int)(sizeof(sm) / sizeof(float)); ++k) ((float*)&sm)[k] = NAN;     // stale smem of another CTA
-    strip_cta(a, sm, g, [&](auto&& phase) {
-      for (int tt = 0; tt < STRIP_NT; ++tt) phase(strip_thread(a, g, reverse ? STRIP_NT - 1 - tt : tt));
-    });
-  }
+void emu_ca_bulk_step(const B2SweParams* p, const EmuStep* e, int reverse, int nt, int ry) {
+  const StripArgs a = strip_args(p, e, nt, ry);
+  if (a.nt == 256) emu_bulk<256>(a, reverse);
+  else emu_bulk<128>(a, reverse);
+}
+void emu_strip_shape(const B2SweParams* p, int* nt, int* ry, int* nctas) {
+  const StripArgs a = strip_args(p, nullptr, 0, 0);
+  *nt = a.nt; *ry = a.ry; *nctas = strip_nstrips(a) * strip_nchunks(a);
 }
 
 // which interior cells do the bulk kernel and the frame kernels WRITE?  marks[j * nx + i]: +1 frame
 // (kernel D's cells = kernel A's full updates), +16 bulk, +256 kernel A's u' / v' band
-void emu_ca_marks(const B2SweParams* p, int* marks) {
+void emu_ca_marks(const B2SweParams* p, int* marks, int nt, int ry) {
   const int cb1 = swe_ca_cb1(*p);
   const CAFrame fd = ca_frame(*p, 3, cb1), fa = ca_frame(*p, 5, cb1 - 2);
   int j, i;
@@ -147,11 +157,12 @@ void emu_ca_marks(const B2SweParams* p, int* marks) {
     if (ca_frame_cell(*p, fd, t, j, i)) marks[j * p->nx + i] += 1;
   for (long long t = 0; t < fa.total; ++t)
     if (ca_frame_cell(*p, fa, t, j, i)) marks[j * p->nx + i] += 256;
-  const int nb = strip_nstrips(*p, cb1) * strip_nchunks(*p);
+  const StripArgs a = strip_args(p, nullptr, nt, ry);
+  const int nb = strip_nstrips(a) * strip_nchunks(a);
   for (int b = 0; b < nb; ++b) {
-    const StripGeo g = strip_geo(*p, cb1, b);
+    const StripGeo g = strip_geo(a, b);
     for (int jj = g.j0; jj < g.j1; ++jj)
-      for (int tid = 4; tid <= STRIP_NT - 4; ++tid)
+      for (int tid = 4; tid <= a.nt - 4; ++tid)
         if (g.i0 - 4 + tid < cb1) marks[jj * p->nx + g.i0 - 4 + tid] += 16;
   }
 }

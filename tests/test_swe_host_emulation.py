@@ -227,7 +227,7 @@ class EmuStep(ctypes.Structure):      # EmuStep (tests/native/swe_host_emu.cpp):
                                                 "dv_o", "upf", "vpf")]
 
 
-def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0):
+def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0, nt=0, ry=0):
     """The launch sequence of b2_swe_multistep_ca on a process grid: per step the bulk kernel (whole
     step, one pass), frame kernel A, the deep exchange, frame kernel D; every prognostic array is a
     ping-pong pair.  (Messages are read before any rank scatters: all sends of a step come from h',
@@ -260,7 +260,7 @@ def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0):
                       **{k + "_o": r[pairs[k][nxt]].ctypes.data for k in pairs},
                       upf=r["upf"].ctypes.data, vpf=r["vpf"].ctypes.data) for r in ranks]
         for p, x, e in zip(ps, xs, es):
-            emu.emu_ca_bulk_step(B(p), B(e), reverse)
+            emu.emu_ca_bulk_step(B(p), B(e), reverse, nt, ry)
             emu.emu_ca_tend_frame(B(p), B(x), B(e), reverse)
         _ca_exchange(emu, ranks, (pairs["h"][nxt], "upf", "vpf"), ny, nx, pitch, epitch, PY, PX)
         for p, x, e in zip(ps, xs, es):
@@ -269,13 +269,14 @@ def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0):
     return [{k: r[pairs[k][cur]][:, :nx] for k in pairs} for r in ranks]
 
 
+@pytest.mark.parametrize("shape_cta", [(0, 0), (256, 128), (128, 16), (128, 8), (256, 32)], ids=str)
 @pytest.mark.parametrize("shape", [(16, 24), (26, 50), (17, 29), (140, 33), (31, 300), (200, 530)])
-def test_ca_bulk_and_frame_partition_the_interior(emu, shape):
+def test_ca_bulk_and_frame_partition_the_interior(emu, shape, shape_cta):
     ny, nx = shape
     p, *_ = _setup(ny, nx, False, 0, 0)
     assert emu.emu_ca_supported(ctypes.byref(p)) == 1
     marks = np.zeros((ny, nx), np.int32)
-    emu.emu_ca_marks(ctypes.byref(p), marks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    emu.emu_ca_marks(ctypes.byref(p), marks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), *shape_cta)
     owner = marks & 0xff                     # 1 = frame kernels, 16 = bulk kernel (several CTAs)
     assert set(np.unique(owner[1:-1, 1:-1])) <= {1, 16}          # every interior cell written exactly once
     assert marks[0].sum() == marks[-1].sum() == marks[:, 0].sum() == marks[:, -1].sum() == 0
@@ -317,8 +318,20 @@ def test_emulated_ca_pipeline_with_several_strips_and_chunks(emu):
 
     model = ShallowWaterModel(ShallowWaterConfig(nx=530, ny=300), device="cpu", backend="ops")
     a = _emulate(emu, model, 1, 1, 3)
-    b = _emulate_ca(emu, model, 1, 1, 3)
-    c = _emulate_ca(emu, model, 1, 1, 3, reverse=1)
-    for name in a[0]:
-        assert np.array_equal(a[0][name][1:-1, 1:-1], b[0][name][1:-1, 1:-1]), name
-        assert np.array_equal(b[0][name][1:-1, 1:-1], c[0][name][1:-1, 1:-1]), (name, "task order")
+    for nt, ry, rev in ((256, 128, 0), (256, 128, 1), (128, 16, 0), (128, 8, 1), (256, 64, 0), (0, 0, 0)):
+        b = _emulate_ca(emu, model, 1, 1, 3, reverse=rev, nt=nt, ry=ry)
+        for name in a[0]:
+            assert np.array_equal(a[0][name][1:-1, 1:-1], b[0][name][1:-1, 1:-1]), (name, nt, ry, rev)
+
+
+def test_strip_shape_fills_the_gpu(emu):
+    """CTA shape heuristics: long wide CTAs on a 4096^2 block, enough CTAs for 148 SMs on an 8-GPU block."""
+    got = {}
+    for ny, nx in ((4098, 4098), (2050, 1026), (2050, 2050), (66, 130)):
+        p, *_ = _setup(ny, nx, False, 0, 0)
+        nt, ry, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        emu.emu_strip_shape(ctypes.byref(p), ctypes.byref(nt), ctypes.byref(ry), ctypes.byref(n))
+        got[(ny, nx)] = (nt.value, ry.value, n.value)
+    assert got[(4098, 4098)][0] == 256 and got[(4098, 4098)][2] >= 444
+    assert got[(2050, 1026)][2] >= 300, got
+    assert got[(2050, 2050)][2] >= 400, got
