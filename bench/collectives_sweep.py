@@ -34,6 +34,10 @@ ap.add_argument("--max-bytes", type=int, default=1 << 30)
 ap.add_argument("--out", default="gpurun_out/collectives_sweep.json")
 ap.add_argument("--quick", action="store_true", help="every fourth size")
 ap.add_argument("--skip-allreduce-algos", action="store_true", help="time only the automatic choice")
+ap.add_argument("--only-allreduce", action="store_true", help="stop after the allreduce tables")
+ap.add_argument("--max-blocks", type=int, default=0, help="override the collective grid cap")
+ap.add_argument("--nvls-pipeline", type=int, default=-1, help="0 / 1: software pipelining of the NVLS allreduce")
+ap.add_argument("--min-bytes", type=int, default=1 << 10)
 ns = ap.parse_args()
 
 comm = MPI.COMM_WORLD
@@ -51,6 +55,10 @@ except Exception as exc:  # pragma: no cover
     nccl = None
 nc = comm._native_comm()
 has_nvls = nc.has_nvls
+if ns.max_blocks:
+    nc.set_tuning(max_blocks=ns.max_blocks)
+if ns.nvls_pipeline >= 0:
+    nc.set_option("nvls_pipeline", ns.nvls_pipeline)
 
 
 def reps_for(nbytes):
@@ -111,7 +119,7 @@ def time_nccl(fn, reps):
         return time_eager(fn, max(reps, 10))
 
 
-sizes = [1 << k for k in range(10, 31, 2 if ns.quick else 1) if (1 << k) <= ns.max_bytes]
+sizes = [1 << k for k in range(10, 31, 2 if ns.quick else 1) if ns.min_bytes <= (1 << k) <= ns.max_bytes]
 result = {"world": size, "nvls": has_nvls, "allreduce": {}, "allgather": {}, "alltoall": {}, "p2p": {}}
 
 # ---------------------------------------------------------------- allreduce
@@ -141,6 +149,14 @@ for dtype, dname in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
             print(dname, nbytes, {k: (v.get("us"), v.get("busbw")) for k, v in row.items()}, flush=True)
         del x
     result["allreduce"][dname] = table
+
+if ns.only_allreduce:
+    if rank == 0:
+        os.makedirs(os.path.dirname(ns.out) or ".", exist_ok=True)
+        with open(ns.out, "w") as f:
+            json.dump(result, f, indent=1)
+    m.flush()
+    sys.exit(0)
 
 # ---------------------------------------------------------------- allgather / alltoall (per-rank payload = nbytes)
 for nbytes in sizes:

@@ -232,26 +232,29 @@ b2_k_allreduce_nvls(const B2DevComm c, const B2ReduceArgs a) {
   const int t = threadIdx.x;
 #define CH_OFF(ch) ((ch) * a.chunk)
 #define CH_LEN(ch) ((a.nbytes - CH_OFF(ch) < a.chunk) ? (a.nbytes - CH_OFF(ch)) : a.chunk)
-  size_t ch = blockIdx.x;
-  if (ch < nchunks) {
-    b2_copy_bytes<false>(mine + CH_OFF(ch), in + CH_OFF(ch), CH_LEN(ch));
-    b2_barrier_arrive(c, ++e);                                   // A1(0)
-    unsigned e_a1 = e;
-    for (; ch < nchunks; ch += gridDim.x) {
-      const size_t nxt = ch + gridDim.x;
-      const bool more = nxt < nchunks;
-      if (more) b2_copy_bytes<false>(mine + CH_OFF(nxt), in + CH_OFF(nxt), CH_LEN(nxt));
-      b2_barrier_wait(c, e_a1, a.opcode);                        // W1: every rank staged this chunk
-      b2_nvls_slice<DT>(c, mc, CH_OFF(ch), CH_LEN(ch));
-      b2_barrier_arrive(c, ++e);                                 // A2
-      const unsigned e_a2 = e;
-      if (more) {                                                // A1 of the next chunk (staged above)
-        b2_barrier_arrive(c, ++e);
-        e_a1 = e;
-      }
-      b2_barrier_wait(c, e_a2, a.opcode);                        // W2: every sub-slice has landed here
-      b2_copy_bytes<true>(out + CH_OFF(ch), mine + CH_OFF(ch), CH_LEN(ch));
+  const bool pipe = a.pipeline != 0;
+  unsigned e_a1 = e;
+  bool staged = false;
+  for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const size_t nxt = ch + gridDim.x;
+    const bool more = pipe && nxt < nchunks;
+    if (!staged) {
+      b2_copy_bytes<false>(mine + CH_OFF(ch), in + CH_OFF(ch), CH_LEN(ch));
+      b2_barrier_arrive(c, ++e);                                 // A1
+      e_a1 = e;
     }
+    if (more) b2_copy_bytes<false>(mine + CH_OFF(nxt), in + CH_OFF(nxt), CH_LEN(nxt));
+    b2_barrier_wait(c, e_a1, a.opcode);                          // W1: every rank staged this chunk
+    b2_nvls_slice<DT>(c, mc, CH_OFF(ch), CH_LEN(ch));
+    b2_barrier_arrive(c, ++e);                                   // A2
+    const unsigned e_a2 = e;
+    staged = more;
+    if (more) {                                                  // A1 of the next chunk (staged above)
+      b2_barrier_arrive(c, ++e);
+      e_a1 = e;
+    }
+    b2_barrier_wait(c, e_a2, a.opcode);                          // W2: every sub-slice has landed here
+    b2_copy_bytes<true>(out + CH_OFF(ch), mine + CH_OFF(ch), CH_LEN(ch));
   }
 #undef CH_OFF
 #undef CH_LEN
@@ -435,6 +438,7 @@ static int reduce_common(B2Comm* c, const void* in, void* out, size_t count, int
   B2ReduceArgs a;
   a.in = in; a.out = out; a.nbytes = nbytes;
   a.src_lo = src_lo; a.src_hi = src_hi; a.has_out = has_out; a.opcode = opcode;
+  a.pipeline = c->nvls_pipeline;
   int grid;
   pick_chunks(c, nbytes, &a.chunk, &grid);
   if (algo == B2_ALGO_NVLS) {

@@ -31,6 +31,7 @@ struct B2ReduceArgs {
   int src_hi;
   int has_out;       // this rank materialises a result (reduce: root only)
   int opcode;
+  int pipeline;      // NVLS allreduce: stage the next chunk / copy the previous one out between arrive and wait
 };
 
 template <typename T, int OP>

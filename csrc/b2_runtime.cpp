@@ -432,6 +432,7 @@ extern "C" B2Comm* b2_comm_create(int device, int rank, int nranks, B2Seg* ctl, 
   c->oneshot_max = 512 * 1024;
   c->nvls_min = 64 * 1024 + 1;
   c->bcast_mc_min = 256 * 1024;
+  c->nvls_pipeline = 1;
   // one 512-thread CTA of the collective kernels (<= 128 registers per thread) fits per SM: grids are
   // capped at the co-resident count (see pick_chunks in b2_collectives.cu)
   c->max_blocks = c->sm_count;
@@ -458,6 +459,13 @@ extern "C" int b2_comm_set_tuning(B2Comm* c, long long ll_max, long long oneshot
   if (oneshot_max >= 0) c->oneshot_max = (size_t)oneshot_max;
   if (nvls_min >= 0) c->nvls_min = (size_t)nvls_min;
   if (max_blocks > 0) c->max_blocks = max_blocks > B2_MAX_BLOCKS ? B2_MAX_BLOCKS : max_blocks;
+  return 0;
+}
+
+extern "C" int b2_comm_set_option(B2Comm* c, const char* key, long long value) {
+  if (strcmp(key, "bcast_mc_min") == 0) c->bcast_mc_min = (size_t)value;
+  else if (strcmp(key, "nvls_pipeline") == 0) c->nvls_pipeline = value != 0;
+  else { b2_set_error("unknown communicator option '%s'", key); return B2_ERR_BAD_ARG; }
   return 0;
 }
 

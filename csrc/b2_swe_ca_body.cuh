@@ -146,7 +146,40 @@ __device__ __forceinline__ float ca_ke(const CACtx& c, int j0, int i) {
 // The 14 flux values of a cell's tendency stencil, as (kind, dj, di); a warp of kernel A evaluates ONE
 // slot for 32 cells, so the cell's latency is one flux evaluation, not fourteen in a row.
 #define CA_NSLOT 14
+// a flux cell at least one cell inside the block on every side: all operands are this rank's own
+// fresh values in the main arrays -- no views, no ext arrays (4/5 of kernel A's cells only ever
+// evaluate such fluxes; the generic accessors cost ~10x the arithmetic they feed)
+__device__ __forceinline__ float ca_flux_plain(const CACtx& c, int j, int i, int kind) {
+  const B2SweParams& p = c.p;
+  const size_t o = ca_m(p, j, i), oh = ca_m(p, hc_row(p, j), i), ohn = ca_m(p, hc_row(p, j + 1), i);
+  const size_t P = (size_t)p.pitch;
+  switch (kind) {
+    case 0: return swe_fe(c.h[oh], c.h[oh + 1], c.ua[o]);
+    case 1: return (p.north_wall && j == p.ny - 2) ? 0.f : swe_fn(c.h[oh], c.h[ohn], c.va[o]);
+    case 2: return swe_q(p, p.coriolis[j], c.va[o + 1], c.va[o], c.ua[o + P], c.ua[o], c.h[oh], c.h[oh + 1], c.h[ohn],
+                         c.h[ohn + 1]);
+    default: return swe_ke(c.ua[o], c.ua[o - 1], c.va[o], c.va[o - P]);
+  }
+}
 __device__ __forceinline__ float ca_flux_slot(const CACtx& c, int j, int i, int slot) {
+  if (j >= 3 && j <= c.p.ny - 4 && i >= 3 && i <= c.p.nx - 4) {        // every flux of the stencil is plain
+    switch (slot) {
+      case 0: return ca_flux_plain(c, j, i, 0);
+      case 1: return ca_flux_plain(c, j, i - 1, 0);
+      case 2: return ca_flux_plain(c, j + 1, i, 0);
+      case 3: return ca_flux_plain(c, j + 1, i - 1, 0);
+      case 4: return ca_flux_plain(c, j, i, 1);
+      case 5: return ca_flux_plain(c, j, i + 1, 1);
+      case 6: return ca_flux_plain(c, j - 1, i, 1);
+      case 7: return ca_flux_plain(c, j - 1, i + 1, 1);
+      case 8: return ca_flux_plain(c, j, i, 2);
+      case 9: return ca_flux_plain(c, j, i - 1, 2);
+      case 10: return ca_flux_plain(c, j - 1, i, 2);
+      case 11: return ca_flux_plain(c, j, i, 3);
+      case 12: return ca_flux_plain(c, j, i + 1, 3);
+      default: return ca_flux_plain(c, j + 1, i, 3);
+    }
+  }
   switch (slot) {
     case 0: return ca_fe(c, j, i);
     case 1: return ca_fe(c, j, i - 1);
@@ -287,9 +320,12 @@ __host__ __device__ inline bool ca_frame_cell(const B2SweParams& p, const CAFram
     i = 1 + (int)(idx % (p.nx - 2));
     j = r < f.w ? 1 + r : (p.ny - 1 - f.w) + (r - f.w);
   } else {
+    // side bands column by column (a warp's 32 cells then share their distance from the edge, i.e.
+    // take the same path through the accessors)
     const long long t = idx - f.nfull;
-    const int s = (int)(t % f.per);
-    j = f.w + 1 + (int)(t / f.per);
+    const int nrows = p.ny - 2 - 2 * f.w;
+    const int s = (int)(t / nrows);
+    j = f.w + 1 + (int)(t % nrows);
     i = s < f.w ? 1 + s : f.ce + (s - f.w);
   }
   return true;

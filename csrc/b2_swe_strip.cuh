@@ -9,14 +9,17 @@
 // FIVE DIFFERENT rows, each consuming only what the previous iterations produced, so one barrier
 // per row is enough and the phases' instructions interleave freely:
 //
-//   L  input rows              row r      registers (prefetched an iteration ahead) -> H, U, V rings
+//   L  input rows              row r + 3  cp.async global -> H, U, V rings (three rows in flight per array;
+//                                         old tendencies of row r - 1 likewise, used three iterations on)
 //   F  fluxes fe, fn, q, ke    row r - 2  -> FE, FN, Q, KE
 //   T  tendencies + AB2 update row r - 4  -> h', dh, du, dv to memory;  u', v' -> UP, VP
 //   U  friction-u              row r - 6  -> UPP (u'')
 //   V  friction-v              row r - 7  -> u'', v'' to memory
 //
 // (The first version had the phases on consecutive rows with a barrier and a global load between
-// them: 1.8 us per row, latency-bound, slower than the kernels it replaced.)
+// them: 1.8 us per row; the second prefetched one row ahead into registers: still waiting on
+// memory every iteration.  A CTA's row loop is serial, so its loads must be issued microseconds,
+// not one iteration, before they are needed.)
 //
 // Each quantity is computed ONCE per cell (the register-only fused kernels it replaces evaluated
 // 9.5 flux quantities and 2.25 friction stencils per cell and were issue-bound); the redundancy is
@@ -51,6 +54,7 @@ struct StripSmem {
   float FE[4][NT], FN[4][NT], Q[4][NT], KE[4][NT];
   float UP[4][NT], VP[4][NT];
   float UPP[4][NT];
+  float DH[4][NT], DU[4][NT], DV[4][NT];      // old tendencies, own column only (cp.async landing zone)
 };
 
 __host__ __device__ inline int strip_nstrips(const StripArgs& a) { return (a.cb1 - 4 + (a.nt - 7) - 1) / (a.nt - 7); }
@@ -88,7 +92,7 @@ __host__ __device__ __forceinline__ int strip_col(const B2SweParams& p, const St
 }
 
 // what a thread knows about itself and its CTA, computed once (the row loop then spends its integer
-// instructions on a handful of row compares), plus its prefetch registers
+// instructions on a handful of row compares)
 struct StripThr {
   int tid;
   bool f_ok, t_ok, u_ok, o_ok;       // this column takes part in the flux / tendency / friction-u phase; is an output column
@@ -97,9 +101,6 @@ struct StripThr {
   int r_last;                        // last input row
   size_t col, pitch;
   long long off;                     // r * pitch + column of the current row index (advanced once per row)
-  float nh, nu, nv;                  // inputs of row r + 1 (in flight while row r is processed)
-  float cdh, cdu, cdv;               // old tendencies of this iteration's tendency row, r - 4
-  float ndh, ndu, ndv;               // ... of the next iteration's
 };
 __host__ __device__ inline StripThr strip_thread(const StripArgs& a, const StripGeo& g, int tid) {
   StripThr t;
@@ -118,30 +119,45 @@ __host__ __device__ inline StripThr strip_thread(const StripArgs& a, const Strip
   t.col = (size_t)strip_col(a.p, g, tid);
   t.pitch = (size_t)a.p.pitch;
   t.off = 0;
-  t.nh = t.nu = t.nv = t.cdh = t.cdu = t.cdv = t.ndh = t.ndu = t.ndv = 0.f;
   return t;
 }
 
 // ---- the phases of row index r; Q = r & 7 is a template parameter (the row loop is unrolled by eight),
 // so every ring slot is a compile-time constant and a shared-memory access costs one instruction ----
-// issue the loads the NEXT iteration consumes: inputs of row r + 1, old tendencies of row r - 3
-__device__ __forceinline__ void strip_prefetch(const StripArgs& a, StripThr& t, int r) {
-  if (r + 1 >= 0 && r + 1 <= t.r_last) {
-    const long long off = t.off + (long long)t.pitch;
-    t.nh = a.h[off]; t.nu = a.u[off]; t.nv = a.v[off];
-  }
-  t.cdh = t.ndh; t.cdu = t.ndu; t.cdv = t.ndv;
-  if (!a.p.first_step && t.t_ok && r + 1 >= t.r_t && r - 3 <= t.r_last) {
-    const long long off = t.off - 3 * (long long)t.pitch;
-    t.ndh = a.dh[off]; t.ndu = a.du[off]; t.ndv = a.dv[off];
-  }
+// asynchronous 4-byte copy global -> shared (the host emulation copies at once)
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ void strip_cp(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void strip_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void strip_wait3() { asm volatile("cp.async.wait_group 3;" ::: "memory"); }
+#else
+static inline void strip_cp(float* dst, const float* src) { *dst = *src; }
+static inline void strip_commit() {}
+static inline void strip_wait3() {}
+#endif
+#define STRIP_PF 3      // rows in flight ahead of the row being assembled
+// group of iteration r: inputs of row r + 3 and the old tendencies of row r - 1 (this thread's column);
+// afterwards everything issued three iterations ago (row r, tendencies of row r - 4) has landed
 template <int Q, class SM>
-__device__ __forceinline__ void strip_load(SM& s, StripThr& t, int r) {
-  if (r > t.r_last) return;
-  s.H[Q][t.tid] = t.nh;
-  s.U[Q][t.tid] = t.nu;
-  s.V[Q][t.tid] = t.nv;
+__device__ __forceinline__ void strip_issue(const StripArgs& a, SM& s, const StripThr& t, int r) {
+  const int tid = t.tid;
+  if (r + STRIP_PF >= 0 && r + STRIP_PF <= t.r_last) {
+    const long long off = t.off + STRIP_PF * (long long)t.pitch;
+    constexpr int w = (Q + STRIP_PF) & 7;
+    strip_cp(&s.H[w][tid], a.h + off);
+    strip_cp(&s.U[w][tid], a.u + off);
+    strip_cp(&s.V[w][tid], a.v + off);
+  }
+  if (!a.p.first_step && t.t_ok && r + 3 >= t.r_t && r - 1 <= t.r_last) {
+    const long long off = t.off - (long long)t.pitch;
+    constexpr int w = (Q + 3) & 3;
+    strip_cp(&s.DH[w][tid], a.dh + off);
+    strip_cp(&s.DU[w][tid], a.du + off);
+    strip_cp(&s.DV[w][tid], a.dv + off);
+  }
+  strip_commit();
+  strip_wait3();
 }
 // fluxes of row jf = r - 2 (rows 1 .. ny-3: no wall rule applies)
 template <int Q, class SM>
@@ -170,7 +186,8 @@ __device__ __forceinline__ void strip_tend(const StripArgs& a, SM& s, const Stri
   in.ke_c = s.KE[c][tid]; in.ke_e = s.KE[c][tid + 1]; in.ken_c = s.KE[n][tid];
   in.h_c = s.H[hc][tid]; in.h_e = s.H[hc][tid + 1]; in.h_n = s.H[hn][tid];
   in.u_o = s.U[hc][tid]; in.v_o = s.V[hc][tid];
-  in.dh_o = t.cdh; in.du_o = t.cdu; in.dv_o = t.cdv;          // (zero on the first step: never loaded)
+  in.dh_o = in.du_o = in.dv_o = 0.f;
+  if (!p.first_step) { in.dh_o = s.DH[c][tid]; in.du_o = s.DU[c][tid]; in.dv_o = s.DV[c][tid]; }
   const SweK2Out o = swe_k2_cell(p, in);
   s.UP[c][tid] = o.u;
   s.VP[c][tid] = o.v;
@@ -211,8 +228,7 @@ __device__ __forceinline__ void strip_fric_v(const StripArgs& a, SM& s, const St
 template <int Q, class SM, class Each>
 __device__ __forceinline__ void strip_row(const StripArgs& a, SM& s, int r, Each&& each) {
   each([&](StripThr& t) {
-    strip_load<Q>(s, t, r);
-    strip_prefetch(a, t, r);
+    strip_issue<Q>(a, s, t, r);
     strip_flux<Q>(a, s, t, r);
     strip_tend<Q>(a, s, t, r);
     strip_fric_u<Q>(a, s, t, r);
@@ -224,9 +240,13 @@ __device__ __forceinline__ void strip_row(const StripArgs& a, SM& s, int r, Each
 template <class SM, class Each>
 __device__ __forceinline__ void strip_cta(const StripArgs& a, SM& s, const StripGeo& g, Each&& each) {
   const int r0 = (g.j0 - 4) & ~7;
-  each([&](StripThr& t) {
-    t.off = (long long)(r0 - 1) * (long long)t.pitch + (long long)t.col;
-    strip_prefetch(a, t, r0 - 1);                                   // row r0 into the prefetch registers
+  each([&](StripThr& t) {                                           // prime the pipeline: rows r0 .. r0 + 2
+    t.off = (long long)(r0 - 3) * (long long)t.pitch + (long long)t.col;
+    strip_issue<5>(a, s, t, r0 - 3);                                // (r0 is a multiple of 8: (r0 - 3) & 7 = 5)
+    t.off += (long long)t.pitch;
+    strip_issue<6>(a, s, t, r0 - 2);
+    t.off += (long long)t.pitch;
+    strip_issue<7>(a, s, t, r0 - 1);
     t.off += (long long)t.pitch;
   });
   for (int rb = r0; rb <= g.j1 + 6; rb += 8) {

@@ -343,6 +343,10 @@ class NativeComm:
     def set_tuning(self, ll_max=-1, oneshot_max=-1, nvls_min=-1, max_blocks=0) -> None:
         _lib().b2_comm_set_tuning(self.handle, ll_max, oneshot_max, nvls_min, max_blocks)
 
+    def set_option(self, key: str, value: int) -> None:
+        """Runtime switches of the native communicator: ``bcast_mc_min`` (bytes), ``nvls_pipeline`` (0/1)."""
+        self._check(_lib().b2_comm_set_option(self.handle, key.encode(), int(value)), "Comm_set_option")
+
     def destroy(self) -> None:
         lib = _lib()
         try:

@@ -254,11 +254,39 @@ def _control_group_for_world():
     return dist.new_group(backend="gloo")
 
 
+def _new_member_group(ranks: Sequence[int], gname: str):
+    """A gloo group created by ITS MEMBERS ONLY, under a name they agree on.
+
+    ``dist.new_group`` must be entered by every process of the job (its group names come from a
+    job-wide counter); its ``use_local_synchronization=True`` variant hashes the member list together
+    with the number of groups THIS process has created so far, so members with different histories --
+    exactly the situation of a Dup / Split on a sub-communicator -- compute different names and hang
+    in the rendezvous.  MPI lets any communicator be duplicated or split by its members alone, so the
+    group is built one level below, with a name derived from the parent communicator (same on every
+    member by construction, see ``Comm._child_name``)."""
+    ranks = sorted(ranks)
+    try:
+        from torch.distributed import distributed_c10d as c10d
+
+        default_pg = c10d._get_default_group()
+        _, store = c10d._world.pg_map[default_pg]
+        backend = c10d.Backend("gloo")
+        pg, _ = c10d._new_process_group_helper(
+            len(ranks), ranks.index(dist.get_rank()), ranks, backend, store, c10d.GroupName(gname),
+            timeout=c10d._get_default_timeout(backend))
+        c10d._world.pg_group_ranks[pg] = {g: i for i, g in enumerate(ranks)}
+        return pg
+    except (ImportError, AttributeError, KeyError, TypeError):   # pragma: no cover - private API moved
+        return dist.new_group(ranks=ranks, backend="gloo", use_local_synchronization=True)
+
+
 class Comm:
     """An intra-communicator over a subset of the job's processes."""
 
-    def __init__(self, group, ranks: Sequence[int], name: str = "comm"):
+    def __init__(self, group, ranks: Sequence[int], name: str = "comm", gname: str = "b2w"):
         global _comm_counter
+        self._gname = gname            # job-unique name of the control-plane group (same on every member)
+        self._children = 0             # Clone / Split calls so far (collective, hence equal on every member)
         self._group = group
         self._ranks = list(ranks)
         self._global_rank = dist.get_rank()
@@ -303,11 +331,10 @@ class Comm:
         """A communicator over the same processes with private message channels
         (collective; reference default comm = ``COMM_WORLD.Clone()``, utils.py:20-27)."""
         self._check_alive()
-        # use_local_synchronization: only the members of THIS communicator take part (hashed group
-        # name instead of the job-wide group counter), so Dup / Split work on sub-communicators
-        # while the other ranks of the job do something else -- as in MPI
-        group = dist.new_group(ranks=self._ranks, backend="gloo", use_local_synchronization=True)
-        return Comm(group, self._ranks, name=self._name + ".clone")
+        # only the members of THIS communicator take part (see _new_member_group), so Dup / Split work
+        # on sub-communicators while the other ranks of the job do something else -- as in MPI
+        gname = self._child_name("c")
+        return Comm(_new_member_group(self._ranks, gname), self._ranks, name=self._name + ".clone", gname=gname)
 
     Dup = Clone
 
@@ -317,13 +344,13 @@ class Comm:
         info = [None] * self.size
         dist.all_gather_object(info, (int(color), int(key), self._global_rank), group=self._group)
         info = self._in_rank_order(info)
+        gname = self._child_name(f"s{color}")         # (counted on every member, UNDEFINED ones included)
         if color == UNDEFINED:
             return None
         members = sorted((k, r) for cc, k, r in info if cc == color)
         ranks = [r for _, r in members]
         # each rank creates only the group it belongs to (member-only synchronisation, see Clone)
-        group = dist.new_group(ranks=ranks, backend="gloo", use_local_synchronization=True)
-        return Comm(group, ranks, name=f"{self._name}.split{color}")
+        return Comm(_new_member_group(ranks, gname), ranks, name=f"{self._name}.split{color}", gname=gname)
 
     def Barrier(self) -> None:
         """Host-side barrier on the control plane (mpi4py ``comm.Barrier()``)."""
@@ -425,6 +452,10 @@ class Comm:
     def _check_alive(self) -> None:
         if self._freed:
             raise MPIError("communicator has been freed")
+
+    def _child_name(self, kind: str) -> str:
+        self._children += 1
+        return f"{self._gname}/{self._children}{kind}"
 
     def _global(self, rank_in_comm: int) -> int:
         return self._ranks[rank_in_comm]
