@@ -40,7 +40,7 @@ struct B2SweState {
 struct B2SweCA {
   float *hx, *upx, *vpx, *uppx, *vppx;
   int epitch;
-  int cb1;            // first column of the east frame (nx - 4; filled in natively)
+  int cb1;            // first column of the east frame: a multiple of 4, <= nx - 4 (filled in natively)
 };
 
 #define SWE_THREADS 256

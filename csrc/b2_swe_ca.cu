@@ -3,16 +3,16 @@
 //
 // One model step (the reference's shallow_water_step, examples/shallow_water.py:270-403):
 //
-//   stream s  (bulk) :  S  the whole step on the bulk, one pass over memory (b2_swe_strip.cuh) ----+--> next step
-//                                                                                                   |
+//   stream s  (bulk) :  B  flux + tendency (bulk) -----------> Fb friction (bulk) ----------+--> next step
+//                                                    ^ (u', v' of the band next to the bulk) |
 //   stream s2 (frame):  A (tendencies, frame band) -> X (deep halo exchange) -> D (friction, frame + ext)
 //
-// S reads only the step's input arrays and writes only bulk cells of the output arrays (every
-// prognostic array is a ping-pong pair), A / X / D own the frame: no edge between the two streams
-// inside a step, two at the step boundary (S(t+1) reads what D(t) wrote next to the bulk, A(t+1)
-// what S(t) wrote next to the frame).  The NVLink round of X is hidden behind S.  Under CUDA-graph
-// capture (mpi4jax_b200.jit) the event fork / join becomes graph edges.
-// 12 array passes per step instead of 32, one exchange instead of three, 4 launches instead of 7.
+// B / Fb read only the step's input arrays (plus A's band for Fb) and write only bulk cells of the
+// output arrays (every prognostic array is a ping-pong pair), A / X / D own the frame: ONE edge
+// between the two streams inside a step (A -> Fb), two at the step boundary (B(t+1) reads what D(t)
+// wrote next to the bulk, A(t+1) what Fb(t) wrote next to the frame).  The NVLink round of X is
+// hidden behind the bulk kernels.  Under CUDA-graph capture (mpi4jax_b200.jit) the event fork /
+// join becomes graph edges.  16 array passes per step instead of 32, one exchange instead of three.
 #include <cstdio>
 #include <cstdlib>
 
@@ -20,7 +20,7 @@
 #include "b2_halo_ll.cuh"
 #include "b2_runtime.h"
 #include "b2_swe_ca_body.cuh"
-#include "b2_swe_strip.cuh"
+#include "b2_swe_k12_body.cuh"
 
 extern "C" void b2_set_error(const char* fmt, ...);
 extern "C" void b2_count_launch(B2Comm* c);
@@ -47,16 +47,21 @@ __device__ __forceinline__ void ca_stamp_end(const CAStamp& s) {
 // The frame is a few thousand cells and sits on the step's critical path: latency, not throughput.
 // A thread per cell would evaluate 14 flux quantities (kernel A) or 3 friction stencils (kernel D) one
 // after the other -- ~4000 dependent-issue instructions, measured 18 us.  Instead a CTA takes 32 cells
-// and one WARP per quantity: warp w evaluates quantity w for the 32 cells (no divergence inside a
-// warp), the values meet in shared memory, warp 0 finishes the cells.
+// and one WARP per kind of quantity: warp w evaluates the fluxes of kind w (fe / fn / q / ke; u'' of
+// the cell / its west / its south neighbour in kernel D) for the 32 cells -- no divergence inside a
+// warp --, the values meet in shared memory, warp 0 finishes the cells.
 #define CA_CELLS 32
-__global__ void __launch_bounds__(CA_CELLS * CA_NSLOT) swe_ca_tend_frame(const CACtx c, const CAFrame f, const CAStamp ts) {
+#define CA_TEND_WARPS 4          // one warp per flux KIND (fe, fn, q, ke): slots 0-3, 4-7, 8-10, 11-13
+__global__ void __launch_bounds__(CA_CELLS * CA_TEND_WARPS) swe_ca_tend_frame(const CACtx c, const CAFrame f, const CAStamp ts) {
   ca_stamp_begin(ts);
   __shared__ float fl[CA_NSLOT][CA_CELLS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int j, i;
   const bool ok = ca_frame_cell(c.p, f, (long long)blockIdx.x * CA_CELLS + lane, j, i);
-  if (ok) fl[w][lane] = ca_flux_slot(c, j, i, w);
+  if (ok) {
+    const int s0 = w == 0 ? 0 : w == 1 ? 4 : w == 2 ? 8 : 11, s1 = w == 0 ? 4 : w == 1 ? 8 : w == 2 ? 11 : 14;
+    for (int s = s0; s < s1; ++s) fl[s][lane] = ca_flux_slot(c, j, i, s);
+  }
   __syncthreads();
   if (ok && w == 0) {
     float v[CA_NSLOT];
@@ -115,25 +120,35 @@ __global__ void __launch_bounds__(CA_THREADS) swe_ca_init_ext(const B2SweParams 
   }
 }
 
-// ---- bulk kernel: the whole step in one pass (phases and geometry: b2_swe_strip.cuh) ---------------
-// an iteration ends with a barrier: the next one reads what other threads just wrote to the rings
-struct StripSync {
-  StripThr t;
-  template <class F>
-  __device__ __forceinline__ void operator()(F&& f) {
-    f(t);
-    __syncthreads();
-  }
+// ---- bulk kernels: flux + tendency, then friction, on whole float4 groups at least four cells from the
+// block edge (b2_swe_k12_body.cuh); every prognostic array is a ping-pong pair; u', v' of the bulk
+// travel through the frame band's store (upf / vpf), whose bulk cells are otherwise unused --------------
+struct BulkArgs {
+  B2SweParams p;
+  int cb1;                                           // bulk columns [4, cb1), bulk rows [4, ny - 4)
+  const float *h, *u, *v, *dh, *du, *dv;             // step inputs
+  float *h_o, *u_o, *v_o, *dh_o, *du_o, *dv_o;       // step outputs (ping-pong partners)
 };
-template <int NT>
-__global__ void __launch_bounds__(NT) swe_ca_bulk_step(const StripArgs a, const CAStamp ts) {
+__global__ void __launch_bounds__(SWE_THREADS, 3)
+swe_ca_bulk_k12(const BulkArgs a, float* __restrict__ up, float* __restrict__ vp, const CAStamp ts) {
   ca_stamp_begin(ts);
-  extern __shared__ __align__(16) unsigned char strip_smem_raw[];       // 52 rows x NT floats: above the 48 KB static limit at NT = 256
-  StripSmem<NT>& sm = *reinterpret_cast<StripSmem<NT>*>(strip_smem_raw);
-  const StripGeo g = strip_geo(a, (int)blockIdx.x);
-  StripSync each;
-  each.t = strip_thread(a, g, (int)threadIdx.x);
-  strip_cta(a, sm, g, each);
+  const long long t = (long long)blockIdx.x * SWE_THREADS + threadIdx.x;
+  if (t < ca_bulk_tasks(a.p, a.cb1)) {
+    int j, i0;
+    ca_bulk_task(a.p, a.cb1, t, j, i0);
+    swe_k12_body(a.p, a.h, a.h_o, a.u, up, a.v, vp, a.dh, a.du, a.dv, a.dh_o, a.du_o, a.dv_o, j, i0);
+  }
+  ca_stamp_end(ts);
+}
+__global__ void __launch_bounds__(SWE_THREADS, 4)
+swe_ca_bulk_fric(const BulkArgs a, const float* __restrict__ up, const float* __restrict__ vp, const CAStamp ts) {
+  ca_stamp_begin(ts);
+  const long long t = (long long)blockIdx.x * SWE_THREADS + threadIdx.x;
+  if (t < ca_bulk_tasks(a.p, a.cb1)) {
+    int j, i0;
+    ca_bulk_task(a.p, a.cb1, t, j, i0);
+    swe_k345_body(a.p, up, a.u_o, vp, a.v_o, j, i0);
+  }
   ca_stamp_end(ts);
 }
 
@@ -203,7 +218,7 @@ __global__ void __launch_bounds__(CA_THREADS) b2_k_halo_ca(const B2DevComm c, co
 
 // ---- host side --------------------------------------------------------------------------------------
 static cudaStream_t g_side = nullptr;
-static cudaEvent_t g_ev[3];
+static cudaEvent_t g_ev[4];
 
 static int ca_streams() {
   if (g_side) return 0;
@@ -216,14 +231,7 @@ static int ca_streams() {
     g_side = nullptr;
     return 1;
   }
-  if (cudaFuncSetAttribute(swe_ca_bulk_step<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(StripSmem<256>)) != cudaSuccess ||
-      cudaFuncSetAttribute(swe_ca_bulk_step<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(StripSmem<128>)) != cudaSuccess) {
-    b2_set_error("swe_ca: cudaFuncSetAttribute(shared memory) failed");
-    return 1;
-  }
-  for (int k = 0; k < 3; ++k)
+  for (int k = 0; k < 4; ++k)
     if (cudaEventCreateWithFlags(&g_ev[k], cudaEventDisableTiming) != cudaSuccess) {
       b2_set_error("swe_ca: cudaEventCreate failed");
       return 1;
@@ -260,7 +268,7 @@ static int ca_check(B2Comm* c, const B2SweParams& p, const B2SweCA& x) {
   return 0;
 }
 
-// timeline buffer: [step][kernel 0 = A, 1 = S (bulk), 2 = X, 3 unused, 4 = D][start, end]
+// timeline buffer: [step][kernel 0 = A, 1 = B, 2 = X, 3 = Fb, 4 = D][start, end]
 static unsigned long long* g_stamps = nullptr;
 static int g_stamp_steps = 0;
 static CAStamp ca_slot(int step, int kernel) {
@@ -331,7 +339,8 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
   if (int rc = ca_check(c, p, x)) return rc;
   if (int rc = ca_streams()) return rc;
   const cudaStream_t s2 = g_side;
-  const cudaEvent_t e0 = g_ev[0], eS = g_ev[1], eD = g_ev[2];
+  const cudaEvent_t e0 = g_ev[0], eS = g_ev[1], eD = g_ev[2], eA = g_ev[3];
+  const unsigned bulk_blocks = ca_blocks(ca_bulk_tasks(p, x.cb1), SWE_THREADS);
   // ping-pong pairs; the flux arrays of the stand-alone path are free here and serve as partners of
   // the tendencies and as the frame band's u', v' store
   float* H[2] = {st->h0, st->h1};
@@ -363,18 +372,16 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
     // ---- bulk stream: needs D of the previous step (u'', v'' of the frame, the arrays' halos)
     if (it > 0) CA_RT(cudaStreamWaitEvent(s, eD, 0));
     if (rc) break;
-    StripArgs sa;
+    BulkArgs sa;
     sa.p = p; sa.cb1 = x.cb1;
-    strip_shape(sa, c->sm_count);
-    const unsigned bulk_blocks = (unsigned)(strip_nstrips(sa) * strip_nchunks(sa));
     sa.h = H[cur]; sa.u = U[cur]; sa.v = V[cur]; sa.dh = DH[cur]; sa.du = DU[cur]; sa.dv = DV[cur];
     sa.h_o = H[nxt]; sa.u_o = U[nxt]; sa.v_o = V[nxt]; sa.dh_o = DH[nxt]; sa.du_o = DU[nxt]; sa.dv_o = DV[nxt];
-    if (sa.nt == 256) swe_ca_bulk_step<256><<<bulk_blocks, 256, sizeof(StripSmem<256>), s>>>(sa, ca_slot(it, 1));
-    else swe_ca_bulk_step<128><<<bulk_blocks, 128, sizeof(StripSmem<128>), s>>>(sa, ca_slot(it, 1));
-    if ((rc = ca_done(c, "swe_ca_bulk_step"))) break;
+    // flux + tendency kernel now; its friction partner follows once kernel A has written u', v' of the
+    // band next to the bulk (enqueued below, after A's event)
+    swe_ca_bulk_k12<<<bulk_blocks, SWE_THREADS, 0, s>>>(sa, upf, vpf, ca_slot(it, 1));
+    if ((rc = ca_done(c, "swe_ca_bulk_k12"))) break;
     // ---- frame stream: needs the bulk kernel of the previous step (u'', v'', h next to the frame)
     if (it > 0) CA_RT(cudaStreamWaitEvent(s2, eS, 0));
-    CA_RT(cudaEventRecord(eS, s));
     if (rc) break;
     CACtx ctx;
     ctx.p = p; ctx.x = x;
@@ -382,8 +389,14 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
     ctx.dh = DH[cur]; ctx.du = DU[cur]; ctx.dv = DV[cur];
     ctx.hn = H[nxt]; ctx.dho = DH[nxt]; ctx.duo = DU[nxt]; ctx.dvo = DV[nxt];
     ctx.upf = upf; ctx.vpf = vpf;
-    swe_ca_tend_frame<<<tend_blocks, CA_CELLS * CA_NSLOT, 0, s2>>>(ctx, fa, ca_slot(it, 0));
+    swe_ca_tend_frame<<<tend_blocks, CA_CELLS * CA_TEND_WARPS, 0, s2>>>(ctx, fa, ca_slot(it, 0));
     if ((rc = ca_done(c, "swe_ca_tend_frame"))) break;
+    CA_RT(cudaEventRecord(eA, s2));
+    CA_RT(cudaStreamWaitEvent(s, eA, 0));
+    if (rc) break;
+    swe_ca_bulk_fric<<<bulk_blocks, SWE_THREADS, 0, s>>>(sa, upf, vpf, ca_slot(it, 3));
+    if ((rc = ca_done(c, "swe_ca_bulk_fric"))) break;
+    CA_RT(cudaEventRecord(eS, s));
     if ((rc = ca_exchange(c, *topo, p, x, H[nxt], upf, vpf, s2, ca_slot(it, 2)))) break;
     swe_ca_fric_frame<<<fric_blocks, CA_CELLS * 3, 0, s2>>>(ctx, fd, U[nxt], V[nxt], ca_slot(it, 4));
     if ((rc = ca_done(c, "swe_ca_fric_frame"))) break;

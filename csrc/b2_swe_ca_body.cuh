@@ -55,7 +55,7 @@ struct CACtx {
 __host__ __device__ inline bool swe_ca_supported(const B2SweParams& p) {
   return p.ny >= 16 && p.nx >= 24;
 }
-__host__ __device__ inline int swe_ca_cb1(const B2SweParams& p) { return p.nx - 4; }
+__host__ __device__ inline int swe_ca_cb1(const B2SweParams& p) { return ((p.nx - 4) >> 2) << 2; }   // multiple of 4 <= nx - 4
 // frame cells proper: within three of the block edge (plus the columns the bulk's alignment leaves over)
 __host__ __device__ __forceinline__ bool ca_is_frame(const B2SweParams& p, int cb1, int j, int i) {
   return j <= 3 || j >= p.ny - 4 || i <= 3 || i >= cb1;
@@ -366,6 +366,16 @@ __device__ __forceinline__ void swe_ca_fric_task(const CACtx& c, const CAFrame& 
   if (ca_needs_vpp(c.p, j, i)) { upp[1] = ca_upp_slot(c, j, i, 1); upp[2] = ca_upp_slot(c, j, i, 2); }
   if (ext) swe_ca_fric_ext_finish(c, ua_out, va_out, j, i, upp);
   else swe_ca_fric_finish(c, ua_out, va_out, j, i, upp);
+}
+
+// the two-kernel bulk (b2_swe_k12_body.cuh): rows [4, ny-5] x whole float4 groups of columns [4, cb1)
+__host__ __device__ inline long long ca_bulk_tasks(const B2SweParams& p, int cb1) {
+  return (long long)(p.ny - 8) * ((cb1 >> 2) - 1);
+}
+__host__ __device__ inline void ca_bulk_task(const B2SweParams& p, int cb1, long long idx, int& j, int& i0) {
+  const int ng = (cb1 >> 2) - 1;
+  j = 4 + (int)(idx / ng);
+  i0 = (1 + (int)(idx % ng)) << 2;
 }
 
 // ---- exchange geometry -----------------------------------------------------------------------------

@@ -1,5 +1,7 @@
-// mpi4jax_b200 -- shallow water, vectorised BULK bodies of the communication-avoiding step
-// (b2_swe_ca.cu): cells at least four away from the block edge, whole float4 groups, no halo.
+// mpi4jax_b200 -- shallow water, vectorised two-kernel BULK of the communication-avoiding step
+// (b2_swe_ca.cu, MPI4JAX_B200_SWE_BULK=k12): cells at least four away from the block edge, whole
+// float4 groups, no halo; 16 array passes.  The default bulk is the one-pass kernel of
+// b2_swe_strip.cuh (12 passes); this pair is kept as the register-only alternative.
 //
 //  * swe_k12_body   flux + tendency kernels fused.  The stand-alone step writes fe, fn, q, ke in K1
 //                   (4 array passes) only for K2 to read them back (4 more, next to h, u, v a second
@@ -36,8 +38,10 @@ __device__ __forceinline__ Row6A ld_row_a(const float* __restrict__ x, int j, in
 __device__ __forceinline__ void swe_k12_body(const B2SweParams& p, const float* __restrict__ h,
                                              float* __restrict__ h_new, const float* __restrict__ u,
                                              float* __restrict__ u_new, const float* __restrict__ v,
-                                             float* __restrict__ v_new, float* __restrict__ dh,
-                                             float* __restrict__ du, float* __restrict__ dv, int j, int i0) {
+                                             float* __restrict__ v_new, const float* __restrict__ dh,
+                                             const float* __restrict__ du, const float* __restrict__ dv,
+                                             float* __restrict__ dh_o, float* __restrict__ du_o,
+                                             float* __restrict__ dv_o, int j, int i0) {
   const int P = p.pitch;
   const size_t off = (size_t)j * P + i0;
   // index d + 1 <-> column i0 + d
@@ -93,9 +97,9 @@ __device__ __forceinline__ void swe_k12_body(const B2SweParams& p, const float* 
   st4(h_new, off, make_float4(Hn[0], Hn[1], Hn[2], Hn[3]));
   st4(u_new, off, make_float4(Un[0], Un[1], Un[2], Un[3]));
   st4(v_new, off, make_float4(Vn[0], Vn[1], Vn[2], Vn[3]));
-  st4(dh, off, make_float4(DH[0], DH[1], DH[2], DH[3]));
-  st4(du, off, make_float4(DU[0], DU[1], DU[2], DU[3]));
-  st4(dv, off, make_float4(DV[0], DV[1], DV[2], DV[3]));
+  st4(dh_o, off, make_float4(DH[0], DH[1], DH[2], DH[3]));
+  st4(du_o, off, make_float4(DU[0], DU[1], DU[2], DU[3]));
+  st4(dv_o, off, make_float4(DV[0], DV[1], DV[2], DV[3]));
 }
 
 // friction phase for one aligned group of row j, all four lanes at least three cells from the edge

@@ -36,15 +36,15 @@ run()
 torch.cuda.synchronize()
 native.lib.b2_swe_ca_timeline(None, 0)
 t = buf.cpu().double()
-names = ["A", "S", "X", "-", "D"]
+names = ["A", "B", "X", "Fb", "D"]
 if comm.Get_rank() in (0, comm.Get_size() - 1):
     print(f"rank {comm.Get_rank()} of {comm.Get_size()}: local block {model.ny_local}x{model.nx_local}", flush=True)
-    t0 = t[0, [0, 1, 2, 4], 0].min()
+    t0 = t[0, :, 0].min()
     prev_end = None
     for s in range(steps):
-        base = t[s, [0, 1, 2, 4], 0].min()
-        row = "  ".join(f"{names[k]} {(t[s, k, 0] - base) / 1e3:6.1f}-{(t[s, k, 1] - base) / 1e3:6.1f}" for k in (0, 1, 2, 4))
-        end = t[s, [0, 1, 2, 4], 1].max()
+        base = t[s, :, 0].min()
+        row = "  ".join(f"{names[k]} {(t[s, k, 0] - base) / 1e3:6.1f}-{(t[s, k, 1] - base) / 1e3:6.1f}" for k in range(5))
+        end = t[s, :, 1].max()
         print(f"step {s}: start +{(base - t0) / 1e3:7.1f} us | {row} | step {(end - base) / 1e3:6.1f} us", flush=True)
     total = (t[:, :, 1].max() - t0) / 1e3
     print(f"rank {comm.Get_rank()}: {steps} steps in {total:.1f} us = {total / steps:.1f} us/step", flush=True)

@@ -19,7 +19,7 @@ struct FakeIdx { unsigned x; };
 static FakeIdx blockIdx, threadIdx;
 
 #include "b2_swe_ca_body.cuh"
-#include "b2_swe_strip.cuh"
+#include "b2_swe_k12_body.cuh"
 
 static void masks(const B2SweParams& p, int i0, bool m[4]) {
   for (int k = 0; k < 4; ++k) m[k] = (i0 + k >= 1) && (i0 + k <= p.nx - 2);
@@ -30,32 +30,6 @@ struct EmuStep {      // the arrays of one rank for one step (B2SweState roles o
   float *h_o, *u_o, *v_o, *dh_o, *du_o, *dv_o, *upf, *vpf;
 };
 
-template <int NT>
-static void emu_bulk(const StripArgs& a, int reverse) {
-  const int nb = strip_nstrips(a) * strip_nchunks(a);
-  static StripSmem<NT> sm;
-  for (int bb = 0; bb < nb; ++bb) {
-    const int b = reverse ? nb - 1 - bb : bb;
-    const StripGeo g = strip_geo(a, b);
-    for (int k = 0; k < (int)(sizeof(sm) / sizeof(float)); ++k) ((float*)&sm)[k] = NAN;     // stale smem of another CTA
-    static StripThr thr[NT];                      // per-thread state (prefetch registers) lives across iterations
-    for (int tt = 0; tt < NT; ++tt) thr[tt] = strip_thread(a, g, tt);
-    strip_cta(a, sm, g, [&](auto&& phase) {
-      for (int tt = 0; tt < NT; ++tt) phase(thr[reverse ? NT - 1 - tt : tt]);
-    });
-  }
-}
-static StripArgs strip_args(const B2SweParams* p, const EmuStep* e, int nt, int ry) {
-  StripArgs a;
-  a.p = *p; a.cb1 = swe_ca_cb1(*p);
-  a.h = e ? e->h : nullptr; a.u = e ? e->u : nullptr; a.v = e ? e->v : nullptr;
-  a.dh = e ? e->dh : nullptr; a.du = e ? e->du : nullptr; a.dv = e ? e->dv : nullptr;
-  a.h_o = e ? e->h_o : nullptr; a.u_o = e ? e->u_o : nullptr; a.v_o = e ? e->v_o : nullptr;
-  a.dh_o = e ? e->dh_o : nullptr; a.du_o = e ? e->du_o : nullptr; a.dv_o = e ? e->dv_o : nullptr;
-  if (nt > 0) { a.nt = nt; a.ry = ry; }
-  else strip_shape(a, 148);
-  return a;
-}
 extern "C" {
 
 // K1 on every interior row / group (what swe_k1_fluxes does)
@@ -137,19 +111,27 @@ void emu_ca_fric_frame(const B2SweParams* p, const B2SweCA* x, const EmuStep* e,
 
 // swe_ca_bulk_step: CTAs one after the other, every phase as a loop over the CTA's threads
 // (`reverse`: CTAs and threads backwards -- a phase only reads what earlier phases wrote)
-void emu_ca_bulk_step(const B2SweParams* p, const EmuStep* e, int reverse, int nt, int ry) {
-  const StripArgs a = strip_args(p, e, nt, ry);
-  if (a.nt == 256) emu_bulk<256>(a, reverse);
-  else emu_bulk<128>(a, reverse);
+// swe_ca_bulk_k12 + swe_ca_bulk_fric (the friction kernel runs after kernel A: it reads the band's u', v')
+void emu_ca_bulk_k12(const B2SweParams* p, const EmuStep* e) {
+  const int cb1 = swe_ca_cb1(*p);
+  for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
+    int j, i0;
+    ca_bulk_task(*p, cb1, t, j, i0);
+    swe_k12_body(*p, e->h, e->h_o, e->u, e->upf, e->v, e->vpf, e->dh, e->du, e->dv, e->dh_o, e->du_o, e->dv_o, j, i0);
+  }
 }
-void emu_strip_shape(const B2SweParams* p, int* nt, int* ry, int* nctas) {
-  const StripArgs a = strip_args(p, nullptr, 0, 0);
-  *nt = a.nt; *ry = a.ry; *nctas = strip_nstrips(a) * strip_nchunks(a);
+void emu_ca_bulk_fric(const B2SweParams* p, const EmuStep* e) {
+  const int cb1 = swe_ca_cb1(*p);
+  for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
+    int j, i0;
+    ca_bulk_task(*p, cb1, t, j, i0);
+    swe_k345_body(*p, e->upf, e->u_o, e->vpf, e->v_o, j, i0);
+  }
 }
 
 // which interior cells do the bulk kernel and the frame kernels WRITE?  marks[j * nx + i]: +1 frame
 // (kernel D's cells = kernel A's full updates), +16 bulk, +256 kernel A's u' / v' band
-void emu_ca_marks(const B2SweParams* p, int* marks, int nt, int ry) {
+void emu_ca_marks(const B2SweParams* p, int* marks) {
   const int cb1 = swe_ca_cb1(*p);
   const CAFrame fd = ca_frame(*p, 3, cb1), fa = ca_frame(*p, 5, cb1 - 2);
   int j, i;
@@ -157,13 +139,10 @@ void emu_ca_marks(const B2SweParams* p, int* marks, int nt, int ry) {
     if (ca_frame_cell(*p, fd, t, j, i)) marks[j * p->nx + i] += 1;
   for (long long t = 0; t < fa.total; ++t)
     if (ca_frame_cell(*p, fa, t, j, i)) marks[j * p->nx + i] += 256;
-  const StripArgs a = strip_args(p, nullptr, nt, ry);
-  const int nb = strip_nstrips(a) * strip_nchunks(a);
-  for (int b = 0; b < nb; ++b) {
-    const StripGeo g = strip_geo(a, b);
-    for (int jj = g.j0; jj < g.j1; ++jj)
-      for (int tid = 4; tid <= a.nt - 4; ++tid)
-        if (g.i0 - 4 + tid < cb1) marks[jj * p->nx + g.i0 - 4 + tid] += 16;
+  for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
+    int i0;
+    ca_bulk_task(*p, cb1, t, j, i0);
+    for (int k = 0; k < 4; ++k) marks[j * p->nx + i0 + k] += 16;
   }
 }
 

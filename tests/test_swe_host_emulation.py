@@ -227,10 +227,10 @@ class EmuStep(ctypes.Structure):      # EmuStep (tests/native/swe_host_emu.cpp):
                                                 "dv_o", "upf", "vpf")]
 
 
-def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0, nt=0, ry=0):
-    """The launch sequence of b2_swe_multistep_ca on a process grid: per step the bulk kernel (whole
-    step, one pass), frame kernel A, the deep exchange, frame kernel D; every prognostic array is a
-    ping-pong pair.  (Messages are read before any rank scatters: all sends of a step come from h',
+def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0):
+    """The launch sequence of b2_swe_multistep_ca on a process grid: per step the bulk flux+tendency
+    kernel, frame kernel A, the bulk friction kernel, the deep exchange, frame kernel D; every
+    prognostic array is a ping-pong pair.  (Messages are read before any rank scatters: all sends of a step come from h',
     u', v' frame cells, which no message writes.)"""
     from ._halo_sim import new_exchange
 
@@ -260,8 +260,9 @@ def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0, nt=0, ry=0):
                       **{k + "_o": r[pairs[k][nxt]].ctypes.data for k in pairs},
                       upf=r["upf"].ctypes.data, vpf=r["vpf"].ctypes.data) for r in ranks]
         for p, x, e in zip(ps, xs, es):
-            emu.emu_ca_bulk_step(B(p), B(e), reverse, nt, ry)
+            emu.emu_ca_bulk_k12(B(p), B(e))
             emu.emu_ca_tend_frame(B(p), B(x), B(e), reverse)
+            emu.emu_ca_bulk_fric(B(p), B(e))
         _ca_exchange(emu, ranks, (pairs["h"][nxt], "upf", "vpf"), ny, nx, pitch, epitch, PY, PX)
         for p, x, e in zip(ps, xs, es):
             emu.emu_ca_fric_frame(B(p), B(x), B(e), reverse)
@@ -269,23 +270,23 @@ def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0, nt=0, ry=0):
     return [{k: r[pairs[k][cur]][:, :nx] for k in pairs} for r in ranks]
 
 
-@pytest.mark.parametrize("shape_cta", [(0, 0), (256, 128), (128, 16), (128, 8), (256, 32)], ids=str)
 @pytest.mark.parametrize("shape", [(16, 24), (26, 50), (17, 29), (140, 33), (31, 300), (200, 530)])
-def test_ca_bulk_and_frame_partition_the_interior(emu, shape, shape_cta):
+def test_ca_bulk_and_frame_partition_the_interior(emu, shape):
     ny, nx = shape
     p, *_ = _setup(ny, nx, False, 0, 0)
     assert emu.emu_ca_supported(ctypes.byref(p)) == 1
     marks = np.zeros((ny, nx), np.int32)
-    emu.emu_ca_marks(ctypes.byref(p), marks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), *shape_cta)
+    emu.emu_ca_marks(ctypes.byref(p), marks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
     owner = marks & 0xff                     # 1 = frame kernels, 16 = bulk kernel (several CTAs)
     assert set(np.unique(owner[1:-1, 1:-1])) <= {1, 16}          # every interior cell written exactly once
     assert marks[0].sum() == marks[-1].sum() == marks[:, 0].sum() == marks[:, -1].sum() == 0
+    cb1 = (nx - 4) // 4 * 4                  # east frame: 3 .. 6 columns (the bulk ends on a float4 boundary)
     jj, ii = np.nonzero(owner == 16)
-    assert jj.min() == 4 and jj.max() == ny - 5 and ii.min() == 4 and ii.max() == nx - 5     # exactly 3 frame cells
+    assert jj.min() == 4 and jj.max() == ny - 5 and ii.min() == 4 and ii.max() == cb1 - 1
     band = (marks & 256) != 0                # kernel A also computes u', v' two cells into the bulk
     want = np.zeros_like(band)
     want[1:-1, 1:-1] = True
-    want[6:ny - 6, 6:nx - 6] = False
+    want[6:ny - 6, 6:cb1 - 2] = False
     assert np.array_equal(band, want)
 
 
@@ -309,29 +310,3 @@ def test_emulated_ca_pipeline_is_bit_identical_to_the_standalone_pipeline(emu, g
             # the main arrays' halos as well (h fresh; u, v stale by the friction step)
             if name in ("h", "u", "v"):
                 assert np.array_equal(ra[name], rb[name]), (grid, name, "halo")
-
-
-def test_emulated_ca_pipeline_with_several_strips_and_chunks(emu):
-    """A block larger than one CTA of the bulk kernel in both directions (3 column strips of 249, 3 row
-    chunks of 128): the strip / chunk seams and the ring warm-up rows, still bit for bit."""
-    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
-
-    model = ShallowWaterModel(ShallowWaterConfig(nx=530, ny=300), device="cpu", backend="ops")
-    a = _emulate(emu, model, 1, 1, 3)
-    for nt, ry, rev in ((256, 128, 0), (256, 128, 1), (128, 16, 0), (128, 8, 1), (256, 64, 0), (0, 0, 0)):
-        b = _emulate_ca(emu, model, 1, 1, 3, reverse=rev, nt=nt, ry=ry)
-        for name in a[0]:
-            assert np.array_equal(a[0][name][1:-1, 1:-1], b[0][name][1:-1, 1:-1]), (name, nt, ry, rev)
-
-
-def test_strip_shape_fills_the_gpu(emu):
-    """CTA shape heuristics: long wide CTAs on a 4096^2 block, enough CTAs for 148 SMs on an 8-GPU block."""
-    got = {}
-    for ny, nx in ((4098, 4098), (2050, 1026), (2050, 2050), (66, 130)):
-        p, *_ = _setup(ny, nx, False, 0, 0)
-        nt, ry, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-        emu.emu_strip_shape(ctypes.byref(p), ctypes.byref(nt), ctypes.byref(ry), ctypes.byref(n))
-        got[(ny, nx)] = (nt.value, ry.value, n.value)
-    assert got[(4098, 4098)][0] == 256 and got[(4098, 4098)][2] >= 444
-    assert got[(2050, 1026)][2] >= 300, got
-    assert got[(2050, 2050)][2] >= 400, got
