@@ -52,15 +52,23 @@ __device__ __forceinline__ void ca_stamp_end(const CAStamp& s) {
 // warp --, the values meet in shared memory, warp 0 finishes the cells.
 #define CA_CELLS 32
 #define CA_TEND_WARPS 4          // one warp per flux KIND (fe, fn, q, ke): slots 0-3, 4-7, 8-10, 11-13
-__global__ void __launch_bounds__(CA_CELLS * CA_TEND_WARPS) swe_ca_tend_frame(const CACtx c, const CAFrame f, const CAStamp ts) {
+__global__ void __launch_bounds__(CA_CELLS * CA_TEND_WARPS)
+swe_ca_tend_frame(const __grid_constant__ CACtx c, const CAFrame f, const CAStamp ts) {
   ca_stamp_begin(ts);
   __shared__ float fl[CA_NSLOT][CA_CELLS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int j, i;
-  const bool ok = ca_frame_cell(c.p, f, (long long)blockIdx.x * CA_CELLS + lane, j, i);
+  const bool ok = ca_frame_cell(c.p, f, (int)blockIdx.x * CA_CELLS + lane, j, i);
   if (ok) {
-    const int s0 = w == 0 ? 0 : w == 1 ? 4 : w == 2 ? 8 : 11, s1 = w == 0 ? 4 : w == 1 ? 8 : w == 2 ? 11 : 14;
-    for (int s = s0; s < s1; ++s) fl[s][lane] = ca_flux_slot(c, j, i, s);
+    float r[4];
+    if (w == 0) ca_flux_kind<0>(c, j, i, r);
+    else if (w == 1) ca_flux_kind<1>(c, j, i, r);
+    else if (w == 2) ca_flux_kind<2>(c, j, i, r);
+    else ca_flux_kind<3>(c, j, i, r);
+    const int s0 = ca_slot_base(w), n = ca_slot_count(w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < n) fl[s0 + k][lane] = r[k];
   }
   __syncthreads();
   if (ok && w == 0) {

@@ -37,6 +37,11 @@
 
 #include "b2_swe_body.cuh"
 
+#ifndef __CUDACC__
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))      // host emulation build (tests/native/swe_host_emu.cpp)
+#endif
+#endif
 #define CA_L 3        // halo layers exchanged per step (layer 1 = the main arrays' halo cell)
 #define CA_NF 3       // fields per exchange: h', u', v'
 
@@ -143,12 +148,24 @@ __device__ __forceinline__ float ca_ke(const CACtx& c, int j0, int i) {
 // Frame cells get everything; the two cells beyond them (distance 4, 5: bulk cells, whose h', dh ..
 // the bulk kernel writes) only need their u', v' here, because kernel D's friction stencil on the
 // frame reaches that far and must not wait for the bulk kernel.
-// The 14 flux values of a cell's tendency stencil, as (kind, dj, di); a warp of kernel A evaluates ONE
-// slot for 32 cells, so the cell's latency is one flux evaluation, not fourteen in a row.
+// The 14 flux values of a cell's tendency stencil, as (kind, dj, di); a warp of kernel A evaluates the
+// slots of ONE kind for 32 cells, so the cell's latency is a few flux evaluations, not fourteen in a row.
 #define CA_NSLOT 14
-// a flux cell at least one cell inside the block on every side: all operands are this rank's own
-// fresh values in the main arrays -- no views, no ext arrays (4/5 of kernel A's cells only ever
-// evaluate such fluxes; the generic accessors cost ~10x the arithmetic they feed)
+__host__ __device__ __forceinline__ int ca_slot_base(int kind) { return kind == 0 ? 0 : kind == 1 ? 4 : kind == 2 ? 8 : 11; }
+__host__ __device__ __forceinline__ int ca_slot_count(int kind) { return kind < 2 ? 4 : 3; }
+// offset of slot k of `kind` from the cell: fe (0,0) (0,-1) (1,0) (1,-1); fn (0,0) (0,1) (-1,0) (-1,1);
+// q (0,0) (0,-1) (-1,0); ke (0,0) (0,1) (1,0)
+__host__ __device__ __forceinline__ int ca_slot_dj(int kind, int k) {
+  return kind == 0 ? (k >> 1) : kind == 1 ? -(k >> 1) : kind == 2 ? -(k >> 1) : (k >> 1);
+}
+__host__ __device__ __forceinline__ int ca_slot_di(int kind, int k) {
+  return kind == 0 ? -(k & 1) : kind == 1 ? (k & 1) : kind == 2 ? -(k & 1) : (k & 1);
+}
+// A flux at one of THIS rank's cells is what the stand-alone flux kernel computes there: every operand
+// comes from the main arrays, whose halo holds exactly the stale value the view rule asks for (kernel D
+// and the exchange keep it so).  Only the fluxes at the cells beyond the edge -- which the reference
+// receives by halo exchange -- need the owner's view, i.e. the ext arrays (generic path below); they
+// enter the stencils of the outermost ring of cells only.
 __device__ __forceinline__ float ca_flux_plain(const CACtx& c, int j, int i, int kind) {
   const B2SweParams& p = c.p;
   const size_t o = ca_m(p, j, i), oh = ca_m(p, hc_row(p, j), i), ohn = ca_m(p, hc_row(p, j + 1), i);
@@ -161,41 +178,40 @@ __device__ __forceinline__ float ca_flux_plain(const CACtx& c, int j, int i, int
     default: return swe_ke(c.ua[o], c.ua[o - 1], c.va[o], c.va[o - P]);
   }
 }
-__device__ __forceinline__ float ca_flux_slot(const CACtx& c, int j, int i, int slot) {
-  if (j >= 3 && j <= c.p.ny - 4 && i >= 3 && i <= c.p.nx - 4) {        // every flux of the stencil is plain
-    switch (slot) {
-      case 0: return ca_flux_plain(c, j, i, 0);
-      case 1: return ca_flux_plain(c, j, i - 1, 0);
-      case 2: return ca_flux_plain(c, j + 1, i, 0);
-      case 3: return ca_flux_plain(c, j + 1, i - 1, 0);
-      case 4: return ca_flux_plain(c, j, i, 1);
-      case 5: return ca_flux_plain(c, j, i + 1, 1);
-      case 6: return ca_flux_plain(c, j - 1, i, 1);
-      case 7: return ca_flux_plain(c, j - 1, i + 1, 1);
-      case 8: return ca_flux_plain(c, j, i, 2);
-      case 9: return ca_flux_plain(c, j, i - 1, 2);
-      case 10: return ca_flux_plain(c, j - 1, i, 2);
-      case 11: return ca_flux_plain(c, j, i, 3);
-      case 12: return ca_flux_plain(c, j, i + 1, 3);
-      default: return ca_flux_plain(c, j + 1, i, 3);
-    }
-  }
-  switch (slot) {
+// the rare path is a real call: inlined, its ~250 instructions per flux would sit in every one of the
+// fourteen slots and the kernel would spend its time fetching instructions (measured: 4096 SASS
+// instructions, "no instruction" the top stall)
+static __device__ __noinline__ float ca_flux_generic(const CACtx& c, int j, int i, int kind) {
+  switch (kind) {
     case 0: return ca_fe(c, j, i);
-    case 1: return ca_fe(c, j, i - 1);
-    case 2: return ca_fe(c, j + 1, i);
-    case 3: return ca_fe(c, j + 1, i - 1);
-    case 4: return ca_fn(c, j, i);
-    case 5: return ca_fn(c, j, i + 1);
-    case 6: return ca_fn(c, j - 1, i);
-    case 7: return ca_fn(c, j - 1, i + 1);
-    case 8: return ca_q(c, j, i);
-    case 9: return ca_q(c, j, i - 1);
-    case 10: return ca_q(c, j - 1, i);
-    case 11: return ca_ke(c, j, i);
-    case 12: return ca_ke(c, j, i + 1);
-    default: return ca_ke(c, j + 1, i);
+    case 1: return ca_fn(c, j, i);
+    case 2: return ca_q(c, j, i);
+    default: return ca_ke(c, j, i);
   }
+}
+// all slots of one kind: the plain evaluations first, branch-free (a flux cell beyond the edge is
+// evaluated at the clamped cell and replaced afterwards), so every load of the warp is in flight at once
+template <int KIND>
+__device__ __forceinline__ void ca_flux_kind(const CACtx& c, int j, int i, float* r) {
+  constexpr int n = KIND < 2 ? 4 : 3;
+  const int ny = c.p.ny, nx = c.p.nx;
+#pragma unroll
+  for (int k = 0; k < n; ++k) {
+    const int fj = j + ca_slot_dj(KIND, k), fi = i + ca_slot_di(KIND, k);
+    const int cj = fj < 1 ? 1 : (fj > ny - 2 ? ny - 2 : fj), ci = fi < 1 ? 1 : (fi > nx - 2 ? nx - 2 : fi);
+    r[k] = ca_flux_plain(c, cj, ci, KIND);
+  }
+#pragma unroll
+  for (int k = 0; k < n; ++k) {
+    const int fj = j + ca_slot_dj(KIND, k), fi = i + ca_slot_di(KIND, k);
+    if (!ca_mine(c.p, fj, fi)) r[k] = ca_flux_generic(c, fj, fi, KIND);
+  }
+}
+__device__ __forceinline__ void ca_flux_all(const CACtx& c, int j, int i, float* fl) {
+  ca_flux_kind<0>(c, j, i, fl);
+  ca_flux_kind<1>(c, j, i, fl + 4);
+  ca_flux_kind<2>(c, j, i, fl + 8);
+  ca_flux_kind<3>(c, j, i, fl + 11);
 }
 __device__ __forceinline__ void swe_ca_tend_finish(const CACtx& c, int j, int i, const float* fl) {
   const B2SweParams& p = c.p;
@@ -220,7 +236,7 @@ __device__ __forceinline__ void swe_ca_tend_finish(const CACtx& c, int j, int i,
 }
 __device__ __forceinline__ void swe_ca_tend_cell(const CACtx& c, int j, int i) {
   float fl[CA_NSLOT];
-  for (int s = 0; s < CA_NSLOT; ++s) fl[s] = ca_flux_slot(c, j, i, s);
+  ca_flux_all(c, j, i, fl);
   swe_ca_tend_finish(c, j, i, fl);
 }
 
@@ -303,29 +319,33 @@ struct CAFrame {
   int w, ce;
   int nfull;          // cells in the 2w full rows
   int per;            // band cells per middle row
-  long long total;
+  int nrows;          // middle rows
+  int total;
 };
 __host__ __device__ inline CAFrame ca_frame(const B2SweParams& p, int w, int ce) {
   CAFrame f;
   f.w = w; f.ce = ce;
   f.nfull = 2 * w * (p.nx - 2);
   f.per = w + (p.nx - 1 - ce);
-  f.total = (long long)f.nfull + (long long)(p.ny - 2 - 2 * w) * f.per;
+  f.nrows = p.ny - 2 - 2 * w;
+  f.total = f.nfull + f.nrows * f.per;
   return f;
 }
-__host__ __device__ inline bool ca_frame_cell(const B2SweParams& p, const CAFrame& f, long long idx, int& j, int& i) {
+// (32-bit arithmetic throughout: the frame of a block that fits a GPU is a few hundred thousand cells,
+// and a 64-bit division costs more than the flux it indexes)
+__host__ __device__ inline bool ca_frame_cell(const B2SweParams& p, const CAFrame& f, int idx, int& j, int& i) {
   if (idx >= f.total) return false;
   if (idx < f.nfull) {
-    const int r = (int)(idx / (p.nx - 2));
-    i = 1 + (int)(idx % (p.nx - 2));
+    const int n = p.nx - 2;
+    const int r = idx / n;
+    i = 1 + (idx - r * n);
     j = r < f.w ? 1 + r : (p.ny - 1 - f.w) + (r - f.w);
   } else {
     // side bands column by column (a warp's 32 cells then share their distance from the edge, i.e.
     // take the same path through the accessors)
-    const long long t = idx - f.nfull;
-    const int nrows = p.ny - 2 - 2 * f.w;
-    const int s = (int)(t / nrows);
-    j = f.w + 1 + (int)(t % nrows);
+    const int t = idx - f.nfull;
+    const int s = t / f.nrows;
+    j = f.w + 1 + (t - s * f.nrows);
     i = s < f.w ? 1 + s : f.ce + (s - f.w);
   }
   return true;
@@ -354,7 +374,7 @@ __host__ __device__ inline bool ca_ext_cell(const B2SweParams& p, long long idx,
 __device__ __forceinline__ bool ca_fric_task(const B2SweParams& p, const CAFrame& f, long long t, int& j, int& i,
                                              bool& ext) {
   ext = t >= f.total;
-  if (!ext) return ca_frame_cell(p, f, t, j, i);
+  if (!ext) return ca_frame_cell(p, f, (int)t, j, i);
   return ca_ext_cell(p, t - f.total, j, i);
 }
 __device__ __forceinline__ void swe_ca_fric_task(const CACtx& c, const CAFrame& f, float* __restrict__ ua_out,

@@ -98,7 +98,7 @@ void emu_ca_tend_frame(const B2SweParams* p, const B2SweCA* x, const EmuStep* e,
   const CAFrame f = ca_frame(c.p, 5, c.x.cb1 - 2);
   for (long long k = 0; k < f.total; ++k) {
     int j, i;
-    if (ca_frame_cell(c.p, f, reverse ? f.total - 1 - k : k, j, i)) swe_ca_tend_cell(c, j, i);
+    if (ca_frame_cell(c.p, f, (int)(reverse ? f.total - 1 - k : k), j, i)) swe_ca_tend_cell(c, j, i);
   }
 }
 
@@ -136,9 +136,9 @@ void emu_ca_marks(const B2SweParams* p, int* marks) {
   const CAFrame fd = ca_frame(*p, 3, cb1), fa = ca_frame(*p, 5, cb1 - 2);
   int j, i;
   for (long long t = 0; t < fd.total; ++t)
-    if (ca_frame_cell(*p, fd, t, j, i)) marks[j * p->nx + i] += 1;
+    if (ca_frame_cell(*p, fd, (int)t, j, i)) marks[j * p->nx + i] += 1;
   for (long long t = 0; t < fa.total; ++t)
-    if (ca_frame_cell(*p, fa, t, j, i)) marks[j * p->nx + i] += 256;
+    if (ca_frame_cell(*p, fa, (int)t, j, i)) marks[j * p->nx + i] += 256;
   for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
     int i0;
     ca_bulk_task(*p, cb1, t, j, i0);
