@@ -7,10 +7,12 @@
 //                                                    ^ (u', v' of the band next to the bulk) |
 //   stream s2 (frame):  A (tendencies, frame band) -> X (deep halo exchange) -> D (friction, frame + ext)
 //
-// B / Fb read only the step's input arrays (plus A's band for Fb) and write only bulk cells of the
-// output arrays (every prognostic array is a ping-pong pair), A / X / D own the frame: ONE edge
-// between the two streams inside a step (A -> Fb), two at the step boundary (B(t+1) reads what D(t)
-// wrote next to the bulk, A(t+1) what Fb(t) wrote next to the frame).  The NVLink round of X is
+// B / Fb write only bulk cells, A / X / D own the frame: ONE edge between the two streams inside a
+// step (A -> Fb), two at the step boundary (B(t+1) reads what D(t) wrote next to the bulk, A(t+1) what
+// Fb(t) wrote next to the frame).  Only h is double-buffered (its stencil is read while h' is written);
+// u', v' travel through their own arrays between the tendency and the friction kernels, so u'', v''
+// and the tendencies are updated in place: nine arrays are live per step -- at 8 GPUs (2 M cells per
+// rank) 75 MB, which stays in the 126 MB L2.  The NVLink round of X is
 // hidden behind the bulk kernels.  Under CUDA-graph capture (mpi4jax_b200.jit) the event fork /
 // join becomes graph edges.  16 array passes per step instead of 32, one exchange instead of three.
 #include <cstdio>
@@ -129,13 +131,14 @@ __global__ void __launch_bounds__(CA_THREADS) swe_ca_init_ext(const B2SweParams 
 }
 
 // ---- bulk kernels: flux + tendency, then friction, on whole float4 groups at least four cells from the
-// block edge (b2_swe_k12_body.cuh); every prognostic array is a ping-pong pair; u', v' of the bulk
-// travel through the frame band's store (upf / vpf), whose bulk cells are otherwise unused --------------
+// block edge (b2_swe_k12_body.cuh); u', v' of the bulk travel through the frame band's store
+// (upf / vpf), whose bulk cells are otherwise unused --------------
 struct BulkArgs {
   B2SweParams p;
   int cb1;                                           // bulk columns [4, cb1), bulk rows [4, ny - 4)
-  const float *h, *u, *v, *dh, *du, *dv;             // step inputs
-  float *h_o, *u_o, *v_o, *dh_o, *du_o, *dv_o;       // step outputs (ping-pong partners)
+  const float *h;                                    // h of this step
+  float *h_o;                                        // h' (the other buffer of the pair)
+  float *u, *v, *dh, *du, *dv;                       // read, then updated in place
 };
 __global__ void __launch_bounds__(SWE_THREADS, 3)
 swe_ca_bulk_k12(const BulkArgs a, float* __restrict__ up, float* __restrict__ vp, const CAStamp ts) {
@@ -144,7 +147,7 @@ swe_ca_bulk_k12(const BulkArgs a, float* __restrict__ up, float* __restrict__ vp
   if (t < ca_bulk_tasks(a.p, a.cb1)) {
     int j, i0;
     ca_bulk_task(a.p, a.cb1, t, j, i0);
-    swe_k12_body(a.p, a.h, a.h_o, a.u, up, a.v, vp, a.dh, a.du, a.dv, a.dh_o, a.du_o, a.dv_o, j, i0);
+    swe_k12_body(a.p, a.h, a.h_o, a.u, up, a.v, vp, a.dh, a.du, a.dv, a.dh, a.du, a.dv, j, i0);
   }
   ca_stamp_end(ts);
 }
@@ -155,7 +158,7 @@ swe_ca_bulk_fric(const BulkArgs a, const float* __restrict__ up, const float* __
   if (t < ca_bulk_tasks(a.p, a.cb1)) {
     int j, i0;
     ca_bulk_task(a.p, a.cb1, t, j, i0);
-    swe_k345_body(a.p, up, a.u_o, vp, a.v_o, j, i0);
+    swe_k345_body(a.p, up, a.u, vp, a.v, j, i0);
   }
   ca_stamp_end(ts);
 }
@@ -331,6 +334,13 @@ int b2_swe_ca_init(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const
   if (int rc = ca_check(c, p, x)) return rc;
   if (int rc = ca_streams()) return rc;       // (here, never inside a stream capture: reset / load_state are eager)
   if (int rc = ca_exchange(c, *topo, p, x, st->h0, st->u, st->v, s)) return rc;
+  // kernel A's private du, dv of the band-only cells (CACtx::dub / dvb) start as copies
+  const size_t bytes = (size_t)p.ny * p.pitch * sizeof(float);
+  if (cudaMemcpyAsync(st->ke, st->du, bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+      cudaMemcpyAsync(st->fe2, st->dv, bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+    b2_set_error("swe_ca_init: cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1000;
+  }
   const long long tasks = ca_ext_total(p) + 2LL * (p.nx - 2) + 2LL * (p.ny - 2);
   swe_ca_init_ext<<<ca_blocks(tasks, CA_THREADS), CA_THREADS, 0, s>>>(p, x, st->u, st->v);
   return ca_done(c, "swe_ca_init_ext");
@@ -339,7 +349,7 @@ int b2_swe_ca_init(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const
 int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, const B2SweCA* x0,
                         const B2HaloDesc* topo, int nsteps, int first_step, cudaStream_t s) {
   // blocks too small for the bulk / frame split, or no friction step: the stand-alone kernels
-  if (!swe_ca_supported(*p0) || !(p0->viscosity > 0.f) || !st->u1 || !st->v1)
+  if (!swe_ca_supported(*p0) || !(p0->viscosity > 0.f))
     return b2_swe_multistep(c, p0, st, topo, nsteps, first_step, s);
   B2SweParams p = *p0;
   B2SweCA x = *x0;
@@ -349,14 +359,9 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
   const cudaStream_t s2 = g_side;
   const cudaEvent_t e0 = g_ev[0], eS = g_ev[1], eD = g_ev[2], eA = g_ev[3];
   const unsigned bulk_blocks = ca_blocks(ca_bulk_tasks(p, x.cb1), SWE_THREADS);
-  // ping-pong pairs; the flux arrays of the stand-alone path are free here and serve as partners of
-  // the tendencies and as the frame band's u', v' store
+  // the flux arrays of the stand-alone path are free here: fe / fn hold u', v' between the tendency and
+  // the friction kernels, ke / fe2 kernel A's copy of du, dv on the band-only cells
   float* H[2] = {st->h0, st->h1};
-  float* U[2] = {st->u, st->u1};
-  float* V[2] = {st->v, st->v1};
-  float* DH[2] = {st->dh, st->q};
-  float* DU[2] = {st->du, st->ke};
-  float* DV[2] = {st->dv, st->fe2};
   float* const upf = st->fe;
   float* const vpf = st->fn;
   const CAFrame fa = ca_frame(p, 5, x.cb1 - 2), fd = ca_frame(p, 3, x.cb1);
@@ -382,8 +387,8 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
     if (rc) break;
     BulkArgs sa;
     sa.p = p; sa.cb1 = x.cb1;
-    sa.h = H[cur]; sa.u = U[cur]; sa.v = V[cur]; sa.dh = DH[cur]; sa.du = DU[cur]; sa.dv = DV[cur];
-    sa.h_o = H[nxt]; sa.u_o = U[nxt]; sa.v_o = V[nxt]; sa.dh_o = DH[nxt]; sa.du_o = DU[nxt]; sa.dv_o = DV[nxt];
+    sa.h = H[cur]; sa.h_o = H[nxt];
+    sa.u = st->u; sa.v = st->v; sa.dh = st->dh; sa.du = st->du; sa.dv = st->dv;
     // flux + tendency kernel now; its friction partner follows once kernel A has written u', v' of the
     // band next to the bulk (enqueued below, after A's event)
     swe_ca_bulk_k12<<<bulk_blocks, SWE_THREADS, 0, s>>>(sa, upf, vpf, ca_slot(it, 1));
@@ -393,9 +398,10 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
     if (rc) break;
     CACtx ctx;
     ctx.p = p; ctx.x = x;
-    ctx.h = H[cur]; ctx.ua = U[cur]; ctx.va = V[cur];
-    ctx.dh = DH[cur]; ctx.du = DU[cur]; ctx.dv = DV[cur];
-    ctx.hn = H[nxt]; ctx.dho = DH[nxt]; ctx.duo = DU[nxt]; ctx.dvo = DV[nxt];
+    ctx.h = H[cur]; ctx.hn = H[nxt];
+    ctx.ua = st->u; ctx.va = st->v;
+    ctx.dh = st->dh; ctx.du = st->du; ctx.dv = st->dv;
+    ctx.dub = st->ke; ctx.dvb = st->fe2;
     ctx.upf = upf; ctx.vpf = vpf;
     swe_ca_tend_frame<<<tend_blocks, CA_CELLS * CA_TEND_WARPS, 0, s2>>>(ctx, fa, ca_slot(it, 0));
     if ((rc = ca_done(c, "swe_ca_tend_frame"))) break;
@@ -406,18 +412,14 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
     if ((rc = ca_done(c, "swe_ca_bulk_fric"))) break;
     CA_RT(cudaEventRecord(eS, s));
     if ((rc = ca_exchange(c, *topo, p, x, H[nxt], upf, vpf, s2, ca_slot(it, 2)))) break;
-    swe_ca_fric_frame<<<fric_blocks, CA_CELLS * 3, 0, s2>>>(ctx, fd, U[nxt], V[nxt], ca_slot(it, 4));
+    swe_ca_fric_frame<<<fric_blocks, CA_CELLS * 3, 0, s2>>>(ctx, fd, st->u, st->v, ca_slot(it, 4));
     if ((rc = ca_done(c, "swe_ca_fric_frame"))) break;
     CA_RT(cudaEventRecord(eD, s2));
     cur = nxt;
   }
   CA_RT(cudaStreamWaitEvent(s, eD, 0));           // join (also required to end a stream capture)
-  if (rc == 0 && cur != 0) {
-    // odd step count: the state goes back to its home buffers
-    const size_t bytes = (size_t)p.ny * p.pitch * sizeof(float);
-    float* const* pairs[6] = {H, U, V, DH, DU, DV};
-    for (int k = 0; k < 6; ++k) CA_RT(cudaMemcpyAsync(pairs[k][0], pairs[k][1], bytes, cudaMemcpyDeviceToDevice, s));
-  }
+  if (rc == 0 && cur != 0)       // odd step count: h goes back to its home buffer
+    CA_RT(cudaMemcpyAsync(H[0], H[1], (size_t)p.ny * p.pitch * sizeof(float), cudaMemcpyDeviceToDevice, s));
 #undef CA_RT
   return rc;
 }

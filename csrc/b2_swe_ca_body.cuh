@@ -50,10 +50,12 @@ struct CACtx {
   B2SweParams p;
   B2SweCA x;
   const float *h;                 // h of this step (halo fresh)
-  const float *ua, *va;           // u'', v'' of the previous step (interior; wall rows constant)
-  const float *dh, *du, *dv;      // tendencies of the previous step
-  float *hn;                      // h' (ping-pong partner of h)
-  float *dho, *duo, *dvo;         // new tendencies (ping-pong partners)
+  float *hn;                      // h' (ping-pong partner of h: the only array that needs one)
+  float *ua, *va;                 // u'', v'' of the previous step (interior; wall rows constant); kernel D
+                                  // overwrites the frame cells in place
+  float *dh, *du, *dv;            // tendencies: read (previous step) and written (this step) cell by cell
+  float *dub, *dvb;               // du, dv of the band-only cells (distance 4, 5), kernel A's private copy:
+                                  // the bulk kernel updates du, dv of those cells in place at the same time
   float *upf, *vpf;               // u', v' of the frame band (cells within 5 of the edge) and, after X, their halo
 };
 
@@ -223,15 +225,18 @@ __device__ __forceinline__ void swe_ca_tend_finish(const CACtx& c, int j, int i,
   in.ke_c = fl[11]; in.ke_e = fl[12]; in.ken_c = fl[13];
   in.h_c = c.h[off]; in.h_e = ca_h(c, j, i + 1); in.h_n = ca_h(c, j + 1, i);
   in.u_o = c.ua[off]; in.v_o = c.va[off];
-  in.dh_o = p.first_step ? 0.f : c.dh[off];
-  in.du_o = p.first_step ? 0.f : c.du[off];
-  in.dv_o = p.first_step ? 0.f : c.dv[off];
+  const bool frame = ca_is_frame(p, c.x.cb1, j, i);
+  in.dh_o = (p.first_step || !frame) ? 0.f : c.dh[off];
+  in.du_o = p.first_step ? 0.f : (frame ? c.du[off] : c.dub[off]);
+  in.dv_o = p.first_step ? 0.f : (frame ? c.dv[off] : c.dvb[off]);
   SweK2Out o = swe_k2_cell(p, in);
   if (p.north_wall && j == p.ny - 2) o.v = 0.f;       // "v" wall rule, after the update
   c.upf[off] = o.u; c.vpf[off] = o.v;
-  if (ca_is_frame(p, c.x.cb1, j, i)) {
+  if (frame) {
     c.hn[off] = o.h;
-    c.dho[off] = o.dh; c.duo[off] = o.du; c.dvo[off] = o.dv;
+    c.dh[off] = o.dh; c.du[off] = o.du; c.dv[off] = o.dv;
+  } else {
+    c.dub[off] = o.du; c.dvb[off] = o.dv;
   }
 }
 __device__ __forceinline__ void swe_ca_tend_cell(const CACtx& c, int j, int i) {

@@ -38,10 +38,9 @@ __device__ __forceinline__ Row6A ld_row_a(const float* __restrict__ x, int j, in
 __device__ __forceinline__ void swe_k12_body(const B2SweParams& p, const float* __restrict__ h,
                                              float* __restrict__ h_new, const float* __restrict__ u,
                                              float* __restrict__ u_new, const float* __restrict__ v,
-                                             float* __restrict__ v_new, const float* __restrict__ dh,
-                                             const float* __restrict__ du, const float* __restrict__ dv,
-                                             float* __restrict__ dh_o, float* __restrict__ du_o,
-                                             float* __restrict__ dv_o, int j, int i0) {
+                                             float* __restrict__ v_new, const float* dh, const float* du,
+                                             const float* dv, float* dh_o, float* du_o, float* dv_o, int j,
+                                             int i0) {      // (dh_o may be dh, ...: each cell reads then writes its own)
   const int P = p.pitch;
   const size_t off = (size_t)j * P + i0;
   // index d + 1 <-> column i0 + d

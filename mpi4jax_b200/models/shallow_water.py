@@ -278,6 +278,10 @@ class ShallowWaterModel:
             if ext is not None:
                 for name in _EXT_NAMES:
                     self._ext_put(name, ext[name])
+                # the exchange in _sync_partners refreshed the halos of u, v; the run being continued
+                # had them stale by one friction step (what the frame kernels' plain path reads)
+                self.u.copy_(state[1], non_blocking=True)
+                self.v.copy_(state[2], non_blocking=True)
 
     # the frame storage as four strips per array (rows / columns within 4 cells of the array edge)
     def ext_state(self) -> Optional[dict]:

@@ -26,8 +26,8 @@ static void masks(const B2SweParams& p, int i0, bool m[4]) {
 }
 
 struct EmuStep {      // the arrays of one rank for one step (B2SweState roles of b2_swe_multistep_ca)
-  const float *h, *u, *v, *dh, *du, *dv;
-  float *h_o, *u_o, *v_o, *dh_o, *du_o, *dv_o, *upf, *vpf;
+  const float *h;
+  float *h_o, *u, *v, *dh, *du, *dv, *dub, *dvb, *upf, *vpf;
 };
 
 extern "C" {
@@ -84,8 +84,8 @@ void emu_k34(const B2SweParams* p, const float* u, float* u_new, const float* v,
 static CACtx make_ctx(const B2SweParams* p, const B2SweCA* x, const EmuStep* e) {
   CACtx c;
   c.p = *p; c.x = *x; c.x.cb1 = swe_ca_cb1(*p);
-  c.h = e->h; c.ua = e->u; c.va = e->v; c.dh = e->dh; c.du = e->du; c.dv = e->dv;
-  c.hn = e->h_o; c.dho = e->dh_o; c.duo = e->du_o; c.dvo = e->dv_o;
+  c.h = e->h; c.hn = e->h_o; c.ua = e->u; c.va = e->v; c.dh = e->dh; c.du = e->du; c.dv = e->dv;
+  c.dub = e->dub; c.dvb = e->dvb;
   c.upf = e->upf; c.vpf = e->vpf;
   return c;
 }
@@ -106,7 +106,7 @@ void emu_ca_fric_frame(const B2SweParams* p, const B2SweCA* x, const EmuStep* e,
   const CACtx c = make_ctx(p, x, e);
   const CAFrame f = ca_frame(c.p, 3, c.x.cb1);
   const long long n = f.total + ca_ext_total(c.p);
-  for (long long k = 0; k < n; ++k) swe_ca_fric_task(c, f, e->u_o, e->v_o, reverse ? n - 1 - k : k);
+  for (long long k = 0; k < n; ++k) swe_ca_fric_task(c, f, e->u, e->v, reverse ? n - 1 - k : k);
 }
 
 // swe_ca_bulk_step: CTAs one after the other, every phase as a loop over the CTA's threads
@@ -117,7 +117,7 @@ void emu_ca_bulk_k12(const B2SweParams* p, const EmuStep* e) {
   for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
     int j, i0;
     ca_bulk_task(*p, cb1, t, j, i0);
-    swe_k12_body(*p, e->h, e->h_o, e->u, e->upf, e->v, e->vpf, e->dh, e->du, e->dv, e->dh_o, e->du_o, e->dv_o, j, i0);
+    swe_k12_body(*p, e->h, e->h_o, e->u, e->upf, e->v, e->vpf, e->dh, e->du, e->dv, e->dh, e->du, e->dv, j, i0);
   }
 }
 void emu_ca_bulk_fric(const B2SweParams* p, const EmuStep* e) {
@@ -125,7 +125,7 @@ void emu_ca_bulk_fric(const B2SweParams* p, const EmuStep* e) {
   for (long long t = 0; t < ca_bulk_tasks(*p, cb1); ++t) {
     int j, i0;
     ca_bulk_task(*p, cb1, t, j, i0);
-    swe_k345_body(*p, e->upf, e->u_o, e->vpf, e->v_o, j, i0);
+    swe_k345_body(*p, e->upf, e->u, e->vpf, e->v, j, i0);
   }
 }
 

@@ -223,15 +223,17 @@ def _ca_ext(blk, epitch):
 
 
 class EmuStep(ctypes.Structure):      # EmuStep (tests/native/swe_host_emu.cpp): one rank's arrays for one step
-    _fields_ = [(n, ctypes.c_void_p) for n in ("h", "u", "v", "dh", "du", "dv", "h_o", "u_o", "v_o", "dh_o", "du_o",
-                                                "dv_o", "upf", "vpf")]
+    _fields_ = [(n, ctypes.c_void_p) for n in ("h", "h_o", "u", "v", "dh", "du", "dv", "dub", "dvb", "upf", "vpf")]
 
 
 def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0):
     """The launch sequence of b2_swe_multistep_ca on a process grid: per step the bulk flux+tendency
-    kernel, frame kernel A, the bulk friction kernel, the deep exchange, frame kernel D; every
-    prognostic array is a ping-pong pair.  (Messages are read before any rank scatters: all sends of a step come from h',
-    u', v' frame cells, which no message writes.)"""
+    kernel, frame kernel A, the bulk friction kernel, the deep exchange, frame kernel D.  Only h is
+    double-buffered; u, v and the tendencies are updated in place (kernel A keeps its own du, dv of the
+    band-only cells).  ``reverse`` walks every kernel's tasks backwards AND swaps the kernels that run
+    concurrently on the device (A before the bulk kernel, D before the bulk friction kernel): the
+    result may not depend on either.  (Messages are read before any rank scatters: all sends of a step
+    come from h', u', v' frame cells, which no message writes.)"""
     from ._halo_sim import new_exchange
 
     ranks, ny, nx, pitch = _blocks(model, PY, PX)
@@ -239,35 +241,43 @@ def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0):
     for name, kind in (("h", "h"), ("u", "u"), ("v", "v")):
         new_exchange([r[name][:, :nx] for r in ranks], PY, PX, kind)
     for r in ranks:
-        r["h1"][:], r["u1"][:], r["v1"][:] = r["h"], r["u"], r["v"]
+        r["h1"][:] = r["h"]
         for n in ("hx", "upx", "vpx", "uppx", "vppx"):
             r[n] = np.full((ny + 4, epitch), np.nan, np.float32)     # NaN = never delivered / computed
-        for n in ("dh1", "du1", "dv1", "upf", "vpf"):
+        for n in ("upf", "vpf"):
             r[n] = np.full((ny, pitch), np.nan, np.float32)
+        r["dub"], r["dvb"] = r["du"].copy(), r["dv"].copy()          # b2_swe_ca_init
     B = ctypes.byref
     _ca_exchange(emu, ranks, ("h", "u", "v"), ny, nx, pitch, epitch, PY, PX)       # b2_swe_ca_init
     for i, r in enumerate(ranks):
         p = _params(model, r, ny, nx, pitch, i // PX, PY, True)
         x = _ca_ext(r, epitch)
         emu.emu_ca_init_ext(B(p), B(x), _ptr(r["u"]), _ptr(r["v"]))
-    pairs = dict(h=("h", "h1"), u=("u", "u1"), v=("v", "v1"), dh=("dh", "dh1"), du=("du", "du1"), dv=("dv", "dv1"))
+    hh = ("h", "h1")
     cur = 0
     for it in range(nsteps):
         nxt = cur ^ 1
         ps = [_params(model, r, ny, nx, pitch, i // PX, PY, it == 0) for i, r in enumerate(ranks)]
         xs = [_ca_ext(r, epitch) for r in ranks]
-        es = [EmuStep(**{k: r[pairs[k][cur]].ctypes.data for k in pairs},
-                      **{k + "_o": r[pairs[k][nxt]].ctypes.data for k in pairs},
-                      upf=r["upf"].ctypes.data, vpf=r["vpf"].ctypes.data) for r in ranks]
+        es = [EmuStep(h=r[hh[cur]].ctypes.data, h_o=r[hh[nxt]].ctypes.data,
+                      **{k: r[k].ctypes.data for k in ("u", "v", "dh", "du", "dv", "dub", "dvb", "upf", "vpf")})
+              for r in ranks]
         for p, x, e in zip(ps, xs, es):
-            emu.emu_ca_bulk_k12(B(p), B(e))
-            emu.emu_ca_tend_frame(B(p), B(x), B(e), reverse)
-            emu.emu_ca_bulk_fric(B(p), B(e))
-        _ca_exchange(emu, ranks, (pairs["h"][nxt], "upf", "vpf"), ny, nx, pitch, epitch, PY, PX)
+            if reverse:
+                emu.emu_ca_tend_frame(B(p), B(x), B(e), reverse)
+                emu.emu_ca_bulk_k12(B(p), B(e))
+            else:
+                emu.emu_ca_bulk_k12(B(p), B(e))
+                emu.emu_ca_tend_frame(B(p), B(x), B(e), reverse)
+            if not reverse:
+                emu.emu_ca_bulk_fric(B(p), B(e))
+        _ca_exchange(emu, ranks, (hh[nxt], "upf", "vpf"), ny, nx, pitch, epitch, PY, PX)
         for p, x, e in zip(ps, xs, es):
             emu.emu_ca_fric_frame(B(p), B(x), B(e), reverse)
+            if reverse:
+                emu.emu_ca_bulk_fric(B(p), B(e))
         cur = nxt
-    return [{k: r[pairs[k][cur]][:, :nx] for k in pairs} for r in ranks]
+    return [dict(h=r[hh[cur]][:, :nx], **{k: r[k][:, :nx] for k in ("u", "v", "dh", "du", "dv")}) for r in ranks]
 
 
 @pytest.mark.parametrize("shape", [(16, 24), (26, 50), (17, 29), (140, 33), (31, 300), (200, 530)])
