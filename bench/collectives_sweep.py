@@ -35,6 +35,7 @@ ap.add_argument("--out", default="gpurun_out/collectives_sweep.json")
 ap.add_argument("--quick", action="store_true", help="every fourth size")
 ap.add_argument("--skip-allreduce-algos", action="store_true", help="time only the automatic choice")
 ap.add_argument("--only-allreduce", action="store_true", help="stop after the allreduce tables")
+ap.add_argument("--only-p2p", action="store_true", help="only the p2p ring, barrier and halo lines")
 ap.add_argument("--max-blocks", type=int, default=0, help="override the collective grid cap")
 ap.add_argument("--nvls-pipeline", type=int, default=-1, help="0 / 1: software pipelining of the NVLS allreduce")
 ap.add_argument("--min-bytes", type=int, default=1 << 10)
@@ -119,7 +120,7 @@ def time_nccl(fn, reps):
         return time_eager(fn, max(reps, 10))
 
 
-sizes = [1 << k for k in range(10, 31, 2 if ns.quick else 1) if ns.min_bytes <= (1 << k) <= ns.max_bytes]
+sizes = [] if ns.only_p2p else [1 << k for k in range(10, 31, 2 if ns.quick else 1) if ns.min_bytes <= (1 << k) <= ns.max_bytes]
 result = {"world": size, "nvls": has_nvls, "allreduce": {}, "allgather": {}, "alltoall": {}, "p2p": {}}
 
 # ---------------------------------------------------------------- allreduce

@@ -106,6 +106,29 @@ __device__ __forceinline__ unsigned p2p_ll_get(const B2DevComm& c, const uint2* 
   }
 }
 
+// The 16-byte header {seq + 1, tag, bytes lo, bytes hi} travels as ONE vector store / load: a
+// receiver that sees the sequence word sees tag and size of the same store (16-byte aligned vector
+// accesses are single transactions on NVLink and in L2 -- what NCCL's LL128 protocol builds on).
+// `release`: the payload of a slot message was written with plain stores before (flag-in-data
+// messages need no ordering: their words carry the flag themselves).
+__device__ __forceinline__ void p2p_hdr_put(unsigned* hdr, unsigned seq1, int tag, size_t nbytes, bool release) {
+  const unsigned lo = (unsigned)(nbytes & 0xffffffffull), hi = (unsigned)((unsigned long long)nbytes >> 32);
+  if (release)
+    asm volatile("st.release.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(hdr), "r"(seq1), "r"((unsigned)tag),
+                 "r"(lo), "r"(hi) : "memory");
+  else
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(hdr), "r"(seq1), "r"((unsigned)tag),
+                 "r"(lo), "r"(hi) : "memory");
+}
+struct P2PHdr { unsigned seq1; int tag; unsigned long long nbytes; };
+__device__ __forceinline__ P2PHdr p2p_hdr_get(const unsigned* hdr) {
+  unsigned a, b, c2, d;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(d) : "l"(hdr) : "memory");
+  P2PHdr h;
+  h.seq1 = a; h.tag = (int)b; h.nbytes = (unsigned long long)c2 | ((unsigned long long)d << 32);
+  return h;
+}
+
 __device__ __forceinline__ void stripe_of(size_t fraglen, int lanes, int lane, size_t* lo,
                                           size_t* hi) {
   size_t stripe = (fraglen + lanes - 1) / lanes;
@@ -118,12 +141,26 @@ __device__ __forceinline__ void stripe_of(size_t fraglen, int lanes, int lane, s
   *hi = b;
 }
 
+#define P2P_LL_WORDS_PER_THREAD ((B2_P2P_LL_MAX / 4 + B2_THREADS - 1) / B2_THREADS)
+
 __device__ void p2p_send_role(const B2DevComm& c, const B2P2PArgs& a, int lane) {
   const size_t slot_bytes = c.lay.p2p_slot_bytes;
-  const unsigned seq0 = b2_ticket_read(c.p2p_send_seq + a.dest);
-  const size_t nfrag = a.send_bytes == 0 ? 1 : (a.send_bytes + slot_bytes - 1) / slot_bytes;
   const char* src = (const char*)a.sendbuf;
   char* dheap = c.heap[a.dest];
+  const bool ll = p2p_is_ll(a.send_bytes);
+  // flag-in-data message: fetch the payload BEFORE the sequence number and the credit are known --
+  // the three memory round trips overlap instead of following each other (the message is latency)
+  unsigned word[P2P_LL_WORDS_PER_THREAD];
+  const size_t nw = ll ? (a.send_bytes + 3) >> 2 : 0;
+  if (ll) {
+#pragma unroll
+    for (int k = 0; k < P2P_LL_WORDS_PER_THREAD; ++k) {
+      const size_t w = (size_t)k * B2_THREADS + threadIdx.x;
+      word[k] = w < nw ? p2p_load_word(src, w, a.send_bytes) : 0u;
+    }
+  }
+  const unsigned seq0 = b2_ticket_read(c.p2p_send_seq + a.dest);
+  const size_t nfrag = a.send_bytes == 0 ? 1 : (a.send_bytes + slot_bytes - 1) / slot_bytes;
   for (size_t f = 0; f < nfrag; ++f) {
     const unsigned fs = seq0 + (unsigned)f;
     const unsigned slot = fs % B2_P2P_NSLOT;
@@ -138,12 +175,13 @@ __device__ void p2p_send_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
       b2_wait_ge(c, ack, fs + 1u - B2_P2P_NSLOT, a.opcode, a.dest);
     }
     __syncthreads();
-    if (p2p_is_ll(a.send_bytes)) {
-      // flag-in-data: no barrier between the payload and the header (nothing to fence)
-      uint2* ll = (uint2*)(dheap + c.lay.p2p_ll_off + ((size_t)c.rank * B2_P2P_NSLOT + slot) * (2 * B2_P2P_LL_MAX));
-      const size_t nw = (a.send_bytes + 3) >> 2;
-      for (size_t w = threadIdx.x; w < nw; w += blockDim.x)
-        p2p_ll_put(ll + w, p2p_load_word(src, w, a.send_bytes), fs + 1u);
+    if (ll) {
+      uint2* area = (uint2*)(dheap + c.lay.p2p_ll_off + ((size_t)c.rank * B2_P2P_NSLOT + slot) * (2 * B2_P2P_LL_MAX));
+#pragma unroll
+      for (int k = 0; k < P2P_LL_WORDS_PER_THREAD; ++k) {
+        const size_t w = (size_t)k * B2_THREADS + threadIdx.x;
+        if (w < nw) p2p_ll_put(area + w, word[k], fs + 1u);
+      }
     } else {
       char* dslot = dheap + c.lay.p2p_slot_off + ((size_t)c.rank * B2_P2P_NSLOT + slot) * slot_bytes;
       b2_copy_bytes<false>(dslot + lo, src + fragoff + lo, hi - lo);
@@ -152,24 +190,23 @@ __device__ void p2p_send_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
     if (threadIdx.x == 0) {
       unsigned* hdr = (unsigned*)(dheap + c.lay.p2p_hdr_off) +
                       (((size_t)c.rank * B2_P2P_NSLOT + slot) * B2_P2P_MAX_LANES + lane) * 4;
-      b2_st_relaxed_sys(hdr + 1, (unsigned)a.send_tag);
-      b2_st_relaxed_sys(hdr + 2, (unsigned)(a.send_bytes & 0xffffffffull));
-      b2_st_relaxed_sys(hdr + 3, (unsigned)(a.send_bytes >> 32));
-      b2_st_release_sys(hdr + 0, fs + 1u);
+      p2p_hdr_put(hdr, fs + 1u, a.send_tag, a.send_bytes, !ll);
     }
   }
-  b2_finish_bump(c.p2p_send_seq + a.dest, c.p2p_ctl + CTL_SEND_FIN, (unsigned)nfrag,
-                 (unsigned)a.send_lanes);
+  if (a.send_lanes == 1) {
+    // the only CTA of the role knows the new value: no counter, no reload (kernel boundaries order it)
+    if (threadIdx.x == 0) b2_st_volatile(c.p2p_send_seq + a.dest, seq0 + (unsigned)nfrag);
+  } else {
+    b2_finish_bump(c.p2p_send_seq + a.dest, c.p2p_ctl + CTL_SEND_FIN, (unsigned)nfrag, (unsigned)a.send_lanes);
+  }
 }
 
 // Sequence number of the first fragment of the message a receive (src, tag) consumes.  Executed by
 // thread 0 of EVERY receiving lane on the lane-0 headers (every message has one): the pair state
 // (head, bitmap) only changes when a receive kernel finishes, headers arrive in sequence order and
 // the scan stops at the first fragment that has not arrived, so all lanes pick the same message.
-__device__ unsigned p2p_match(const B2DevComm& c, const B2P2PArgs& a, int src) {
-  const unsigned head = b2_ld_volatile(c.p2p_recv_seq + src);
-  if (a.recv_tag < 0) return head;                       // ANY_TAG: always the head of the queue
-  const unsigned ooo = b2_ld_volatile(c.p2p_ctl + CTL_OOO + src);
+__device__ unsigned p2p_match(const B2DevComm& c, const B2P2PArgs& a, int src, unsigned head, unsigned ooo,
+                              P2PHdr* found) {
   const size_t slot_bytes = c.lay.p2p_slot_bytes;
   const unsigned* hdr_base = (const unsigned*)(c.heap[c.rank] + c.lay.p2p_hdr_off);
   unsigned long long t0 = 0;
@@ -180,14 +217,13 @@ __device__ unsigned p2p_match(const B2DevComm& c, const B2P2PArgs& a, int src) {
       if ((ooo >> i) & 1u) { ++i; continue; }            // already consumed out of order
       const unsigned sq = head + i;
       const unsigned* h = hdr_base + (((size_t)src * B2_P2P_NSLOT + sq % B2_P2P_NSLOT) * B2_P2P_MAX_LANES) * 4;
-      if (b2_ld_acquire_sys(h) != sq + 1u) break;        // not here yet (nor anything behind it)
-      const int tag = (int)b2_ld_volatile(h + 1);
-      const unsigned long long nb =
-          (unsigned long long)b2_ld_volatile(h + 2) | ((unsigned long long)b2_ld_volatile(h + 3) << 32);
-      const unsigned long long nf = nb == 0 ? 1 : (nb + slot_bytes - 1) / slot_bytes;
-      if (tag == a.recv_tag) {
+      const P2PHdr hd = p2p_hdr_get(h);
+      if (hd.seq1 != sq + 1u) break;                     // not here yet (nor anything behind it)
+      const unsigned long long nf = hd.nbytes == 0 ? 1 : (hd.nbytes + slot_bytes - 1) / slot_bytes;
+      if (a.recv_tag < 0 || hd.tag == a.recv_tag) {      // ANY_TAG: always the head of the queue
         if (i != 0 && nf != 1)       // a streamed message cannot overtake (see the file header)
-          b2_fatal(c, B2_ERR_TAG_MISMATCH, a.opcode, src, (unsigned)a.recv_tag, (unsigned)tag, 5);
+          b2_fatal(c, B2_ERR_TAG_MISMATCH, a.opcode, src, (unsigned)a.recv_tag, (unsigned)hd.tag, 5);
+        *found = hd;
         return sq;
       }
       if (nf >= B2_P2P_NSLOT - i) break;                  // its fragments fill the rest of the window
@@ -242,8 +278,8 @@ __device__ bool p2p_scan(const B2DevComm& c, const B2P2PArgs& a, int src) {
 #endif
 
 __device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) {
-  __shared__ int s_src;
-  __shared__ unsigned s_seq0;
+  __shared__ int s_src, s_tag;
+  __shared__ unsigned s_seq0, s_head, s_ooo, s_gen;
   const size_t slot_bytes = c.lay.p2p_slot_bytes;
   const unsigned* hdr_base = (const unsigned*)(c.heap[c.rank] + c.lay.p2p_hdr_off);
 
@@ -296,11 +332,23 @@ __device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
       }
     }
     s_src = src;
-    s_seq0 = p2p_match(c, a, src);
+    // pair state: three independent loads in flight together (GEN is only needed for the final bump)
+    s_head = b2_ld_volatile(c.p2p_recv_seq + src);
+    s_ooo = b2_ld_volatile(c.p2p_ctl + CTL_OOO + src);
+    s_gen = b2_ld_volatile(c.p2p_ctl + CTL_GEN);
+    P2PHdr hd;
+    s_seq0 = p2p_match(c, a, src, s_head, s_ooo, &hd);
+    // the matched header is lane 0's header of the message's first fragment: check it once, here
+    if (a.recv_tag >= 0 && hd.tag != a.recv_tag)
+      b2_fatal(c, B2_ERR_TAG_MISMATCH, a.opcode, src, (unsigned)a.recv_tag, (unsigned)hd.tag, 0);
+    if (hd.nbytes != (unsigned long long)a.recv_bytes)
+      b2_fatal(c, B2_ERR_TRUNCATE, a.opcode, src, (unsigned)a.recv_bytes, (unsigned)hd.nbytes, 0);
+    s_tag = hd.tag;
   }
   __syncthreads();
   const int src = s_src;
   const unsigned seq0 = s_seq0;
+  const bool ll = p2p_is_ll(a.recv_bytes);
 
   const size_t nfrag = a.recv_bytes == 0 ? 1 : (a.recv_bytes + slot_bytes - 1) / slot_bytes;
   char* dst = (char*)a.recvbuf;
@@ -312,71 +360,74 @@ __device__ void p2p_recv_role(const B2DevComm& c, const B2P2PArgs& a, int lane) 
     const size_t fraglen = (a.recv_bytes - fragoff < slot_bytes) ? (a.recv_bytes - fragoff) : slot_bytes;
     size_t lo, hi;
     stripe_of(fraglen, a.recv_lanes, lane, &lo, &hi);
-    const unsigned* hdr = hdr_base + (((size_t)src * B2_P2P_NSLOT + slot) * B2_P2P_MAX_LANES + lane) * 4;
-    if (threadIdx.x == 0) {
-      b2_wait_eq(c, hdr, fs + 1u, a.opcode, src);
-      if (f == 0) {
-        const int tag = (int)b2_ld_volatile(hdr + 1);
-        const unsigned long long nb =
-            (unsigned long long)b2_ld_volatile(hdr + 2) | ((unsigned long long)b2_ld_volatile(hdr + 3) << 32);
-        if (a.recv_tag >= 0 && tag != a.recv_tag)
-          b2_fatal(c, B2_ERR_TAG_MISMATCH, a.opcode, src, (unsigned)a.recv_tag, (unsigned)tag, 0);
-        if (nb != (unsigned long long)a.recv_bytes)
-          b2_fatal(c, B2_ERR_TRUNCATE, a.opcode, src, (unsigned)a.recv_bytes, (unsigned)nb, 0);
-        if (lane == 0 && a.status != nullptr) {
-          a.status->source = src;
-          a.status->tag = tag;
-          a.status->count_bytes = (long long)nb;
-          a.status->error = 0;
-          __threadfence_system();
-          a.status->ready = 1;
-        }
-      }
-    }
-    __syncthreads();
-    if (p2p_is_ll(a.recv_bytes)) {
-      const uint2* ll = (const uint2*)(myheap + c.lay.p2p_ll_off + ((size_t)src * B2_P2P_NSLOT + slot) * (2 * B2_P2P_LL_MAX));
+    if (ll) {
+      // flag-in-data: the words are polled themselves; nothing to wait for, nothing to fence
+      const uint2* area = (const uint2*)(myheap + c.lay.p2p_ll_off + ((size_t)src * B2_P2P_NSLOT + slot) * (2 * B2_P2P_LL_MAX));
       const size_t nw = (a.recv_bytes + 3) >> 2;
       for (size_t w = threadIdx.x; w < nw; w += blockDim.x)
-        p2p_store_word(dst, w, a.recv_bytes, p2p_ll_get(c, ll + w, fs + 1u, a.opcode, src));
+        p2p_store_word(dst, w, a.recv_bytes, p2p_ll_get(c, area + w, fs + 1u, a.opcode, src));
     } else {
+      // this lane's stripe of the slot was written by the sender's lane of the same index: its header
+      // (acquire) orders the payload loads
+      const unsigned* hdr = hdr_base + (((size_t)src * B2_P2P_NSLOT + slot) * B2_P2P_MAX_LANES + lane) * 4;
+      if (threadIdx.x == 0) b2_wait_eq(c, hdr, fs + 1u, a.opcode, src);
+      __syncthreads();
       const char* sslot = myheap + c.lay.p2p_slot_off + ((size_t)src * B2_P2P_NSLOT + slot) * slot_bytes;
       b2_copy_bytes<true>(dst + fragoff + lo, sslot + lo, hi - lo);
     }
     __syncthreads();
+    // credit back to the sender: every load of the slot has returned (their values were stored)
     if (threadIdx.x == 0) {
-      __threadfence();
-      unsigned* done = c.p2p_ctl + CTL_SLOT_DONE + slot;
-      const unsigned old = atomicAdd(done, 1u);
-      if (old == (unsigned)a.recv_lanes - 1u) {
-        b2_st_volatile(done, 0u);
-        unsigned* ack = (unsigned*)(c.heap[src] + c.lay.p2p_ack_off) + (size_t)c.rank * B2_P2P_NSLOT + slot;
-        b2_st_release_sys(ack, fs + 1u);
+      unsigned* ack = (unsigned*)(c.heap[src] + c.lay.p2p_ack_off) + (size_t)c.rank * B2_P2P_NSLOT + slot;
+      if (a.recv_lanes == 1) {
+        if (ll) b2_st_relaxed_sys(ack, fs + 1u);      // (the polled words were consumed: nothing left to order)
+        else b2_st_release_sys(ack, fs + 1u);
+      } else {
+        __threadfence();
+        unsigned* done = c.p2p_ctl + CTL_SLOT_DONE + slot;
+        const unsigned old = atomicAdd(done, 1u);
+        if (old == (unsigned)a.recv_lanes - 1u) {
+          b2_st_volatile(done, 0u);
+          b2_st_release_sys(ack, fs + 1u);
+        }
       }
     }
   }
+  if (threadIdx.x == 0 && lane == 0 && a.status != nullptr) {
+    a.status->source = src;
+    a.status->tag = s_tag;
+    a.status->count_bytes = (long long)a.recv_bytes;
+    a.status->error = 0;
+    __threadfence_system();
+    a.status->ready = 1;
+  }
   // advance recv_seq[src] (+ election generation) once every lane is done
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned old = atomicAdd(c.p2p_ctl + CTL_RECV_FIN, 1u);
-    if (old == (unsigned)a.recv_lanes - 1u) {
-      b2_st_volatile(c.p2p_ctl + CTL_RECV_FIN, 0u);
-      const unsigned head = b2_ld_volatile(c.p2p_recv_seq + src);
-      unsigned ooo = b2_ld_volatile(c.p2p_ctl + CTL_OOO + src);
-      if (seq0 == head) {
-        // in order: advance past this message and past anything behind it that was already taken
-        unsigned nh = head + (unsigned)nfrag;
-        ooo = nfrag >= B2_P2P_NSLOT ? 0u : (ooo >> (unsigned)nfrag);
-        while (ooo & 1u) { ooo >>= 1; ++nh; }
-        b2_st_volatile(c.p2p_recv_seq + src, nh);
-      } else {
-        ooo |= 1u << (seq0 - head);                     // single-slot message taken ahead of the head
-      }
-      b2_st_volatile(c.p2p_ctl + CTL_OOO + src, ooo);
-      b2_st_volatile(c.p2p_ctl + CTL_GEN, b2_ld_volatile(c.p2p_ctl + CTL_GEN) + 1u);
+  bool last = a.recv_lanes == 1;
+  if (!last) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
       __threadfence();
+      const unsigned old = atomicAdd(c.p2p_ctl + CTL_RECV_FIN, 1u);
+      last = old == (unsigned)a.recv_lanes - 1u;
+      if (last) b2_st_volatile(c.p2p_ctl + CTL_RECV_FIN, 0u);
     }
+  }
+  if (threadIdx.x == 0 && last) {
+    // (head, ooo, gen as read at entry: the pair state only changes here, at the end of a receive)
+    const unsigned head = s_head;
+    unsigned ooo = s_ooo;
+    if (seq0 == head) {
+      // in order: advance past this message and past anything behind it that was already taken
+      unsigned nh = head + (unsigned)nfrag;
+      ooo = nfrag >= B2_P2P_NSLOT ? 0u : (ooo >> (unsigned)nfrag);
+      while (ooo & 1u) { ooo >>= 1; ++nh; }
+      b2_st_volatile(c.p2p_recv_seq + src, nh);
+    } else {
+      ooo |= 1u << (seq0 - head);                     // single-slot message taken ahead of the head
+    }
+    b2_st_volatile(c.p2p_ctl + CTL_OOO + src, ooo);
+    b2_st_volatile(c.p2p_ctl + CTL_GEN, s_gen + 1u);
+    __threadfence();
   }
 }
 

@@ -469,6 +469,16 @@ extern "C" int b2_comm_set_option(B2Comm* c, const char* key, long long value) {
   return 0;
 }
 
+// read back what the launches use (tests/test_coresidency.py checks the grid cap against the SM count)
+extern "C" long long b2_comm_get_option(B2Comm* c, const char* key) {
+  if (strcmp(key, "max_blocks") == 0) return c->max_blocks;
+  if (strcmp(key, "sm_count") == 0) return c->sm_count;
+  if (strcmp(key, "bcast_mc_min") == 0) return (long long)c->bcast_mc_min;
+  if (strcmp(key, "nvls_pipeline") == 0) return c->nvls_pipeline ? 1 : 0;
+  b2_set_error("unknown communicator option '%s'", key);
+  return -1;
+}
+
 static const char* opcode_name(int opc) {
   static const char* names[] = {"Barrier", "Allreduce", "Reduce", "Scan", "Allgather", "Alltoall",
                                 "Bcast", "Gather", "Scatter", "Send", "Recv", "Sendrecv", "Halo"};

@@ -107,7 +107,8 @@ int b2_comm_set_stage(B2Comm* c, B2Seg* stage, B2Mc* mc);
 size_t b2_comm_stage_half(B2Comm* c);
 int b2_comm_set_tuning(B2Comm* c, long long ll_max, long long oneshot_max, long long nvls_min,
                        int max_blocks);
-int b2_comm_set_option(B2Comm* c, const char* key, long long value);   // "bcast_mc_min", "nvls_pipeline"
+int b2_comm_set_option(B2Comm* c, const char* key, long long value);
+long long b2_comm_get_option(B2Comm* c, const char* key);   // "bcast_mc_min", "nvls_pipeline"
 int b2_comm_check_error(B2Comm* c, char* buf, int buflen);     // 0 = ok
 int b2_comm_destroy(B2Comm* c);
 size_t b2_stage_need(int opcode, int nranks, size_t blk_bytes); // staging half needed by an op

@@ -347,6 +347,17 @@ class NativeComm:
         """Runtime switches of the native communicator: ``bcast_mc_min`` (bytes), ``nvls_pipeline`` (0/1)."""
         self._check(_lib().b2_comm_set_option(self.handle, key.encode(), int(value)), "Comm_set_option")
 
+    def get_option(self, key: str) -> int:
+        """Current value of a launch parameter: ``max_blocks``, ``sm_count``, ``bcast_mc_min``, ``nvls_pipeline``."""
+        value = int(_lib().b2_comm_get_option(self.handle, key.encode()))
+        if value < 0:
+            raise ValueError(f"unknown communicator option {key!r}")
+        return value
+
+    @property
+    def max_blocks(self) -> int:
+        return self.get_option("max_blocks")
+
     def destroy(self) -> None:
         lib = _lib()
         try:

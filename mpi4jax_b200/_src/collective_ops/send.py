@@ -36,8 +36,14 @@ class _SendWithGrad(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _g):
         shape, dtype, device = ctx.meta
-        template = torch.empty(shape, dtype=dtype, device=device)
-        return _dispatch.recv(ctx.comm, template, ctx.dest, ctx.tag, None), None, None, None
+        comm, dest, tag = ctx.comm, ctx.dest, ctx.tag
+
+        def receive(_token_cotangent):
+            return _dispatch.recv(comm, torch.empty(shape, dtype=dtype, device=device), dest, tag, None)
+
+        # (under torch.func.grad even a tensor created HERE is a transform wrapper without storage; the
+        # backend, which takes raw pointers on the GPU path, has to run below the transform levels)
+        return _dispatch.run_opaque(receive, _g), None, None, None
 
 
 @enforce_types(dest=(np.integer,), tag=(np.integer,), comm=(type(None), Comm))

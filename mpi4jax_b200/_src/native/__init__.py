@@ -162,6 +162,7 @@ _SIGNATURES = {
     "b2_comm_stage_half": (c_size_t, [c_void_p]),
     "b2_comm_set_tuning": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong, c_int]),
     "b2_comm_set_option": (c_int, [c_void_p, c_char_p, c_longlong]),
+    "b2_comm_get_option": (c_longlong, [c_void_p, c_char_p]),
     "b2_comm_check_error": (c_int, [c_void_p, c_char_p, c_int]),
     "b2_comm_destroy": (c_int, [c_void_p]),
     "b2_stage_need": (c_size_t, [c_int, c_int, c_size_t]),
