@@ -3,13 +3,14 @@
 //
 // One model step (the reference's shallow_water_step, examples/shallow_water.py:270-403):
 //
-//   stream s  (bulk) :  B  flux + tendency (bulk) -----------> Fb friction (bulk) ----------+--> next step
-//                                                    ^ (u', v' of the band next to the bulk) |
+//   stream s  (bulk) :  B  flux + tendency (bulk) -----+-----> Fb friction (bulk) ----------+--> next step
+//                                                    ^ |  (u', v' of the band next to the bulk; B done
+//                                                    | v   before D overwrites the frame's u, v)
 //   stream s2 (frame):  A (tendencies, frame band) -> X (deep halo exchange) -> D (friction, frame + ext)
 //
-// B / Fb write only bulk cells, A / X / D own the frame: ONE edge between the two streams inside a
-// step (A -> Fb), two at the step boundary (B(t+1) reads what D(t) wrote next to the bulk, A(t+1) what
-// Fb(t) wrote next to the frame).  Only h is double-buffered (its stencil is read while h' is written);
+// B / Fb write only bulk cells, A / X / D own the frame: two edges between the streams inside a step
+// (A -> Fb, B -> D), two at the step boundary (B(t+1) reads what D(t) wrote next to the bulk, A(t+1)
+// what Fb(t) wrote next to the frame).  Only h is double-buffered (its stencil is read while h' is written);
 // u', v' travel through their own arrays between the tendency and the friction kernels, so u'', v''
 // and the tendencies are updated in place: nine arrays are live per step -- at 8 GPUs (2 M cells per
 // rank) 75 MB, which stays in the 126 MB L2.  The NVLink round of X is
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(CA_THREADS) b2_k_halo_ca(const B2DevComm c, co
 
 // ---- host side --------------------------------------------------------------------------------------
 static cudaStream_t g_side = nullptr;
-static cudaEvent_t g_ev[4];
+static cudaEvent_t g_ev[5];
 
 static int ca_streams() {
   if (g_side) return 0;
@@ -242,7 +243,7 @@ static int ca_streams() {
     g_side = nullptr;
     return 1;
   }
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < 5; ++k)
     if (cudaEventCreateWithFlags(&g_ev[k], cudaEventDisableTiming) != cudaSuccess) {
       b2_set_error("swe_ca: cudaEventCreate failed");
       return 1;
@@ -357,7 +358,7 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
   if (int rc = ca_check(c, p, x)) return rc;
   if (int rc = ca_streams()) return rc;
   const cudaStream_t s2 = g_side;
-  const cudaEvent_t e0 = g_ev[0], eS = g_ev[1], eD = g_ev[2], eA = g_ev[3];
+  const cudaEvent_t e0 = g_ev[0], eS = g_ev[1], eD = g_ev[2], eA = g_ev[3], eB = g_ev[4];
   const unsigned bulk_blocks = ca_blocks(ca_bulk_tasks(p, x.cb1), SWE_THREADS);
   // the flux arrays of the stand-alone path are free here: fe / fn hold u', v' between the tendency and
   // the friction kernels, ke / fe2 kernel A's copy of du, dv on the band-only cells
@@ -393,6 +394,7 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
     // band next to the bulk (enqueued below, after A's event)
     swe_ca_bulk_k12<<<bulk_blocks, SWE_THREADS, 0, s>>>(sa, upf, vpf, ca_slot(it, 1));
     if ((rc = ca_done(c, "swe_ca_bulk_k12"))) break;
+    CA_RT(cudaEventRecord(eB, s));
     // ---- frame stream: needs the bulk kernel of the previous step (u'', v'', h next to the frame)
     if (it > 0) CA_RT(cudaStreamWaitEvent(s2, eS, 0));
     if (rc) break;
@@ -412,6 +414,11 @@ int b2_swe_multistep_ca(B2Comm* c, const B2SweParams* p0, const B2SweState* st, 
     if ((rc = ca_done(c, "swe_ca_bulk_fric"))) break;
     CA_RT(cudaEventRecord(eS, s));
     if ((rc = ca_exchange(c, *topo, p, x, H[nxt], upf, vpf, s2, ca_slot(it, 2)))) break;
+    // D overwrites u, v of the frame IN PLACE: the bulk kernel, whose stencil reads them next to the
+    // frame, must be done (it is, long before, except on very large blocks -- where D then runs under the
+    // bulk friction kernel instead of under B)
+    CA_RT(cudaStreamWaitEvent(s2, eB, 0));
+    if (rc) break;
     swe_ca_fric_frame<<<fric_blocks, CA_CELLS * 3, 0, s2>>>(ctx, fd, st->u, st->v, ca_slot(it, 4));
     if ((rc = ca_done(c, "swe_ca_fric_frame"))) break;
     CA_RT(cudaEventRecord(eD, s2));

@@ -1,22 +1,17 @@
 #!/bin/bash
-# round 2, call F (8 GPUs): multi-rank GPU suite with per-rank logs, scaling curve, timeline, sweeps, profiles
+# round 2, call F (8 GPUs): multi-rank GPU suite with per-rank logs, scaling points, timeline, sweeps, profiles
 mkdir -p gpurun_out
-export MPI4JAX_B200_TIMEOUT=60
+export MPI4JAX_B200_TIMEOUT=30
 T0=$(date +%s)
 stamp() { echo "== $1 (+$(( $(date +%s) - T0 )) s)"; }
 stamp "pytest 8 ranks"
-timeout 600 python -m mpi4jax_b200.run -n 8 --timeout 560 --output-dir gpurun_out/r2f_pytest_n8 -m pytest tests/collective_ops tests/test_extensions.py \
-   tests/test_examples.py tests/test_models.py tests/test_jit.py tests/test_common.py tests/test_gemm.py tests/test_transport.py \
-   -q -m gpu -p no:cacheprovider -rf > /dev/null 2>&1
+timeout 300 python -m mpi4jax_b200.run -n 8 --timeout 280 --output-dir gpurun_out/r2f_pytest_n8 -m pytest tests \
+   -v -m gpu -p no:cacheprovider -rf > /dev/null 2>&1
 echo "pytest n8 exit $?"; tail -n 3 gpurun_out/r2f_pytest_n8/rank0.log | cut -c1-200; grep -h "^FAILED\|^ERROR" gpurun_out/r2f_pytest_n8/rank*.log | sort | uniq -c | head -n 12
-for n in 8 4 2 1; do
+for n in 8 4; do
   stamp "bench n=$n k=20"
-  if [ $n = 1 ]; then
-    timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2f_bench_n1_k20.json 2> gpurun_out/r2f_bench_n1_k20.err
-  else
-    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) \
+  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) \
       bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r2f_bench_n${n}_k20.json 2> gpurun_out/r2f_bench_n${n}_k20.err
-  fi
   python - <<PY
 import json
 try:
@@ -30,30 +25,22 @@ except Exception as e:
 PY
   tail -n 2 gpurun_out/r2f_bench_n${n}_k20.err | cut -c1-300
 done
-stamp "bench n=8 k=200"
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29650 \
-   bench.py --gpus 8 --steps 200 --warmup 20 --no-sweep > gpurun_out/r2f_bench_n8_k200.json 2> gpurun_out/r2f_bench_n8_k200.err
-cut -c1-260 gpurun_out/r2f_bench_n8_k200.json
 stamp "timeline"
-timeout 200 python -m mpi4jax_b200.run -n 8 --timeout 180 --output-dir gpurun_out/r2f_timeline_n8 scripts/swe_timeline.py 4096 8 > /dev/null 2>&1
+timeout 120 python -m mpi4jax_b200.run -n 8 --timeout 100 --output-dir gpurun_out/r2f_timeline_n8 scripts/swe_timeline.py 4096 8 > /dev/null 2>&1
 tail -n 10 gpurun_out/r2f_timeline_n8/rank0.log
 stamp "sweep"
-timeout 600 python -m mpi4jax_b200.run -n 8 --timeout 560 bench/collectives_sweep.py --quick --skip-allreduce-algos \
+timeout 400 python -m mpi4jax_b200.run -n 8 --timeout 380 bench/collectives_sweep.py --quick --skip-allreduce-algos \
    --out gpurun_out/r2f_sweep_n8.json > gpurun_out/r2f_sweep_n8.log 2>&1
 echo "sweep exit $?"; grep -E "^fp32|^bf16" gpurun_out/r2f_sweep_n8.log | cut -c1-200; grep -E "^rooted|^allgather|^p2p" gpurun_out/r2f_sweep_n8.log | cut -c1-700
-stamp "allreduce variants"
-for v in "0 148" "1 296" "0 296"; do
-  set -- $v
-  timeout 300 python -m mpi4jax_b200.run -n 8 --timeout 280 bench/collectives_sweep.py --quick --skip-allreduce-algos --only-allreduce \
-     --min-bytes 1048576 --nvls-pipeline $1 --max-blocks $2 --out gpurun_out/r2f_ar_pipe$1_mb$2.json > gpurun_out/r2f_ar_pipe$1_mb$2.log 2>&1
-  echo "pipeline=$1 max_blocks=$2"; grep -E "^fp32" gpurun_out/r2f_ar_pipe$1_mb$2.log | cut -c1-160
-done
+stamp "bw probe"
+timeout 200 python -m mpi4jax_b200.run -n 8 --timeout 180 scripts/bw_probe.py 64 > gpurun_out/r2f_bw_probe_n8.log 2>&1
+grep -E "MiB|nccl" gpurun_out/r2f_bw_probe_n8.log | cut -c1-400 || tail -n 5 gpurun_out/r2f_bw_probe_n8.log
 stamp "mlp grad"
-timeout 300 python -m mpi4jax_b200.run -n 8 --timeout 280 bench/mlp_grad.py --out gpurun_out/r2f_mlp_grad_n8.json > gpurun_out/r2f_mlp_grad_n8.log 2>&1
+timeout 120 python -m mpi4jax_b200.run -n 8 --timeout 100 bench/mlp_grad.py --out gpurun_out/r2f_mlp_grad_n8.json > gpurun_out/r2f_mlp_grad_n8.log 2>&1
 tail -n 4 gpurun_out/r2f_mlp_grad_n8.log | cut -c1-300
 stamp "ncu rank 0"
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29660 --no-python \
-   scripts/rank0_ncu.sh x --set full --import-source on -k regex:'b2_k_|swe_ca_' -s 14 -c 22 -o gpurun_out/r2f_rank0_n8 -- \
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29660 --no-python \
+   scripts/rank0_ncu.sh x --set full --import-source on -k regex:'b2_k_|swe_ca_' -s 14 -c 24 -o gpurun_out/r2f_rank0_n8 -- \
    scripts/prof_collectives.py > gpurun_out/r2f_ncu_n8.log 2>&1
 echo "ncu rc=$?"; tail -n 3 gpurun_out/r2f_ncu_n8.log | cut -c1-200
 stamp "done"

@@ -109,19 +109,21 @@ def test_native_step_is_bitwise_reproducible(pdl):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(256, 192), (100, 52), (1024, 320)])
+@pytest.mark.parametrize("shape", [(256, 192), (100, 52), (1024, 320), (4096, 4096)])
 def test_ca_pipeline_is_bit_identical_to_the_standalone_kernels(shape):
     """Same discrete system, different launch schedules: the communication-avoiding step (one deep
     exchange per step, frame recomputed with owner views, fused bulk kernels, csrc/b2_swe_ca.cu)
     against the four stand-alone kernels with three exchanges (csrc/b2_swe.cu).  Every rounding in
     the shared bodies is explicit, so the comparison is bitwise -- halos of the main arrays
     included (h fresh; u, v stale by the friction step, as the reference's in-place update leaves
-    them)."""
+    them).  The 4096 x 4096 case is there for the SCHEDULE: only on blocks that large do the bulk and
+    the frame kernels really overlap in time (a missing dependency between the two streams goes
+    unnoticed on small blocks, where each kernel is over before the next one starts)."""
     pipeline = "ca"
     if not torch.cuda.is_available():
         pytest.skip("needs CUDA")
     size = comm.Get_size()
-    cfg = ShallowWaterConfig.for_resolution(shape[0] * max(1, size // 2), shape[1])
+    cfg = ShallowWaterConfig.for_resolution(shape[0] * max(1, size // 2) if shape[0] < 4096 else shape[0], shape[1])
     runs = {}
     for name, mode in (("a", pipeline), ("again", pipeline), ("standalone", "standalone")):
         model = ShallowWaterModel(cfg, comm=comm, device=comm.device, backend="native", pipeline=mode)

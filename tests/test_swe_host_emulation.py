@@ -232,7 +232,8 @@ def _emulate_ca(emu, model, PY, PX, nsteps, reverse=0):
     double-buffered; u, v and the tendencies are updated in place (kernel A keeps its own du, dv of the
     band-only cells).  ``reverse`` walks every kernel's tasks backwards AND swaps the kernels that run
     concurrently on the device (A before the bulk kernel, D before the bulk friction kernel): the
-    result may not depend on either.  (Messages are read before any rank scatters: all sends of a step
+    result may not depend on either.  (D never runs before the bulk flux+tendency kernel: it overwrites
+    u, v of the frame in place, which that kernel's stencil reads -- the B -> D edge of the schedule.)  (Messages are read before any rank scatters: all sends of a step
     come from h', u', v' frame cells, which no message writes.)"""
     from ._halo_sim import new_exchange
 
