@@ -101,8 +101,123 @@ __device__ __forceinline__ void b2_gather_bytes(char* __restrict__ dst, const ch
   }
 }
 
-__global__ void __launch_bounds__(B2_THREADS)
-b2_k_move(const B2DevComm c, const B2MoveArgs a) {
+// stage one chunk of every input block (plain local copy, or the fused gather of a strided input)
+__device__ __forceinline__ void move_stage(const B2MoveArgs& a, char* mine, const char* in, size_t off, size_t len) {
+  for (int j = 0; j < a.nin; ++j) {
+    if (a.lay.nd > 0)
+      b2_gather_bytes(mine + (size_t)j * a.blk_stride + off, in + (long long)j * a.in_blk_stride, a.lay, off, len);
+    else
+      b2_copy_bytes<false>(mine + (size_t)j * a.blk_stride + off, in + (size_t)j * a.blk_bytes + off, len);
+  }
+}
+
+// Pull chunk [off, off + len) from the peers' staging into the output AND stage chunk [noff, noff + nlen)
+// of this rank's input, in ONE loop: the NVLink loads (~3 us round trip) and the local HBM loads of a
+// thread are in flight together, U vectors each -- a CTA is one per SM (co-residency, pick_chunks), so
+// what it cannot overlap inside a thread it cannot overlap at all.  Measured before (2 GPUs, 256 MiB,
+// profiles/r2_bw_probe_n2.log): 460 GB/s for every collective, proportional to the CTA count, next to
+// 625 GB/s for the p2p ring on 64 CTAs -- latency-bound phases in a row, not the link.
+template <int NS, int NI, int U, bool SPLIT>
+__device__ __noinline__ void move_pull_and_stage(const B2DevComm& c, const B2MoveArgs& a, const size_t par,
+                                                 char* mine, const char* in, char* out, const size_t off,
+                                                 const size_t len, const size_t noff, const size_t nlen) {
+  // (a real call per chunk: every instantiation gets its own register allocation; everything the loop
+  // needs is read from the argument structs ONCE -- the stores below go through char pointers, which
+  // may alias anything as far as the compiler knows)
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int nsrc = a.nsrc, nin = a.nin;
+  const size_t nvp = len >> 4, nvi = nlen >> 4;
+  const size_t nvmax = nvp > nvi ? nvp : nvi;
+  const char* psrc[NS];
+  char* pdst[NS];
+  const char* ssrc[NI];
+  char* sdst[NI];
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) {
+    const int k = s2 < nsrc ? (s2 + c.rank) % nsrc : 0;      // stagger peers across ranks
+    psrc[s2] = c.stage[a.src_rank[k]] + par + (size_t)a.src_blk[k] * a.blk_stride + off;
+    pdst[s2] = out + (size_t)a.dst_blk[k] * a.blk_bytes + off;
+  }
+#pragma unroll
+  for (int j = 0; j < NI; ++j) {
+    ssrc[j] = in + (size_t)j * a.blk_bytes + noff;
+    sdst[j] = mine + (size_t)j * a.blk_stride + noff;
+  }
+  (void)nvmax;
+  // main part: whole tiles of U x blockDim vectors on BOTH sides, no per-vector conditions (arrays that
+  // are defined under a condition end up in local memory)
+  const size_t tile = (size_t)U * nt;
+  const size_t nvmin = nvp < nvi ? nvp : nvi;
+  const size_t full = nvmin / tile * tile;
+  for (size_t base = 0; base < full; base += tile) {
+    uint4 pv[U][NS], sv[U][NI];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = base + (size_t)u * nt + t;
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) {
+        pv[u][s2] = make_uint4(0, 0, 0, 0);
+        if (s2 < nsrc) pv[u][s2] = b2_ld_peer16(psrc[s2] + (i << 4));
+      }
+      if (!SPLIT) {
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          sv[u][j] = make_uint4(0, 0, 0, 0);
+          if (j < nin) sv[u][j] = b2_ld_stream16(ssrc[j] + (i << 4));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = base + (size_t)u * nt + t;
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2)
+        if (s2 < nsrc) b2_st16(pdst[s2] + (i << 4), pv[u][s2]);
+      if (SPLIT) {        // (2 x 8 vectors live at once do not fit the register file: one side after the other)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          sv[u][j] = make_uint4(0, 0, 0, 0);
+          if (j < nin) sv[u][j] = b2_ld_stream16(ssrc[j] + (i << 4));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NI; ++j)
+        if (j < nin) b2_st16(sdst[j] + (i << 4), sv[u][j]);
+    }
+  }
+  // remainders (the last tile of a chunk, a shorter or missing next chunk): one side after the other
+  for (size_t i = full + t; i < nvp; i += nt) {
+    uint4 pv[NS];
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) {
+      pv[s2] = make_uint4(0, 0, 0, 0);
+      if (s2 < nsrc) pv[s2] = b2_ld_peer16(psrc[s2] + (i << 4));
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2)
+      if (s2 < nsrc) b2_st16(pdst[s2] + (i << 4), pv[s2]);
+  }
+  for (size_t i = full + t; i < nvi; i += nt) {
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+      if (j < nin) b2_st16(sdst[j] + (i << 4), b2_ld_stream16(ssrc[j] + (i << 4)));
+  }
+  // the last < 16 bytes of either chunk
+  const size_t ptail = len & 15, stail = nlen & 15;
+  if (ptail && (size_t)t < ptail) {
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2)
+      if (s2 < nsrc) pdst[s2][(nvp << 4) + t] = ((const volatile char*)psrc[s2])[(nvp << 4) + t];
+  }
+  if (stail && (size_t)t < stail) {
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+      if (j < nin) sdst[j][(nvi << 4) + t] = ssrc[j][(nvi << 4) + t];
+  }
+}
+
+__global__ void __launch_bounds__(B2_THREADS, 1)
+b2_k_move(const __grid_constant__ B2DevComm c, const __grid_constant__ B2MoveArgs a) {
   const unsigned ticket = b2_ticket_read(c.ticket);
   const size_t par = (size_t)(ticket & 1u) * c.stage_half;
   unsigned e = b2_ld_volatile(c.epoch + blockIdx.x);
@@ -110,54 +225,46 @@ b2_k_move(const B2DevComm c, const B2MoveArgs a) {
   char* out = (char*)a.out;
   char* mine = c.stage[c.rank] + par;
   const size_t nchunks = (a.blk_bytes + a.chunk - 1) / a.chunk;
-
-  for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const size_t off = ch * a.chunk;
-    const size_t len = (a.blk_bytes - off < a.chunk) ? (a.blk_bytes - off) : a.chunk;
-    for (int j = 0; j < a.nin; ++j) {
-      if (a.lay.nd > 0)
-        b2_gather_bytes(mine + (size_t)j * a.blk_stride + off, in + (long long)j * a.in_blk_stride, a.lay, off, len);
-      else
-        b2_copy_bytes<false>(mine + (size_t)j * a.blk_stride + off, in + (size_t)j * a.blk_bytes + off, len);
-    }
-    b2_barrier_all(c, ++e, a.opcode);
-    if (a.vec_ok) {
-      // all sources of a vector are loaded before any is stored: the NVLink round trips of the
-      // P pulls overlap instead of adding up (one latency instead of P)
-      const size_t nv = len >> 4, tail = len & 15;
-      for (size_t i = threadIdx.x; i < nv; i += blockDim.x) {
-        uint4 v[B2_MAX_RANKS];
-#pragma unroll
-        for (int s = 0; s < B2_MAX_RANKS; ++s)
-          if (s < a.nsrc) {
-            const int k = (s + c.rank) % a.nsrc;      // stagger peers across ranks
-            v[s] = b2_ld_peer16(c.stage[a.src_rank[k]] + par + (size_t)a.src_blk[k] * a.blk_stride +
-                                off + (i << 4));
-          }
-#pragma unroll
-        for (int s = 0; s < B2_MAX_RANKS; ++s)
-          if (s < a.nsrc) {
-            const int k = (s + c.rank) % a.nsrc;
-            b2_st16(out + (size_t)a.dst_blk[k] * a.blk_bytes + off + (i << 4), v[s]);
-          }
-      }
-      if (tail) {
-        for (int s = 0; s < a.nsrc; ++s)
-          if (threadIdx.x < tail) {
-            const size_t b = (nv << 4) + threadIdx.x;
-            out[(size_t)a.dst_blk[s] * a.blk_bytes + off + b] =
-                ((const volatile char*)(c.stage[a.src_rank[s]] + par + (size_t)a.src_blk[s] * a.blk_stride + off))[b];
-          }
-      }
+  // the fused loop moves whole 16-byte vectors on both sides
+  const bool fuse = a.vec_ok && a.lay.nd == 0 && ((((uintptr_t)in) & 15) == 0) && (a.nin <= 1 || (a.blk_bytes & 15) == 0);
+#define CH_OFF(ch) ((ch) * a.chunk)
+#define CH_LEN(ch) ((a.blk_bytes - CH_OFF(ch) < a.chunk) ? (a.blk_bytes - CH_OFF(ch)) : a.chunk)
+  size_t ch = blockIdx.x;
+  unsigned e_cur = e;
+  if (ch < nchunks) {
+    move_stage(a, mine, in, CH_OFF(ch), CH_LEN(ch));
+    b2_barrier_arrive(c, ++e);
+    e_cur = e;
+  }
+  for (; ch < nchunks; ch += gridDim.x) {
+    const size_t nxt = ch + gridDim.x;
+    const bool more = nxt < nchunks;
+    const size_t off = CH_OFF(ch), len = CH_LEN(ch);
+    const size_t noff = more ? CH_OFF(nxt) : 0, nlen = more ? CH_LEN(nxt) : 0;
+    b2_barrier_wait(c, e_cur, a.opcode);            // every rank staged this chunk
+    if (fuse && a.nin <= 1 && a.nsrc <= 8) {
+      if (a.nsrc <= 1) move_pull_and_stage<1, 1, 4, false>(c, a, par, mine, in, out, off, len, noff, nlen);
+      else if (a.nsrc <= 3) move_pull_and_stage<3, 1, 2, false>(c, a, par, mine, in, out, off, len, noff, nlen);
+      else move_pull_and_stage<8, 1, 1, false>(c, a, par, mine, in, out, off, len, noff, nlen);
+    } else if (fuse && a.nsrc <= 8 && a.nin <= 8) {       // alltoall, the root of a scatter
+      if (a.nsrc <= 2 && a.nin <= 2) move_pull_and_stage<2, 2, 2, false>(c, a, par, mine, in, out, off, len, noff, nlen);
+      else if (a.nsrc <= 4 && a.nin <= 4) move_pull_and_stage<4, 4, 1, false>(c, a, par, mine, in, out, off, len, noff, nlen);
+      else move_pull_and_stage<8, 8, 1, true>(c, a, par, mine, in, out, off, len, noff, nlen);
     } else {
-      for (int s = 0; s < a.nsrc; ++s) {
-        const int k = (s + c.rank) % a.nsrc;
+      for (int s2 = 0; s2 < a.nsrc; ++s2) {
+        const int k = (s2 + c.rank) % a.nsrc;
         b2_copy_bytes<true>(out + (size_t)a.dst_blk[k] * a.blk_bytes + off,
-                            c.stage[a.src_rank[k]] + par + (size_t)a.src_blk[k] * a.blk_stride + off,
-                            len);
+                            c.stage[a.src_rank[k]] + par + (size_t)a.src_blk[k] * a.blk_stride + off, len);
       }
+      if (more) move_stage(a, mine, in, noff, nlen);
+    }
+    if (more) {
+      b2_barrier_arrive(c, ++e);
+      e_cur = e;
     }
   }
+#undef CH_OFF
+#undef CH_LEN
   __syncthreads();
   if (threadIdx.x == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
   b2_finish_bump(c.ticket, c.ticket + 1, 1u, gridDim.x);
@@ -235,6 +342,11 @@ b2_k_allreduce_nvls(const B2DevComm c, const B2ReduceArgs a) {
   const bool pipe = a.pipeline != 0;
   unsigned e_a1 = e;
   bool staged = false;
+  // phase timeline of CTA 0 (debug option "trace_ptr"): %globaltimer after every phase
+  int tr_n = 0;
+#define TRACE() do { if (a.trace != nullptr && blockIdx.x == 0) { __syncthreads(); \
+    if (t == 0 && tr_n < a.trace_cap) a.trace[tr_n] = b2_gtime(); ++tr_n; } } while (0)
+  TRACE();
   for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const size_t nxt = ch + gridDim.x;
     const bool more = pipe && nxt < nchunks;
@@ -243,9 +355,13 @@ b2_k_allreduce_nvls(const B2DevComm c, const B2ReduceArgs a) {
       b2_barrier_arrive(c, ++e);                                 // A1
       e_a1 = e;
     }
+    TRACE();                                                     // 1: staged (or nothing)
     if (more) b2_copy_bytes<false>(mine + CH_OFF(nxt), in + CH_OFF(nxt), CH_LEN(nxt));
+    TRACE();                                                     // 2: next chunk staged
     b2_barrier_wait(c, e_a1, a.opcode);                          // W1: every rank staged this chunk
+    TRACE();                                                     // 3: W1
     b2_nvls_slice<DT>(c, mc, CH_OFF(ch), CH_LEN(ch));
+    TRACE();                                                     // 4: in-switch reduction + broadcast issued
     b2_barrier_arrive(c, ++e);                                   // A2
     const unsigned e_a2 = e;
     staged = more;
@@ -254,8 +370,11 @@ b2_k_allreduce_nvls(const B2DevComm c, const B2ReduceArgs a) {
       e_a1 = e;
     }
     b2_barrier_wait(c, e_a2, a.opcode);                          // W2: every sub-slice has landed here
+    TRACE();                                                     // 5: W2
     b2_copy_bytes<true>(out + CH_OFF(ch), mine + CH_OFF(ch), CH_LEN(ch));
+    TRACE();                                                     // 6: copied out
   }
+#undef TRACE
 #undef CH_OFF
 #undef CH_LEN
   __syncthreads();
@@ -283,7 +402,18 @@ b2_k_bcast_mc(const B2DevComm c, const B2MoveArgs a, const int root) {
     const size_t len = (a.blk_bytes - off < a.chunk) ? (a.blk_bytes - off) : a.chunk;
     if (c.rank == root) {
       const size_t nv = len >> 4, tail = len & 15;
-      for (size_t i = t; i < nv; i += nt) b2_mc_st(mc + off + (i << 4), b2_ld_stream16(in + off + (i << 4)));
+      size_t i = t;
+      for (; i + 3 * (size_t)nt < nv; i += 4 * (size_t)nt) {       // four HBM loads in flight per thread
+        const uint4 v0 = b2_ld_stream16(in + off + (i << 4));
+        const uint4 v1 = b2_ld_stream16(in + off + ((i + nt) << 4));
+        const uint4 v2 = b2_ld_stream16(in + off + ((i + 2 * (size_t)nt) << 4));
+        const uint4 v3 = b2_ld_stream16(in + off + ((i + 3 * (size_t)nt) << 4));
+        b2_mc_st(mc + off + (i << 4), v0);
+        b2_mc_st(mc + off + ((i + nt) << 4), v1);
+        b2_mc_st(mc + off + ((i + 2 * (size_t)nt) << 4), v2);
+        b2_mc_st(mc + off + ((i + 3 * (size_t)nt) << 4), v3);
+      }
+      for (; i < nv; i += nt) b2_mc_st(mc + off + (i << 4), b2_ld_stream16(in + off + (i << 4)));
       if (tail && t == 0) {
         alignas(16) unsigned char tmp[16] = {0};
         for (size_t k = 0; k < tail; ++k) tmp[k] = ((const unsigned char*)in)[off + (nv << 4) + k];
@@ -312,21 +442,69 @@ b2_k_reduce_root_nvls(const B2DevComm c, const B2ReduceArgs a) {
   const char* mc = c.stage_mc + par;
   const size_t nchunks = (a.nbytes + a.chunk - 1) / a.chunk;
   const int t = threadIdx.x, nt = blockDim.x;
-  for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const size_t off = ch * a.chunk;
-    const size_t len = (a.nbytes - off < a.chunk) ? (a.nbytes - off) : a.chunk;
-    b2_copy_bytes<false>(mine + off, in + off, len);
-    b2_barrier_all(c, ++e, a.opcode);
+#define CH_OFF(ch) ((ch) * a.chunk)
+#define CH_LEN(ch) ((a.nbytes - CH_OFF(ch) < a.chunk) ? (a.nbytes - CH_OFF(ch)) : a.chunk)
+  // software pipeline: the next chunk is staged while this one is reduced -- on the root in the SAME
+  // loop as the multimem.ld_reduce, so the switch round trips and the HBM loads overlap
+  size_t ch = blockIdx.x;
+  unsigned e_cur = e;
+  if (ch < nchunks) {
+    b2_copy_bytes<false>(mine + CH_OFF(ch), in + CH_OFF(ch), CH_LEN(ch));
+    b2_barrier_arrive(c, ++e);
+    e_cur = e;
+  }
+  const bool vec_in = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+  for (; ch < nchunks; ch += gridDim.x) {
+    const size_t nxt = ch + gridDim.x;
+    const bool more = nxt < nchunks;
+    const size_t off = CH_OFF(ch), len = CH_LEN(ch);
+    const size_t noff = more ? CH_OFF(nxt) : 0, nlen = more ? CH_LEN(nxt) : 0;
+    b2_barrier_wait(c, e_cur, a.opcode);              // every rank staged this chunk
+    size_t staged = 0;                                // vectors of the next chunk staged by the fused loop
     if (a.has_out) {
       const size_t nv = (len + 15) >> 4;
-      for (size_t i = t; i < nv; i += nt) {
+      const size_t nfull = len >> 4;                  // whole output vectors
+      const size_t nvi = vec_in ? (nlen >> 4) : 0;
+      const size_t both = (nfull < nvi ? nfull : nvi) / (2 * (size_t)nt) * (2 * (size_t)nt);
+      for (size_t base = 0; base < both; base += 2 * (size_t)nt) {
+        const size_t i0 = base + t, i1 = i0 + nt;
+        const uint4 r0 = b2_mc_ld_reduce<DT>(mc + off + (i0 << 4));
+        const uint4 r1 = b2_mc_ld_reduce<DT>(mc + off + (i1 << 4));
+        const uint4 s0 = b2_ld_stream16(in + noff + (i0 << 4));
+        const uint4 s1 = b2_ld_stream16(in + noff + (i1 << 4));
+        b2_st16(out + off + (i0 << 4), r0);
+        b2_st16(out + off + (i1 << 4), r1);
+        b2_st16(mine + noff + (i0 << 4), s0);
+        b2_st16(mine + noff + (i1 << 4), s1);
+      }
+      staged = both;
+      size_t i = both + t;
+      for (; i + 3 * (size_t)nt < nfull; i += 4 * (size_t)nt) {
+        const uint4 r0 = b2_mc_ld_reduce<DT>(mc + off + (i << 4));
+        const uint4 r1 = b2_mc_ld_reduce<DT>(mc + off + ((i + nt) << 4));
+        const uint4 r2 = b2_mc_ld_reduce<DT>(mc + off + ((i + 2 * (size_t)nt) << 4));
+        const uint4 r3 = b2_mc_ld_reduce<DT>(mc + off + ((i + 3 * (size_t)nt) << 4));
+        b2_st16(out + off + (i << 4), r0);
+        b2_st16(out + off + ((i + nt) << 4), r1);
+        b2_st16(out + off + ((i + 2 * (size_t)nt) << 4), r2);
+        b2_st16(out + off + ((i + 3 * (size_t)nt) << 4), r3);
+      }
+      for (; i < nv; i += nt) {
         const uint4 r = b2_mc_ld_reduce<DT>(mc + off + (i << 4));
-        const size_t b = i << 4;
-        if (b + 16 <= len) b2_st16(out + off + b, r);
-        else b2_store_partial(out + off + b, r, (int)(len - b));
+        const size_t b2 = i << 4;
+        if (b2 + 16 <= len) b2_st16(out + off + b2, r);
+        else b2_store_partial(out + off + b2, r, (int)(len - b2));
       }
     }
+    if (more) {
+      const size_t done = staged << 4;
+      b2_copy_bytes<false>(mine + noff + done, in + noff + done, nlen - done);
+      b2_barrier_arrive(c, ++e);
+      e_cur = e;
+    }
   }
+#undef CH_OFF
+#undef CH_LEN
   __syncthreads();
   if (t == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
   b2_finish_bump(c.ticket, c.ticket + 1, 1u, gridDim.x);
@@ -337,15 +515,41 @@ b2_k_reduce_root_nvls(const B2DevComm c, const B2ReduceArgs a) {
 // ---------------------------------------------------------------------------
 static size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
-// Same answer on every rank: depends only on (nbytes, size, max_blocks).  max_blocks is the number of
-// CTAs of a 512-thread collective kernel that are co-resident (one per SM): every CTA of a launch
-// is then resident at once, so the block-paired barriers cannot wait for a CTA that has not been
-// scheduled yet -- independent of the order in which the hardware dispatches CTAs.
-static void pick_chunks(const B2Comm* c, size_t nbytes, size_t* chunk_out, int* grid_out) {
+// How many CTAs of `kernel` (B2_THREADS threads, no dynamic shared memory) are resident at the same
+// time on this GPU: occupancy x SM count, bounded by the communicator's max_blocks.  A launch of at
+// most that many CTAs has every CTA resident at once whatever order the hardware dispatches them in,
+// so the block-paired barriers cannot wait for a CTA that has not been scheduled yet (if other work
+// owns the SMs the launch starts late, it does not deadlock: tests/test_coresidency.py).  The 64-register
+// kernels (NVLS allreduce, multicast bcast, reduce-to-root) fit twice per SM -- and their bandwidth
+// is proportional to the CTA count up to the link limit (profiles/r2_bw_probe_*.log).
+#include <map>
+static int coresident_blocks(const B2Comm* c, const void* kernel) {
+  static std::map<const void*, int> per_sm;
+  int n = 1;
+  if (kernel != nullptr) {
+    auto it = per_sm.find(kernel);
+    if (it == per_sm.end()) {
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, B2_THREADS, 0) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 1;
+      }
+      it = per_sm.emplace(kernel, occ).first;
+    }
+    n = it->second;
+  }
+  long long cap = (long long)n * c->sm_count;
+  if (cap > c->max_blocks) cap = c->max_blocks;
+  if (cap > B2_MAX_BLOCKS) cap = B2_MAX_BLOCKS;
+  return (int)cap;
+}
+
+// Same answer on every rank: depends only on (nbytes, size, the grid cap).
+static void pick_chunks(const B2Comm* c, size_t nbytes, int cap, size_t* chunk_out, int* grid_out) {
   const size_t unit = 16 * (size_t)c->dev.size;
   const size_t min_chunk = round_up(16 * 1024, unit);
   const size_t max_chunk = round_up(512 * 1024, unit);
-  const size_t target = (size_t)c->max_blocks;
+  const size_t target = (size_t)(cap < 1 ? 1 : cap);
   // >= 4 MiB: at least two chunks per CTA, so that the software pipeline of the kernels (stage the
   // next chunk / copy the previous one out while the flags of this one travel) has something to
   // overlap and CTAs drift to different phases; below that one chunk per CTA (latency regime)
@@ -439,8 +643,18 @@ static int reduce_common(B2Comm* c, const void* in, void* out, size_t count, int
   a.in = in; a.out = out; a.nbytes = nbytes;
   a.src_lo = src_lo; a.src_hi = src_hi; a.has_out = has_out; a.opcode = opcode;
   a.pipeline = c->nvls_pipeline;
+  a.trace = c->trace; a.trace_cap = c->trace_cap;
   int grid;
-  pick_chunks(c, nbytes, &a.chunk, &grid);
+  const void* kern = nullptr;
+  if (algo == B2_ALGO_NVLS) {
+    if (opcode == B2_OPC_REDUCE)
+      kern = dtype == B2_F32 ? (const void*)b2_k_reduce_root_nvls<B2_F32>
+             : dtype == B2_BF16 ? (const void*)b2_k_reduce_root_nvls<B2_BF16> : (const void*)b2_k_reduce_root_nvls<B2_F16>;
+    else
+      kern = dtype == B2_F32 ? (const void*)b2_k_allreduce_nvls<B2_F32>
+             : dtype == B2_BF16 ? (const void*)b2_k_allreduce_nvls<B2_BF16> : (const void*)b2_k_allreduce_nvls<B2_F16>;
+  }
+  pick_chunks(c, nbytes, coresident_blocks(c, kern), &a.chunk, &grid);     // (typed kernels: one CTA per SM)
   if (algo == B2_ALGO_NVLS) {
     if (c->dev.stage_mc == nullptr || op != B2_SUM ||
         !(dtype == B2_F32 || dtype == B2_BF16 || dtype == B2_F16)) {
@@ -537,7 +751,7 @@ static int move_common(B2Comm* c, B2MoveArgs& a, const char* name, cudaStream_t 
   a.blk_stride = round_up(a.blk_bytes, 16);
   a.vec_ok = ((((uintptr_t)a.out) & 15) == 0 && (a.blk_bytes % 16 == 0 || a.nsrc <= 1)) ? 1 : 0;
   int grid;
-  pick_chunks(c, a.blk_bytes, &a.chunk, &grid);
+  pick_chunks(c, a.blk_bytes, coresident_blocks(c, (const void*)b2_k_move), &a.chunk, &grid);
   b2_k_move<<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
   return finish_launch(c, cudaGetLastError(), name);
 }
@@ -605,7 +819,7 @@ extern "C" int b2_bcast(B2Comm* c, const void* in, void* out, size_t nbytes, int
           rc = B2_ERR_BAD_ARG;
         } else {
           int grid;
-          pick_chunks(c, a.blk_bytes, &a.chunk, &grid);
+          pick_chunks(c, a.blk_bytes, coresident_blocks(c, (const void*)b2_k_bcast_mc), &a.chunk, &grid);
           b2_k_bcast_mc<<<grid, B2_THREADS, 0, stream>>>(c->dev, a, root);
           rc = finish_launch(c, cudaGetLastError(), "bcast");
         }

@@ -32,6 +32,8 @@ struct B2ReduceArgs {
   int has_out;       // this rank materialises a result (reduce: root only)
   int opcode;
   int pipeline;      // NVLS allreduce: stage the next chunk / copy the previous one out between arrive and wait
+  unsigned long long* trace;   // optional phase timeline of CTA 0 (communicator option "trace_ptr"), else null
+  int trace_cap;
 };
 
 template <typename T, int OP>

@@ -433,9 +433,11 @@ extern "C" B2Comm* b2_comm_create(int device, int rank, int nranks, B2Seg* ctl, 
   c->nvls_min = 64 * 1024 + 1;
   c->bcast_mc_min = 256 * 1024;
   c->nvls_pipeline = 1;
+  c->trace = nullptr;
+  c->trace_cap = 0;
   // one 512-thread CTA of the collective kernels (<= 128 registers per thread) fits per SM: grids are
   // capped at the co-resident count (see pick_chunks in b2_collectives.cu)
-  c->max_blocks = c->sm_count;
+  c->max_blocks = 2 * c->sm_count;       // upper bound; every launch is further capped at its kernel's co-resident count
   if (c->max_blocks > B2_MAX_BLOCKS) c->max_blocks = B2_MAX_BLOCKS;
   cudaDeviceSynchronize();
   return c;
@@ -465,6 +467,8 @@ extern "C" int b2_comm_set_tuning(B2Comm* c, long long ll_max, long long oneshot
 extern "C" int b2_comm_set_option(B2Comm* c, const char* key, long long value) {
   if (strcmp(key, "bcast_mc_min") == 0) c->bcast_mc_min = (size_t)value;
   else if (strcmp(key, "nvls_pipeline") == 0) c->nvls_pipeline = value != 0;
+  else if (strcmp(key, "trace_ptr") == 0) c->trace = (unsigned long long*)(uintptr_t)value;
+  else if (strcmp(key, "trace_cap") == 0) c->trace_cap = (int)value;
   else { b2_set_error("unknown communicator option '%s'", key); return B2_ERR_BAD_ARG; }
   return 0;
 }

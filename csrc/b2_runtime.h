@@ -54,6 +54,8 @@ struct B2Comm {
   size_t nvls_min;
   size_t bcast_mc_min;          // bcast: root multimem.st from this size on
   int nvls_pipeline;            // software-pipelined NVLS allreduce (default on)
+  unsigned long long* trace;    // device buffer for the phase timeline of CTA 0 (scripts/allreduce_phases.py)
+  int trace_cap;
   int max_blocks;
   B2ErrorRecord* err_host;      // host pointer of the mapped error record
   int launches;                 // kernels launched through this communicator

@@ -9,15 +9,15 @@
 // result (h', u', v') is exchanged ONCE, three cells deep, and everything the other two exchanges
 // used to deliver is recomputed from it on a thin frame around the block:
 //
-//   frame kernel A   h', u', v' on the cells within 3 of the block edge.  The fluxes a ring cell
-//                    needs from its neighbours' side of the edge are evaluated locally, each
-//                    with the operands its OWNER would have used (see "views" below).
+//   frame kernel A   h', u', v' on the cells within 3 of the block edge (u', v' two cells further: the
+//                    "band").  The fluxes a ring cell needs from its neighbours' side of the edge are
+//                    evaluated locally, each with the operands its OWNER would have used (see "views").
 //   exchange X       3 layers of (h', u', v') to all eight neighbours (b2_swe_ca.cu).
 //   frame kernel D   friction (u' -> u'', v' -> v'') on the frame, and the neighbours' u'', v''
 //                    one / two cells beyond the edge, which next step's halo fluxes need.
-//   bulk kernel      the whole step in one pass over memory on everything else (b2_swe_strip.cuh):
-//                    its dependency cone stays inside the step's input arrays, so it needs nothing
-//                    from X and runs concurrently with A -> X -> D.
+//   bulk kernels     flux + tendency, then friction, on everything else (b2_swe_k12_body.cuh): their
+//                    dependency cone stays inside the step's input arrays and kernel A's band, so they
+//                    need nothing from X and run concurrently with A -> X -> D.
 //
 // Views.  The reference's discrete system is decomposition dependent: a rank computes its
 // fluxes from u, v whose HALO is stale by the friction update (the halo of u, v is exchanged
@@ -316,7 +316,7 @@ __device__ __forceinline__ void swe_ca_fric_ext_finish(const CACtx& c, float* __
   }
 }
 // ---- task enumeration ----------------------------------------------------------------------------
-// Bulk (b2_swe_strip.cuh) = rows [4, ny-5] x columns [4, cb1); frame = every other interior cell.
+// Bulk (b2_swe_k12_body.cuh) = rows [4, ny-5] x columns [4, cb1); frame = every other interior cell.
 // A band of width w: rows [1, w] and [ny-1-w, ny-2] completely, of the rows in between the columns
 // [1, w] and [ce, nx-2].  Kernel D walks the frame (w = 3, ce = cb1), kernel A the frame plus the two
 // cells beyond it (w = 5, ce = cb1 - 2).

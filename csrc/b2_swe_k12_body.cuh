@@ -1,14 +1,13 @@
-// mpi4jax_b200 -- shallow water, vectorised two-kernel BULK of the communication-avoiding step
-// (b2_swe_ca.cu, MPI4JAX_B200_SWE_BULK=k12): cells at least four away from the block edge, whole
-// float4 groups, no halo; 16 array passes.  The default bulk is the one-pass kernel of
-// b2_swe_strip.cuh (12 passes); this pair is kept as the register-only alternative.
+// mpi4jax_b200 -- shallow water, the vectorised BULK kernels of the communication-avoiding step
+// (b2_swe_ca.cu): cells at least four away from the block edge, whole float4 groups, no halo;
+// 16 array passes per step instead of the stand-alone kernels' 32.
 //
 //  * swe_k12_body   flux + tendency kernels fused.  The stand-alone step writes fe, fn, q, ke in K1
 //                   (4 array passes) only for K2 to read them back (4 more, next to h, u, v a second
 //                   time): 23 passes.  Here the four quantities are recomputed at the stencil
 //                   neighbours of a cell from h, u, v (rows j-1..j+1) and the Adams-Bashforth
-//                   update is applied directly: 12 passes.  u, v are read at neighbouring cells, so
-//                   they are ping-ponged like h.
+//                   update is applied directly: 12 passes.  u', v' go to their own arrays (the friction
+//                   kernel's input), so only h needs a second buffer.
 //  * swe_k345_body  friction phase fused (u' -> u and v' -> v in one kernel).  The stand-alone phase
 //                   is K34 (u' -> u, writes the friction-v fluxes fe2, fn2), exchange(fe2, fn2), K5
 //                   (v' -> v): 9 passes.  A bulk cell's K5 needs fe2 / fn2 only at its own, its west

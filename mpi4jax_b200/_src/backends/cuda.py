@@ -240,10 +240,10 @@ class NativeComm:
         if len({h for h, _ in devs}) != 1:
             raise MPIError("the GPU transport needs all ranks of a communicator on one NVLink node")
         self.shared_gpu = len(set(devs)) != len(devs)   # several ranks on one GPU (testing only)
-        # p2p ring slot: 16 MiB stripes give 614 GB/s on a 256 MiB sendrecv vs 384 GB/s with 4 MiB
-        # (profiles/r1_p2p_slot_size_2gpu.log); the whole ring area is capped at 256 MiB per rank
-        # (8 ranks: 4 MiB slots, the configuration of the 8-GPU measurements in profiles/)
-        slot = env_int("MPI4JAX_B200_P2P_SLOT_BYTES", min(16 << 20, (256 << 20) // (comm.size * 8)))
+        # p2p ring slot: 16 MiB stripes give 625 GB/s on a 256 MiB sendrecv, 4 MiB ones 380 GB/s (one
+        # header + credit round per 64 KiB lane stripe: profiles/r2_sweep_n8.log vs r2_p2p_n2.log).  The ring
+        # area is P x 8 slots per rank -- 1 GiB at 8 ranks, 0.6 % of a B200's HBM
+        slot = env_int("MPI4JAX_B200_P2P_SLOT_BYTES", 16 << 20)
         ll_cap = env_int("MPI4JAX_B200_LL_BYTES", 128 << 10)
         halo_cap = env_int("MPI4JAX_B200_HALO_BYTES", 256 << 10)
         timeout = env_float("MPI4JAX_B200_TIMEOUT", 60.0)

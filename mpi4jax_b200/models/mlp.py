@@ -66,11 +66,16 @@ class ParallelMLP:
     def step(self, x, y, lr: float = 1e-2) -> torch.Tensor:
         """One SGD step; returns the (global) loss.  In dp mode the gradient of the bcast
         parameters arrives on the root already summed over ranks (reduce-to-root VJP)."""
-        for p in self.parameters():
-            p.grad = None
+        params = list(self.parameters())
         loss = self.loss(x, y)
-        loss.backward()
+        # autograd.grad, not loss.backward(): no AccumulateGrad nodes, whose stream bookkeeping (they
+        # belong to the stream the parameter was created on) invalidates a CUDA-graph capture of the
+        # step (mpi4jax_b200.jit(mlp.step): forward, backward through the collectives' VJPs and update
+        # as ONE graph -- BASELINE config 5, bench/mlp_grad.py)
+        grads = torch.autograd.grad(loss, params, allow_unused=True)
         with torch.no_grad():
-            for p in self.parameters():
-                p -= lr * p.grad
+            for p, g in zip(params, grads):
+                p.grad = g
+                if g is not None:
+                    p -= lr * g
         return loss.detach()

@@ -78,7 +78,7 @@ void emu_k34(const B2SweParams* p, const float* u, float* u_new, const float* v,
     }
 }
 
-// ---- communication-avoiding step (csrc/b2_swe_ca_body.cuh, b2_swe_strip.cuh): the kernels of
+// ---- communication-avoiding step (csrc/b2_swe_ca_body.cuh, b2_swe_k12_body.cuh): the kernels of
 // b2_swe_ca.cu as loops.  `reverse` walks the tasks backwards: a kernel whose threads only read what no
 // thread of the same launch (or phase) writes gives the same bits in any order.
 static CACtx make_ctx(const B2SweParams* p, const B2SweCA* x, const EmuStep* e) {

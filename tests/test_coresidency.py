@@ -1,8 +1,8 @@
 """The collective kernels synchronise their CTAs with each other and with the peer GPUs' CTAs
 (csrc/b2_device.cuh: b2_barrier_all, the block-paired cross-GPU barrier).  That is only safe if every
 CTA of a launch can be resident at the same time whatever else the GPU is running: the launch grids
-are capped at the co-resident count (csrc/b2_collectives.cu: pick_chunks, max_blocks = SM count), so a
-collective that is launched while other kernels own the SMs starts late but never deadlocks.
+are capped at the kernel's co-resident count (csrc/b2_collectives.cu: coresident_blocks = occupancy x SM
+count), so a collective that is launched while other kernels own the SMs starts late but never deadlocks.
 
 The reference has no counterpart (its collectives are MPI calls issued from a host callback,
 mpi_xla_bridge_cuda.cpp); round 1's review asked for this property to be tested, not assumed."""
@@ -61,9 +61,12 @@ def test_collectives_complete_while_other_kernels_own_the_sms(nbytes):
 
 @pytest.mark.gpu
 def test_launch_grids_fit_the_gpu():
-    """Every collective launch is capped at one CTA per SM (the co-resident bound the barrier needs)."""
+    """Every collective launch is capped at its kernel's co-resident CTA count (occupancy x SMs, the bound
+    the barrier needs), itself bounded by the communicator's max_blocks: never more than two 512-thread
+    CTAs per SM."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     nc = comm._native_comm()
     sms = torch.cuda.get_device_properties(comm.device).multi_processor_count
-    assert 1 <= nc.max_blocks <= sms
+    assert nc.get_option("sm_count") == sms
+    assert 1 <= nc.max_blocks <= 2 * sms

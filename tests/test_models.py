@@ -50,6 +50,35 @@ def test_mlp_tensor_parallel_matches_dense(device):
     assert torch.allclose(mlp.w2.detach().cpu(), w2.detach()[rank * k:(rank + 1) * k])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["dp", "tp"])
+def test_mlp_training_step_as_one_cuda_graph(mode):
+    """mpi4jax_b200.jit(mlp.step): forward, backward through the collectives' VJPs and the update are
+    captured into ONE CUDA graph (the reference's headline use: jax.grad of a jitted loss that
+    calls allreduce / bcast, README.rst:59-96); replays match eager steps of a twin model."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    if mode == "tp" and 8 % size != 0:
+        pytest.skip("hidden size 8 must divide")
+    dev = comm.device
+    g = torch.Generator().manual_seed(11 + (rank if mode == "dp" else 0))
+    x = torch.randn(5, 6, generator=g).to(dev)
+    y = torch.randn(5, 3, generator=g).to(dev)
+    a = ParallelMLP(6, 8, 3, comm=comm, device=dev, dtype=torch.float32, mode=mode)
+    b = ParallelMLP(6, 8, 3, comm=comm, device=dev, dtype=torch.float32, mode=mode)
+    with torch.no_grad():
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            pb.copy_(pa)
+    fast = m.jit(lambda u, v: b.step(u, v, lr=0.1))
+    for _ in range(4):                      # call 1 warms up eagerly, call 2 captures, 3.. replay
+        la = a.step(x, y, lr=0.1)
+        lb = fast(x, y)
+        assert torch.allclose(la, lb, rtol=1e-5, atol=1e-6)
+    m.flush()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6)
+
+
 def test_parallel_patterns(device):
     from mpi4jax_b200.parallel import (alltoall_reshard, average_gradients, broadcast_parameters,
                                        cartesian_neighbors, ring_shift)
