@@ -428,6 +428,37 @@ def allreduce_sweep(m, MPI, comm, dev):
                                 "busbw": round(nbytes / us / 1e3 * 2 * (size - 1) / size, 1)}
             del f, x
         res[name] = row
+    # the same reduction on SYMMETRIC tensors, in place (mpi4jax_b200.symmetric_empty / allreduce_): no
+    # staging copies around the in-switch reduction
+    if size > 1 and comm._native_comm().has_nvls:
+        pool = m.symmetric_empty((1 << 30,), torch.uint8, comm=comm)
+        row = {}
+        for nbytes in (1 << 10, 1 << 14, 1 << 17, 1 << 20, 1 << 23, 1 << 26, 1 << 28, 1 << 30):
+            x = pool[:nbytes].view(torch.float32)
+            x.fill_(1.0)
+            reps = 20 if nbytes <= (1 << 23) else 5
+
+            def body(t, reps=reps):
+                for _ in range(reps):
+                    m.allreduce_(t, comm=comm)
+                return t
+
+            f = m.jit(body, warmup=1, donate_outputs=True, static_inputs=True)
+            f(x)
+            f(x)
+            x.fill_(1.0)
+            torch.cuda.synchronize()
+            comm.Barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            f(x)
+            e.record()
+            e.synchronize()
+            us = max_over_ranks(s.elapsed_time(e), comm) * 1e3 / reps
+            row[str(nbytes)] = {"us": round(us, 2),
+                                "busbw": round(nbytes / us / 1e3 * 2 * (size - 1) / size, 1)}
+            del f
+        res["fp32_symmetric_inplace"] = row
     return res
 
 

@@ -124,6 +124,9 @@ sizes = [] if ns.only_p2p else [1 << k for k in range(10, 31, 2 if ns.quick else
 result = {"world": size, "nvls": has_nvls, "allreduce": {}, "allgather": {}, "alltoall": {}, "p2p": {}}
 
 # ---------------------------------------------------------------- allreduce
+sym_pool = None
+if sizes and size > 1 and dev.type == "cuda":
+    sym_pool = m.symmetric_empty((max(sizes),), torch.uint8, comm=comm)
 for dtype, dname in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
     table = {}
     for nbytes in sizes:
@@ -145,6 +148,15 @@ for dtype, dname in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
         if nccl is not None:
             us = time_nccl(lambda: dist.all_reduce(x, group=nccl), reps)
             row["nccl"] = {"us": round(us, 2), "busbw": round(nbytes / us / 1e3 * 2 * (size - 1) / size, 1)}
+        if sym_pool is not None and has_nvls and nbytes >= 16:
+            # the same reduction on a SYMMETRIC tensor, in place (no staging copies): mpi4jax_b200.allreduce_
+            xs = sym_pool[: nbytes].view(dtype)
+            xs.fill_(1)
+            try:
+                us = time_graph(lambda: m.allreduce_(xs, comm=comm), reps)
+                row["sym"] = {"us": round(us, 2), "busbw": round(nbytes / us / 1e3 * 2 * (size - 1) / size, 1)}
+            except Exception as exc:
+                row["sym"] = {"error": str(exc)[:120]}
         table[str(nbytes)] = row
         if rank == 0:
             print(dname, nbytes, {k: (v.get("us"), v.get("busbw")) for k, v in row.items()}, flush=True)

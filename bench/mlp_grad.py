@@ -102,7 +102,11 @@ for mode, dtype in (("dp", torch.float32), ("tp", torch.float32), ("tp", torch.b
         fast(x, y)
         row["jit_us"] = round(timed(lambda: fast(x, y), ns.steps), 1)
     except Exception as exc:  # pragma: no cover - capture of the autograd engine failed
+        import traceback
+
         row["jit_error"] = str(exc)[:200]
+        if rank == 0:
+            traceback.print_exc()
     flops = 6 * ns.batch * (ns.d_in * ns.d_hidden / (size if mode == "tp" else 1) + ns.d_hidden * ns.d_out
                             / (size if mode == "tp" else 1))
     row["tflops_per_gpu_jit"] = round(flops / row.get("jit_us", row["eager_us"]) / 1e6, 2)

@@ -383,6 +383,48 @@ b2_k_allreduce_nvls(const B2DevComm c, const B2ReduceArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// allreduce of a SYMMETRIC tensor, in place (mpi4jax_b200.symmetric_empty / allreduce_): the buffer
+// lives in a multicast-bound segment at the same offset on every rank, so there is nothing to stage
+// and nothing to copy out -- barrier, every rank reduces its 1/P of the vectors inside the switch
+// (multimem.ld_reduce) and broadcasts them back through it (multimem.st), barrier.  No chunks: the
+// two barriers are the only synchronisation, the links are busy in between.
+// ---------------------------------------------------------------------------
+struct B2SymArgs {
+  char* mc;          // multicast address of the buffer
+  size_t nbytes;     // multiple of 16
+  int opcode;
+};
+template <int DT>
+__global__ void __launch_bounds__(B2_THREADS)
+b2_k_allreduce_sym(const B2DevComm c, const B2SymArgs a) {
+  unsigned e = b2_ld_volatile(c.epoch + blockIdx.x);
+  b2_barrier_all(c, ++e, a.opcode);                  // every rank's kernels that wrote the buffer are done
+  const int t = threadIdx.x, nt = blockDim.x;
+  const size_t nv = a.nbytes >> 4;
+  const size_t per = (nv + c.size - 1) / c.size;     // this rank's slice of the vectors
+  size_t v0 = per * (size_t)c.rank;
+  if (v0 > nv) v0 = nv;
+  size_t v1 = v0 + per;
+  if (v1 > nv) v1 = nv;
+  // tiles of 4 x blockDim vectors, round-robin over the CTAs: four in-switch reductions in flight per thread
+  const size_t tile = 4 * (size_t)nt;
+  for (size_t base = v0 + (size_t)blockIdx.x * tile; base < v1; base += (size_t)gridDim.x * tile) {
+    const size_t i0 = base + t, i1 = i0 + nt, i2 = i1 + nt, i3 = i2 + nt;
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
+    if (i0 < v1) r0 = b2_mc_ld_reduce<DT>(a.mc + (i0 << 4));
+    if (i1 < v1) r1 = b2_mc_ld_reduce<DT>(a.mc + (i1 << 4));
+    if (i2 < v1) r2 = b2_mc_ld_reduce<DT>(a.mc + (i2 << 4));
+    if (i3 < v1) r3 = b2_mc_ld_reduce<DT>(a.mc + (i3 << 4));
+    if (i0 < v1) b2_mc_st(a.mc + (i0 << 4), r0);
+    if (i1 < v1) b2_mc_st(a.mc + (i1 << 4), r1);
+    if (i2 < v1) b2_mc_st(a.mc + (i2 << 4), r2);
+    if (i3 < v1) b2_mc_st(a.mc + (i3 << 4), r3);
+  }
+  b2_barrier_all(c, ++e, a.opcode);                  // every slice has landed everywhere
+  if (t == 0) b2_st_volatile(c.epoch + blockIdx.x, e);
+}
+
+// ---------------------------------------------------------------------------
 // bcast: the root writes its data ONCE with multimem.st -- the NVSwitch replicates it into every
 // rank's staging -- instead of P-1 peers pulling P-1 copies over the root's links
 // ---------------------------------------------------------------------------
@@ -685,6 +727,39 @@ extern "C" int b2_allreduce(B2Comm* c, const void* in, void* out, size_t count, 
   B2DebugScope* dbg = b2_debug_begin(c, "Allreduce", det, stream);
   int rc = reduce_common(c, in, out, count, dtype, op, algo, 0, c->dev.size, 1, B2_OPC_ALLREDUCE,
                          "allreduce", stream);
+  b2_debug_end(dbg, rc);
+  return rc;
+}
+
+// In-place allreduce (SUM; f32 / bf16 / f16) of a buffer inside a multicast-bound symmetric segment;
+// `mc` is the buffer's multicast address (segment multicast base + the buffer's offset).
+extern "C" int b2_allreduce_sym(B2Comm* c, void* mc, size_t count, int dtype, cudaStream_t stream) {
+  char det[96];
+  snprintf(det, sizeof det, "with %zu items (symmetric, in place)", count);
+  B2DebugScope* dbg = b2_debug_begin(c, "Allreduce", det, stream);
+  int rc = 0;
+  const size_t nbytes = count * b2_dtype_size(dtype);
+  if (!(dtype == B2_F32 || dtype == B2_BF16 || dtype == B2_F16)) {
+    b2_set_error("allreduce_: the in-switch reduction supports float32, bfloat16 and float16");
+    rc = B2_ERR_BAD_ARG;
+  } else if (mc == nullptr || (((uintptr_t)mc) & 15) != 0 || (nbytes & 15) != 0) {
+    b2_set_error("allreduce_: the buffer must be 16-byte aligned and a multiple of 16 bytes long");
+    rc = B2_ERR_BAD_ARG;
+  } else if (nbytes > 0) {
+    B2SymArgs a;
+    a.mc = (char*)mc; a.nbytes = nbytes; a.opcode = B2_OPC_ALLREDUCE;
+    const void* kern = dtype == B2_F32 ? (const void*)b2_k_allreduce_sym<B2_F32>
+                       : dtype == B2_BF16 ? (const void*)b2_k_allreduce_sym<B2_BF16> : (const void*)b2_k_allreduce_sym<B2_F16>;
+    // one tile of 4 x 512 vectors (32 KiB) per CTA and round at least; never more CTAs than co-resident
+    const size_t slice = (nbytes / 16 + c->dev.size - 1) / c->dev.size;
+    size_t want = (slice + 4 * B2_THREADS - 1) / (4 * B2_THREADS);
+    int grid = coresident_blocks(c, kern);
+    if (want < (size_t)grid) grid = (int)(want < 1 ? 1 : want);
+    if (dtype == B2_F32) b2_k_allreduce_sym<B2_F32><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
+    else if (dtype == B2_BF16) b2_k_allreduce_sym<B2_BF16><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
+    else b2_k_allreduce_sym<B2_F16><<<grid, B2_THREADS, 0, stream>>>(c->dev, a);
+    rc = finish_launch(c, cudaGetLastError(), "allreduce_");
+  }
   b2_debug_end(dbg, rc);
   return rc;
 }

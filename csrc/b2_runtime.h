@@ -129,6 +129,7 @@ struct B2Strided {
 int b2_barrier(B2Comm* c, cudaStream_t stream);
 int b2_allreduce(B2Comm* c, const void* in, void* out, size_t count, int dtype, int op, int algo,
                  cudaStream_t stream);
+int b2_allreduce_sym(B2Comm* c, void* mc, size_t count, int dtype, cudaStream_t stream);
 int b2_reduce(B2Comm* c, const void* in, void* out, size_t count, int dtype, int op, int root,
               cudaStream_t stream);
 int b2_scan(B2Comm* c, const void* in, void* out, size_t count, int dtype, int op,

@@ -16,6 +16,7 @@ from ._src import (  # noqa: F401
     alltoall,
     barrier,
     bcast,
+    allreduce_,
     comm_reserve,
     flush,
     gather,
@@ -28,6 +29,7 @@ from ._src import (  # noqa: F401
     send,
     send_with_grad,
     sendrecv,
+    symmetric_empty,
 )
 from . import MPI  # noqa: F401
 from ._src.jit import jit, linear_transpose  # noqa: F401
@@ -39,4 +41,5 @@ __all__ = [
     "allgather", "allreduce", "alltoall", "barrier", "bcast", "gather", "recv", "reduce",
     "scan", "scatter", "send", "sendrecv", "has_cuda_support", "has_sycl_support",
     "MPI", "jit", "compiled", "flush", "effects_barrier", "linear_transpose", "send_with_grad", "comm_reserve",
+    "symmetric_empty", "allreduce_",
 ]

@@ -31,4 +31,4 @@ from .collective_ops.send import send, send_with_grad  # noqa: E402,F401
 from .collective_ops.sendrecv import sendrecv  # noqa: E402,F401
 
 from .comm import flush  # noqa: E402,F401
-from .utils import comm_reserve, has_cuda_support, has_sycl_support  # noqa: E402,F401
+from .utils import allreduce_, comm_reserve, has_cuda_support, has_sycl_support, symmetric_empty  # noqa: E402,F401

@@ -257,6 +257,7 @@ class NativeComm:
         self._stage_half = 0
         self._retired: list = []
         self._status_pool: list = []
+        self._symmetric: list = []        # (base pointer, bytes, _Segment) of symmetric_empty allocations
         self._grow_stage(_MIN_STAGE)
         if comm.size > 1:
             dist.barrier(group=comm._group)
@@ -373,6 +374,9 @@ class NativeComm:
         for seg in self._retired:
             seg.destroy()
         self._retired = []
+        for _, _, seg in self._symmetric:
+            seg.destroy()
+        self._symmetric = []
         for rec in self._status_pool:
             lib.b2_status_free(rec)
         del self._status_pool[:]
@@ -392,6 +396,49 @@ class NativeComm:
                                  algo, self._stream())
         self._check(rc, "Allreduce")
         return out
+
+    # -- symmetric tensors: user memory inside the symmetric heap ---------------------------------
+    def symmetric_empty(self, shape, dtype: torch.dtype) -> torch.Tensor:
+        """A tensor whose storage is a symmetric segment of this communicator (same size on every rank,
+        mapped into every peer and bound to an NVSwitch multicast object).  Collective.  The segment
+        lives as long as the communicator."""
+        shape = tuple(int(d) for d in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)))
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        nbytes = max(16, itemsize * int(torch.Size(shape).numel()))
+        sizes = _all_gather_obj(self.comm, nbytes)
+        if len(set(sizes)) != 1:
+            raise MPIError(f"symmetric_empty: every rank must ask for the same size (got {sizes} bytes)")
+        torch.cuda.synchronize(self.device)
+        seg = _Segment(self.comm, self.device, nbytes, self.mode, want_mc=self.want_mc)
+        base = int(_lib().b2_seg_ptr(seg.seg, self.comm.rank))
+        self._symmetric.append((base, seg.bytes, seg))
+        raw = torch.as_tensor(_RawDeviceBytes(base, seg.bytes), device=f"cuda:{self.device}")
+        return raw[: itemsize * int(torch.Size(shape).numel())].view(dtype).reshape(shape)
+
+    def _symmetric_of(self, x: torch.Tensor):
+        ptr = x.data_ptr()
+        for base, nbytes, seg in self._symmetric:
+            if base <= ptr and ptr + x.numel() * x.element_size() <= base + nbytes:
+                return seg, ptr - base
+        return None, 0
+
+    def allreduce_inplace(self, x: torch.Tensor) -> torch.Tensor:
+        """SUM-allreduce of a symmetric tensor IN PLACE, reduced inside the NVSwitch: no staging copy in,
+        none out (csrc/b2_collectives.cu: b2_k_allreduce_sym)."""
+        if self.comm.size == 1:
+            return x
+        seg, off = self._symmetric_of(x)
+        if seg is None or not x.is_contiguous():
+            raise ValueError("allreduce_: needs a contiguous tensor (or view) from mpi4jax_b200.symmetric_empty")
+        if seg.mc is None:
+            raise MPIError("allreduce_: NVLS multicast is unavailable on this communicator")
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise TypeError("allreduce_: the in-switch reduction supports float32, bfloat16 and float16")
+        dt = codes.DTYPE_CODE[x.dtype]
+        mc = int(_lib().b2_mc_ptr(seg.mc)) + off
+        rc = _lib().b2_allreduce_sym(self.handle, mc, x.numel(), dt, self._stream())
+        self._check(rc, "Allreduce")
+        return x
 
     def reduce(self, x: torch.Tensor, op_code: int, root: int) -> Optional[torch.Tensor]:
         x, dt, op_code = _prep_reduce(x, op_code)

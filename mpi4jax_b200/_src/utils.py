@@ -168,3 +168,42 @@ def comm_reserve(nbytes: int, *, comm: Optional[_comm.Comm] = None) -> None:
         native_comm = comm._native_comm()
         if hasattr(native_comm, "reserve"):
             native_comm.reserve(int(nbytes))
+
+
+def symmetric_empty(shape, dtype=None, *, comm: Optional[_comm.Comm] = None):
+    """Uninitialised tensor in the SYMMETRIC heap of ``comm``: the same allocation on every rank, mapped
+    into every peer GPU and bound to an NVSwitch multicast object.  Collectives on ordinary tensors stage
+    their payload through such memory (one local copy in, one out); :func:`allreduce_` on a symmetric
+    tensor skips both.  Collective (every rank must call it with the same shape and dtype); the memory is
+    released with the communicator.  On a CPU communicator this is ``torch.empty``.
+
+    Extension: the reference hands device pointers of XLA buffers to MPI (mpi_xla_bridge_cuda.cpp) and
+    has no notion of registered / symmetric memory."""
+    import torch
+
+    if comm is None:
+        comm = get_default_comm()
+    dtype = dtype or torch.float32
+    if comm.device.type != "cuda":
+        return torch.empty(shape, dtype=dtype)
+    return comm._native_comm().symmetric_empty(shape, dtype)
+
+
+def allreduce_(x, op=None, *, comm: Optional[_comm.Comm] = None):
+    """SUM-allreduce ``x`` IN PLACE and return it.  ``x`` must come from :func:`symmetric_empty` (or be a
+    contiguous view of such a tensor) and be float32 / bfloat16 / float16; the sum is formed inside the
+    NVSwitch (``multimem.ld_reduce``, fp32 accumulation) and written back through it, without staging
+    copies.  Not differentiable.  On a CPU communicator: an ordinary in-place allreduce."""
+    from . import comm as _c
+
+    if comm is None:
+        comm = get_default_comm()
+    if op is not None and op is not _c.SUM:
+        raise NotImplementedError("allreduce_ reduces with MPI.SUM only (what the switch implements)")
+    if comm.device.type != "cuda" or not x.is_cuda:
+        from .collective_ops.allreduce import allreduce as _allreduce
+
+        x.copy_(_allreduce(x, _c.SUM, comm=comm))
+        return x
+    return comm._native_comm().allreduce_inplace(x)
+

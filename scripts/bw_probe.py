@@ -58,7 +58,7 @@ ops = {
     "sendrecv": (lambda: m.sendrecv(x, x, source=(rank - 1) % size, dest=(rank + 1) % size, comm=comm), nbytes),
 }
 sms = nc.get_option("sm_count")
-for mb in ((64, sms) if size > 2 else (32, 64, 96, sms)):
+for mb in ((sms, 2 * sms) if size > 2 else (64, sms, 2 * sms)):
     nc.set_tuning(max_blocks=mb)
     for pipe in (0, 1):
         nc.set_option("nvls_pipeline", pipe)

@@ -184,3 +184,40 @@ def test_large_rooted_ops_and_scan(device, nbytes):
     rb = m.reduce(xb, MPI.SUM, 0, comm=comm)
     if rank == 0:
         assert torch.equal(rb.float(), (torch.arange(n, device=device) % 7).float() * size + size * (size - 1) / 2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n", [4, 1000, 70_000, (1 << 20) + 8])
+def test_symmetric_tensor_allreduce_in_place(device, dtype, n):
+    """Extension: tensors allocated in the symmetric heap are reduced in place inside the NVSwitch
+    (no staging copy in, none out).  The reference has no registered-memory notion to compare with;
+    the oracle is the functional allreduce of the same values."""
+    comm2 = comm
+    x = m.symmetric_empty((n,), dtype, comm=comm2)
+    vals = (torch.arange(n, device=device, dtype=torch.float32) % 13 + rank).to(dtype)
+    x.copy_(vals)
+    want = m.allreduce(vals, MPI.SUM, comm=comm2)
+    if device.type == "cuda" and size > 1 and (n * x.element_size()) % 16:
+        with pytest.raises(Exception, match="16"):
+            m.allreduce_(x, comm=comm2)
+        m.flush()
+        return
+    out = m.allreduce_(x, comm=comm2)
+    assert out.data_ptr() == x.data_ptr()
+    assert torch.equal(out, want)
+    # a contiguous, 16-byte aligned view is fine too; twice in a row reuses the barrier epochs
+    if n >= 1000:
+        view = x[8: 8 + 64]
+        before = view.clone()
+        m.allreduce_(view, comm=comm2)
+        assert torch.equal(view.float(), before.float() * size)
+    with pytest.raises(NotImplementedError):
+        m.allreduce_(x, MPI.MAX, comm=comm2)
+
+
+def test_allreduce_inplace_rejects_ordinary_cuda_tensors(device):
+    if device.type != "cuda" or size == 1:
+        pytest.skip("only the GPU transport distinguishes symmetric memory (and only with peers)")
+    with pytest.raises(ValueError, match="symmetric_empty"):
+        m.allreduce_(torch.ones(64, device=device), comm=comm)
+
