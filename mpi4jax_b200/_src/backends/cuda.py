@@ -434,6 +434,9 @@ class NativeComm:
             raise MPIError("allreduce_: NVLS multicast is unavailable on this communicator")
         if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
             raise TypeError("allreduce_: the in-switch reduction supports float32, bfloat16 and float16")
+        if (x.numel() * x.element_size()) % 16 or off % 16:
+            raise ValueError("allreduce_: the tensor must start on a 16-byte boundary and be a multiple of 16 "
+                             f"bytes long (got {x.numel() * x.element_size()} bytes at offset {off})")
         dt = codes.DTYPE_CODE[x.dtype]
         mc = int(_lib().b2_mc_ptr(seg.mc)) + off
         rc = _lib().b2_allreduce_sym(self.handle, mc, x.numel(), dt, self._stream())

@@ -44,21 +44,22 @@ class ParallelMLP:
     def parameters(self):
         return [self.w1, self.w2]
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, weights=None) -> torch.Tensor:
+        w1_, w2_ = weights if weights is not None else (self.w1, self.w2)
         if self.mode == "tp":
-            h = torch.tanh(x @ self.w1)                       # column-parallel
+            h = torch.tanh(x @ w1_)                           # column-parallel
             if h.is_cuda and h.dtype == torch.bfloat16:
                 # row-parallel GEMM and its allreduce as ONE tcgen05 + multimem.red kernel
                 from ..ops.linear import linear_allreduce
 
-                return linear_allreduce(h, self.w2.t(), comm=self.comm)
-            return ops.allreduce(h @ self.w2, SUM, comm=self.comm)   # row-parallel + sum
-        w1 = ops.bcast(self.w1, 0, comm=self.comm)            # parameters live on the root
-        w2 = ops.bcast(self.w2, 0, comm=self.comm)
+                return linear_allreduce(h, w2_.t(), comm=self.comm)
+            return ops.allreduce(h @ w2_, SUM, comm=self.comm)       # row-parallel + sum
+        w1 = ops.bcast(w1_, 0, comm=self.comm)                # parameters live on the root
+        w2 = ops.bcast(w2_, 0, comm=self.comm)
         return torch.tanh(x @ w1) @ w2
 
-    def loss(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        local = ((self.forward(x) - y) ** 2).mean()
+    def loss(self, x: torch.Tensor, y: torch.Tensor, weights=None) -> torch.Tensor:
+        local = ((self.forward(x, weights) - y) ** 2).mean()
         if self.mode == "tp":
             return local
         return ops.allreduce(local, SUM, comm=self.comm) / self.comm.Get_size()
@@ -67,12 +68,15 @@ class ParallelMLP:
         """One SGD step; returns the (global) loss.  In dp mode the gradient of the bcast
         parameters arrives on the root already summed over ranks (reduce-to-root VJP)."""
         params = list(self.parameters())
-        loss = self.loss(x, y)
-        # autograd.grad, not loss.backward(): no AccumulateGrad nodes, whose stream bookkeeping (they
-        # belong to the stream the parameter was created on) invalidates a CUDA-graph capture of the
-        # step (mpi4jax_b200.jit(mlp.step): forward, backward through the collectives' VJPs and update
-        # as ONE graph -- BASELINE config 5, bench/mlp_grad.py)
-        grads = torch.autograd.grad(loss, params, allow_unused=True)
+        # Differentiate with respect to VIEWS of the parameters, with autograd.grad: the backward pass then
+        # never touches the parameters' AccumulateGrad nodes, which belong to the stream the parameters were
+        # created on (the legacy default stream) -- the engine would make that stream wait for the backward
+        # pass, which is illegal while the step is being captured into a CUDA graph
+        # (mpi4jax_b200.jit(mlp.step): forward, backward through the collectives' VJPs and update as ONE
+        # graph -- BASELINE config 5, bench/mlp_grad.py).
+        views = [p.view_as(p) for p in params]
+        loss = self.loss(x, y, views)
+        grads = torch.autograd.grad(loss, views, allow_unused=True)
         with torch.no_grad():
             for p, g in zip(params, grads):
                 p.grad = g
