@@ -145,15 +145,16 @@ def main() -> int:
     torch.cuda.synchronize()
     comm.Barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(gpu_index=torch.cuda.current_device(), period_s=0.1) as clocks:
+    with ClockSampler(gpu_index=torch.cuda.current_device(), period_s=0.005, first_delay_s=0.003) as clocks:
         torch.cuda.synchronize()
         # The timed window is K steps ON THE DEVICE.  A short spin kernel first: while the GPU sits in it
         # the host enqueues everything below (barrier kernel, start event, the graph launches), so what
         # runs between the two events is the replayed steps and not this process' Python / launch
         # latency (measured before: 20 steps at 8 GPUs took 817 us in the window, 32 us per step in the
-        # device timeline -- the rest was the host getting from `start.record()` to `cudaGraphLaunch`,
-        # which the end-to-end number below accounts for separately).
-        torch.cuda._sleep(int(3e6))                 # ~1.5 ms at 1.9 GHz
+        # device timeline -- the rest was the host getting from `start.record()` to `cudaGraphLaunch`
+        # while eight `nvidia-smi` clock queries started next to it; the clocks are now read through
+        # in-process NVML, and the end-to-end number below accounts for launch latency separately).
+        torch.cuda._sleep(int(4e7))                 # ~20 ms at 1.9 GHz: also covers a descheduled rank process
         # device-side barrier on the stream right before the start event: the ranks' timed windows
         # open together on the GPUs, whatever skew the host-side barrier left between the processes
         m.barrier(comm=comm)

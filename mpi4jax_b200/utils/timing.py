@@ -61,27 +61,72 @@ def device_time_ms(fn: Callable[[], None], iters: int = 10, warmup: int = 3, flu
 
 
 class ClockSampler:
-    """Samples ``nvidia-smi`` clocks / throttle reasons in the background during a timed region."""
+    """Samples SM clocks / throttle reasons in the background during a timed region.
+
+    In-process NVML (``pynvml``) when available: a query costs microseconds, so the samples really fall
+    inside short timed regions and sampling does not disturb them.  The fallback spawns ``nvidia-smi``
+    (tens of milliseconds of CPU and driver locks per query -- on an 8-rank job, eight of them at the
+    moment the ranks enqueue their timed work were measured to skew the ranks against each other by
+    ~100 us), so its first query is delayed."""
 
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int = 0, period_s: float = 0.2):
-        self.gpu_index, self.period_s = gpu_index, period_s
+    def __init__(self, gpu_index: int = 0, period_s: float = 0.2, first_delay_s: float = 0.0):
+        self.gpu_index, self.period_s, self.first_delay_s = gpu_index, period_s, first_delay_s
         self.samples: list = []
+        self.source = "none"
         self._stop = threading.Event()
         self._thread: Optional[threading.Thread] = None
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self._nvml = (pynvml, handle)
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv, h = self._nvml
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            power = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            power = 0.0
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bits = (nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap)
+        self.samples.append([str(sm), str(mx), f"{power:.1f}"] + ["Active" if mask & b else "Not Active" for b in bits])
 
     def _run(self):
+        if self._nvml is None and self._stop.wait(max(self.first_delay_s, 0.05)):
+            return
+        if self._nvml is not None and self.first_delay_s > 0 and self._stop.wait(self.first_delay_s):
+            return
         while not self._stop.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                     "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self.source = "nvidia-smi"
+                    out = subprocess.run(
+                        ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                         "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) >= 7:
+                        self.samples.append(parts)
             except Exception:
                 pass
             self._stop.wait(self.period_s)
@@ -106,4 +151,5 @@ class ClockSampler:
             "sm_max_mhz": max(mx) if mx else None,
             "reasons": reasons,
             "samples": len(self.samples),
+            "source": self.source,
         }
