@@ -57,6 +57,7 @@ struct GemmArgs {
   int M, N, K;
   __nv_bfloat16* out;
   int fused;           // > 1 rank: per-tile NVLS allreduce through the staging segment
+  int raster;          // tile order: 0 = row-major, G > 0 = bands of G tile rows (b2_gemm_raster.h)
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t cnt) {
@@ -180,7 +181,7 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       int m_blk, n_blk;
-      b2_gemm_tile_coords(tile, g.M / BM, num_n, m_blk, n_blk);
+      b2_gemm_tile_coords(tile, g.M / BM, num_n, g.raster, m_blk, n_blk);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(bar(&empty_bar[stage]), phase ^ 1u);
         mbar_expect_tx(bar(&full_bar[stage]), A_STAGE_BYTES + B_STAGE_BYTES);
@@ -222,7 +223,7 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       int m_blk, n_blk;
-      b2_gemm_tile_coords(tile, g.M / BM, num_n, m_blk, n_blk);
+      b2_gemm_tile_coords(tile, g.M / BM, num_n, g.raster, m_blk, n_blk);
       mbar_wait(bar(&tmem_full_bar[as]), aph);
       asm volatile("tcgen05.fence::after_thread_sync;");
       const size_t row = (size_t)m_blk * BM + q * 32 + lane;
@@ -268,7 +269,7 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 const int slot = i / slice_vec, w = i - slot * slice_vec;
                 const int tl = pend[slot], r = r0 + w / (BN / 8), v8 = w % (BN / 8);
                 int tm, tn;
-                b2_gemm_tile_coords(tl, g.M / BM, num_n, tm, tn);
+                b2_gemm_tile_coords(tl, g.M / BM, num_n, g.raster, tm, tn);
                 offs[u] = ((size_t)tm * BM + r) * g.N + (size_t)tn * BN + v8 * 8;
                 v[u] = mc_ld_reduce_bf16(stage_mc + offs[u]);   // fp32 sum inside the NVSwitch
               }
@@ -289,7 +290,7 @@ b2_k_gemm_allreduce(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 const int slot = i / (BM * (BN / 8)), w = i - slot * (BM * (BN / 8));
                 const int tl = pend[slot], r = w / (BN / 8), v8 = w % (BN / 8);
                 int tm, tn;
-                b2_gemm_tile_coords(tl, g.M / BM, num_n, tm, tn);
+                b2_gemm_tile_coords(tl, g.M / BM, num_n, g.raster, tm, tn);
                 offs[u] = ((size_t)tm * BM + r) * g.N + (size_t)tn * BN + v8 * 8;
                 v[u] = b2_ld_peer16(stage_local + offs[u]);
               }
@@ -329,6 +330,7 @@ extern "C" int b2_gemm_allreduce(B2Comm* c, const void* A, const void* B, void* 
   g.M = M; g.N = N; g.K = K;
   g.out = (__nv_bfloat16*)out;
   g.fused = (c->dev.size > 1) ? 1 : 0;
+  g.raster = c->gemm_raster >= 0 ? c->gemm_raster : B2_GEMM_RASTER_GROUP;
   if (g.fused) {
     if (c->dev.stage_mc == nullptr) {
       b2_set_error("gemm_allreduce: multi-rank call needs a multicast-bound staging segment (NVLS)");

@@ -433,6 +433,7 @@ extern "C" B2Comm* b2_comm_create(int device, int rank, int nranks, B2Seg* ctl, 
   c->nvls_min = 64 * 1024 + 1;
   c->bcast_mc_min = 256 * 1024;
   c->nvls_pipeline = 1;
+  c->gemm_raster = -1;
   c->trace = nullptr;
   c->trace_cap = 0;
   // one 512-thread CTA of the collective kernels (<= 128 registers per thread) fits per SM: grids are
@@ -467,6 +468,7 @@ extern "C" int b2_comm_set_tuning(B2Comm* c, long long ll_max, long long oneshot
 extern "C" int b2_comm_set_option(B2Comm* c, const char* key, long long value) {
   if (strcmp(key, "bcast_mc_min") == 0) c->bcast_mc_min = (size_t)value;
   else if (strcmp(key, "nvls_pipeline") == 0) c->nvls_pipeline = value != 0;
+  else if (strcmp(key, "gemm_raster") == 0) c->gemm_raster = (int)value;
   else if (strcmp(key, "trace_ptr") == 0) c->trace = (unsigned long long*)(uintptr_t)value;
   else if (strcmp(key, "trace_cap") == 0) c->trace_cap = (int)value;
   else { b2_set_error("unknown communicator option '%s'", key); return B2_ERR_BAD_ARG; }
@@ -479,6 +481,7 @@ extern "C" long long b2_comm_get_option(B2Comm* c, const char* key) {
   if (strcmp(key, "sm_count") == 0) return c->sm_count;
   if (strcmp(key, "bcast_mc_min") == 0) return (long long)c->bcast_mc_min;
   if (strcmp(key, "nvls_pipeline") == 0) return c->nvls_pipeline ? 1 : 0;
+  if (strcmp(key, "gemm_raster") == 0) return c->gemm_raster < 0 ? 0 : c->gemm_raster;
   b2_set_error("unknown communicator option '%s'", key);
   return -1;
 }

@@ -54,6 +54,7 @@ struct B2Comm {
   size_t nvls_min;
   size_t bcast_mc_min;          // bcast: root multimem.st from this size on
   int nvls_pipeline;            // software-pipelined NVLS allreduce (default on)
+  int gemm_raster;              // tile order of the persistent GEMM: -1 = compile-time default, 0 = row-major, G = bands
   unsigned long long* trace;    // device buffer for the phase timeline of CTA 0 (scripts/allreduce_phases.py)
   int trace_cap;
   int max_blocks;
