@@ -91,7 +91,7 @@ def main() -> int:
     import mpi4jax_b200 as m
     from mpi4jax_b200 import MPI
     from mpi4jax_b200._src import native
-    from mpi4jax_b200.models import ModelState, ShallowWaterConfig, ShallowWaterModel
+    from mpi4jax_b200.models import ShallowWaterConfig, ShallowWaterModel
     from mpi4jax_b200.utils import ClockSampler, flush_l2, max_over_ranks
 
     comm = MPI.COMM_WORLD
@@ -184,8 +184,8 @@ def main() -> int:
     chunk = min(100, max(1, K - 1))
     model.reset()
     torch.cuda.synchronize()
-    host_ic = ModelState(*[t.detach().cpu().pin_memory() for t in model.state])
-    host_h = torch.empty_like(host_ic.h).pin_memory()
+    host_ic = [t.detach().cpu().pin_memory() for t in (model.h, model.u, model.v)]
+    host_h = torch.empty_like(host_ic[0]).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in host_ic)
     d2h = host_h.numel() * host_h.element_size()
     step_chunk, _ = graph_for(chunk)
@@ -193,7 +193,7 @@ def main() -> int:
     step_tail = graph_for(tail)[0] if tail else None
 
     def e2e_run():
-        model.load_state(host_ic)                   # pinned host -> device (+ frame storage, collective)
+        model.load_initial_condition(*host_ic)      # pinned host -> device: h, u, v (+ frame storage, collective)
         model.step(first_step=True)
         nsnap = 0
         for fn in [step_chunk] * ((K - 1) // chunk) + ([step_tail] if tail else []):
@@ -290,7 +290,7 @@ def main() -> int:
                 "h2d_bytes_per_step": int(h2d // K),
                 "d2h_bytes_per_step": int(d2h * nsnap // K),
                 "e2e_chunk_steps": chunk,
-                "note": ("solve loop through the public API: initial condition H2D from pinned memory once "
+                "note": ("solve loop through the public API: initial condition (h, u, v) H2D from pinned memory once "
                          f"({h2d} B), Euler step + K-1 steps in jit(multistep) chunks, surface-height snapshot "
                          "D2H + host read after every chunk"),
             },

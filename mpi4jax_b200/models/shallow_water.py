@@ -283,6 +283,20 @@ class ShallowWaterModel:
                 self.u.copy_(state[1], non_blocking=True)
                 self.v.copy_(state[2], non_blocking=True)
 
+    def load_initial_condition(self, h, u, v) -> None:
+        """Start from ``(h, u, v)`` (local blocks incl. their halo cells, e.g. in pinned host memory; copied
+        non-blocking): the Adams-Bashforth tendencies start at zero ON THE DEVICE -- nothing but the three
+        prognostic fields crosses PCIe, as in the reference's solve loop, which builds the initial state on
+        the host and lets ``jnp.zeros`` create the rest (examples/shallow_water.py:414-430).  The next call
+        must be ``step(first_step=True)``.  Collective on the native path (frame storage)."""
+        for dst, src in zip((self.h, self.u, self.v), (h, u, v)):
+            dst.copy_(src, non_blocking=True)
+        for t in (self.dh, self.du, self.dv):
+            t.zero_()
+        self.steps_done = 0
+        if self.backend == "native" and self.pipeline == "ca":
+            self._sync_partners()
+
     # the frame storage as four strips per array (rows / columns within 4 cells of the array edge)
     def ext_state(self) -> Optional[dict]:
         if not (self.backend == "native" and self.pipeline == "ca"):
