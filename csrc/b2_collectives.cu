@@ -10,8 +10,11 @@
 // (mpi_ops_common.h:222-306; mpi_xla_bridge_cuda.cpp:99-148, 227-503) is fused
 // into the NVLink pull; there is no host sync and no host staging.
 //
-// Reduction collectives live in b2_reduce.cuh; this file adds the NVLS
-// (multimem) allreduce and the size-based algorithm selection.
+// Reduction collectives live in b2_reduce.cuh; this file adds the kernels that go through the
+// NVSwitch multicast object -- the NVLS allreduce of staged data (b2_k_allreduce_nvls), the
+// in-place allreduce of symmetric tensors (b2_k_allreduce_sym), the multicast bcast
+// (b2_k_bcast_mc), the reduce-to-root (b2_k_reduce_root_nvls) --, the size-based algorithm
+// selection and the grid cap that keeps every launch co-resident (coresident_blocks).
 #include <cstdio>
 #include <cstring>
 

@@ -12,7 +12,7 @@
 // receiver (both derive the lane count from the byte count):
 //
 //   sender lane l          : wait credit(slot)  -> push stripe l into d's slot (NVLink stores)
-//                            -> st.release hdr[slot][l] = {fs+1, tag, nbytes}
+//                            -> hdr[slot][l] = {fs+1, tag, nbytes} as ONE 16-byte release store
 //   receiver lane l        : wait hdr[slot][l].seq == fs+1 -> validate -> copy stripe to the
 //                            user buffer -> last lane to finish releases ack[slot] = fs+1 to s
 //
