@@ -261,14 +261,15 @@ def recv(comm: Comm, template: torch.Tensor, source: int, tag: int,
          status: Optional[Status]) -> torch.Tensor:
     src, t, payload = recv_bytes(comm, source, tag)
     want = template.numel() * template.element_size()
-    if payload.numel() > want:
+    if payload.numel() != want:
+        # same rule as the GPU transport (csrc/b2_p2p.cu: B2_ERR_TRUNCATE): the template fixes the message
+        # size.  (MPI would accept a shorter message; the reference never relies on that, and a
+        # transport-dependent answer is worse than a strict one.)
         raise RuntimeError(
-            f"message truncated: received {payload.numel()} bytes into a {want}-byte buffer")
+            f"message size mismatch: received {payload.numel()} bytes into a {want}-byte buffer "
+            "(send and recv must agree on the size, docs/sharp-bits.md)")
     out = torch.empty(template.shape, dtype=template.dtype)
-    flat = out.reshape(-1).view(torch.uint8)
-    flat[: payload.numel()] = payload
-    if payload.numel() < want:
-        flat[payload.numel():] = _bytes_view(template)[payload.numel():]
+    out.reshape(-1).view(torch.uint8)[:] = payload
     if status is not None:
         status._set(src, t, payload.numel(), template.element_size())
     return out

@@ -237,3 +237,13 @@ def test_any_source_with_tag_matches_behind_the_head(device):
     assert torch.equal(got, b) and status.Get_source() == rank and status.Get_tag() == 2
     got = m.recv(torch.empty_like(a), source=MPI.ANY_SOURCE, tag=1, status=status)
     assert torch.equal(got, a) and status.Get_tag() == 1
+
+
+def test_recv_size_must_match_the_message():
+    """Both transports fix the message size by the receive template (the GPU kernel raises
+    B2_ERR_TRUNCATE and aborts the job, so only the CPU side of the rule is exercised here)."""
+    cpu = torch.device("cpu")
+    m.send(torch.arange(3.0, device=cpu), rank, tag=31)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        m.recv(torch.empty(4, device=cpu), source=rank, tag=31)
+
