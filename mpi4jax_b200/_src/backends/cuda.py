@@ -253,6 +253,24 @@ class NativeComm:
                                          slot, ll_cap, halo_cap, timeout)
         if not self.handle:
             raise MPIError(f"native communicator creation failed: {native.last_error()}")
+        # transport thresholds for THIS world size on THIS GPU model (measured table, optionally overridden by
+        # a tuning file: _src/tuning.py); every rank must end up with the same numbers -- the transport
+        # choice is made independently on each rank from sizes and thresholds only
+        from .. import tuning
+
+        try:
+            gpu_name = torch.cuda.get_device_name(self.device)
+        except Exception:                       # pragma: no cover - a name is only needed to find a table
+            gpu_name = None
+        self.tuning = tuning.thresholds(comm.size, gpu_name)
+        seen = _all_gather_obj(comm, sorted(self.tuning.items()))
+        if any(t != seen[0] for t in seen):
+            raise MPIError(f"the ranks disagree on the transport thresholds (MPI4JAX_B200_TUNING_FILE?): {seen}")
+        if any(self.tuning[k] != tuning.NATIVE_DEFAULTS[k] for k in ("ll_max", "oneshot_max", "nvls_min")):
+            lib.b2_comm_set_tuning(self.handle, self.tuning["ll_max"], self.tuning["oneshot_max"],
+                                   self.tuning["nvls_min"], 0)
+        if self.tuning["bcast_mc_min"] != tuning.NATIVE_DEFAULTS["bcast_mc_min"]:
+            lib.b2_comm_set_option(self.handle, b"bcast_mc_min", self.tuning["bcast_mc_min"])
         self.stage: Optional[_Segment] = None
         self._stage_half = 0
         self._retired: list = []
