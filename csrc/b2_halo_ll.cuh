@@ -1,5 +1,5 @@
 // mpi4jax_b200 -- flag-in-data ("LL") halo transport shared by the stand-alone exchange kernel
-// (b2_halo.cu) and the stencil kernels with the exchange fused in (b2_swe_fused.cu).
+// (b2_halo.cu) and the deep exchange of the communication-avoiding shallow-water step (b2_swe_ca.cu).
 //
 // A halo element travels as ONE 8-byte store {value, flag}; 8-byte stores are atomic, so a reader
 // that sees the flag sees the value: no fence, no separate signal, one NVLink one-way latency.
